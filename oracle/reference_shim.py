@@ -1,0 +1,36 @@
+"""ORACLE (test infrastructure).  Imports the unmodified reference from /root/reference so that
+`oracle/make_golden.py` can run it to produce the fixtures under `tests/golden/`.
+
+This only works in the build container: /root/reference does not exist on the GPU box, and nothing
+in `tests/ -m gpu`, `smoke()` or `bench.py` goes through this module.
+
+Shims: a stub `visualizer_supcon` module (final_main.py:26 imports it and it
+drags in matplotlib/umap), identity `.cuda()` on a CPU-only host (final_main.py:62,64,447-448,675),
+and `torch.cuda.is_available() -> True` so set_model_multiple_adapter binds its return value
+(final_main.py:338-343).
+"""
+from __future__ import annotations
+
+import sys
+import types
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def import_reference():
+    import torch
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    if "visualizer_supcon" not in sys.modules:
+        stub = types.ModuleType("visualizer_supcon")
+        stub.skim_dataloader_by_group = lambda *a, **k: None
+        sys.modules["visualizer_supcon"] = stub
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        torch.cuda.is_available = lambda: True
+        torch.cuda.manual_seed = lambda *a, **k: None
+    import final_main  # noqa: E402  (the reference's module)
+    import demo.util as ref_util  # noqa: E402
+    return final_main, ref_util
