@@ -1,0 +1,112 @@
+"""ctypes binding of libdbmm.so (the C ABI declared in include/dbmm.h).
+
+There is no CPU fallback: importing the package works anywhere (so CLI parsing, data conversion and
+the CPU tests of host logic run without a GPU), but every compute entry point raises if the shared
+library is missing or no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdbmm.so")
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--expt-relaxed-constexpr", "--extended-lambda", "-shared", "-Xcompiler", "-fPIC"]
+SOURCES = ["dbmm_api.cu"]
+
+MAX_H, MAX_C, MAX_G = 128, 16, 16
+PHASE_GEMM1, PHASE_ROWS, PHASE_WGRAD, PHASE_UPDATE, PHASE_ALL = 1, 2, 4, 8, 15
+OP_EVAL, OP_TRAIN, OP_HEAD, OP_SUPCON = 1, 2, 3, 4
+
+
+class DbmmError(RuntimeError):
+    pass
+
+
+class AdapterPtrs(C.Structure):
+    """struct dbmm_adapter"""
+    _fields_ = [("W1", C.c_void_p), ("b1", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+                ("W2", C.c_void_p), ("b2", C.c_void_p)]
+
+
+class BatchStats(C.Structure):
+    """struct dbmm_batch_stats"""
+    _fields_ = [("loss_sum", C.c_void_p), ("counts", C.c_void_p)]
+
+
+def sources_newer_than_lib() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "dbmm.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libdbmm.so next to this file (nvcc cross-compiles without a GPU)."""
+    if not force and not sources_newer_than_lib():
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise DbmmError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+_i32, _i64, _f32, _vp, _sz = C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+_AP = C.POINTER(AdapterPtrs)
+
+SIGNATURES = {
+    "dbmm_abi_version": (C.c_int, []),
+    "dbmm_last_error": (C.c_char_p, []),
+    "dbmm_build_info": (C.c_char_p, []),
+    "dbmm_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
+    "dbmm_normalize_text": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "dbmm_eval_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32, _vp, _f32,
+                                _i64, BatchStats, _vp, _vp, _vp, _sz, _vp]),
+    "dbmm_train_step": (C.c_int, [_i32, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32,
+                                  _vp, _f32, _vp, _vp, _f32, _f32, _f32, _i32, BatchStats, _i64, _vp, _sz, _vp]),
+    "dbmm_train_epoch": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _AP, _AP, _f32,
+                                   _vp, _f32, _vp, _vp, C.POINTER(C.c_float), _f32, _f32, _i32, BatchStats,
+                                   _vp, _sz, _vp]),
+    "dbmm_sgd_step": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _i32, _vp]),
+    "dbmm_group_counts": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i64, BatchStats, _vp, _vp]),
+}
+
+
+def load(require_gpu: bool = True):
+    """Load libdbmm.so; fails loudly (no fallback) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DbmmError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a). There is no CPU fallback for the adapter kernels.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.dbmm_abi_version() != 1:
+            raise DbmmError("libdbmm.so ABI version mismatch")
+        _lib = lib
+    if require_gpu:
+        import torch
+        if not torch.cuda.is_available():
+            raise DbmmError("no CUDA device: the dbmm kernels are sm_100a-only and there is no CPU fallback")
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load(require_gpu=False).dbmm_last_error().decode()
+        raise DbmmError(f"libdbmm error {rc}: {msg}")

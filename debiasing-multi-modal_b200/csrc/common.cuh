@@ -1,0 +1,126 @@
+// Shared helpers for the dbmm kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dbmm.h"
+
+#define DBMM_WARP 32
+#define DBMM_BN_EPS 1e-5f
+#define DBMM_BN_MOMENTUM 0.1f
+
+namespace dbmm {
+
+void set_error(const char* fmt, ...);
+
+#define DBMM_CHECK_ARG(cond, ...)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            dbmm::set_error(__VA_ARGS__);         \
+            return DBMM_ERR_INVALID_ARG;          \
+        }                                         \
+    } while (0)
+
+#define DBMM_CHECK_SHAPE(cond, ...)               \
+    do {                                          \
+        if (!(cond)) {                            \
+            dbmm::set_error(__VA_ARGS__);         \
+            return DBMM_ERR_UNSUPPORTED_SHAPE;    \
+        }                                         \
+    } while (0)
+
+#define DBMM_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            dbmm::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,              \
+                            cudaGetErrorString(e__));                                         \
+            return DBMM_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define DBMM_LAUNCH_CHECK()                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) {                                                             \
+            dbmm::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,          \
+                            cudaGetErrorString(e__));                                         \
+            return DBMM_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Device-side view of one adapter's tensors (copied by value into kernel arguments).
+struct AdapterView {
+    const float* W1;
+    const float* b1;
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    long long* nbt;
+    const float* W2;
+    const float* b2;
+};
+
+static inline AdapterView view_of(const dbmm_adapter* a) {
+    AdapterView v;
+    v.W1 = a->W1; v.b1 = a->b1; v.gamma = a->gamma; v.beta = a->beta;
+    v.running_mean = a->running_mean; v.running_var = a->running_var;
+    v.nbt = (long long*)a->num_batches_tracked; v.W2 = a->W2; v.b2 = a->b2;
+    return v;
+}
+
+// Train-step workspace carve-up (all offsets in bytes, 256-byte aligned).
+struct TrainWs {
+    double* colsum;   // [nad][2][H]   sum a, sum a^2         (zeroed every step)
+    double* dgb;      // [2][H]        dgamma, dbeta          (zeroed every step)
+    float* A;         // [nad][B][H]   pre-BatchNorm activations
+    float* hbuf;      // [B][H]        relu output of the trainable adapter
+    float* dahat;     // [B][H]        dL/d(normalised activation)
+    float* cvec;      // [B]           c = -(dl . l_new) / n^2
+    float* ds;        // [B][C]        dL/ds
+    float* gram;      // [nad][H+1][H+1+C]
+    float* S;         // [H+1+C][H+1]
+    size_t accum_bytes;  // bytes of the zeroed region at the start (colsum + dgb)
+    size_t total;
+};
+
+static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C, int nad) {
+    TrainWs w;
+    char* p = (char*)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_colsum = take(sizeof(double) * nad * 2 * H);
+    size_t o_dgb = take(sizeof(double) * 2 * H);
+    w.accum_bytes = off;
+    size_t o_A = take(sizeof(float) * (size_t)nad * B * H);
+    size_t o_h = take(sizeof(float) * (size_t)B * H);
+    size_t o_da = take(sizeof(float) * (size_t)B * H);
+    size_t o_c = take(sizeof(float) * (size_t)B);
+    size_t o_ds = take(sizeof(float) * (size_t)B * C);
+    size_t o_gram = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));
+    size_t o_S = take(sizeof(float) * (size_t)(H + 1 + C) * (H + 1));
+    w.total = off;
+    w.colsum = (double*)(p + o_colsum); w.dgb = (double*)(p + o_dgb);
+    w.A = (float*)(p + o_A); w.hbuf = (float*)(p + o_h); w.dahat = (float*)(p + o_da);
+    w.cvec = (float*)(p + o_c); w.ds = (float*)(p + o_ds); w.gram = (float*)(p + o_gram); w.S = (float*)(p + o_S);
+    return w;
+}
+
+}  // namespace dbmm

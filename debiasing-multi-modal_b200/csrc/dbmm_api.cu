@@ -1,0 +1,282 @@
+// C ABI of libdbmm.so (see include/dbmm.h).  Host-side argument checking, workspace carving and
+// kernel launches; no allocation, no exceptions, errors via return code + dbmm_last_error().
+#include <stdarg.h>
+
+#include "kernels_simt.cuh"
+
+namespace dbmm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+constexpr int64_t EVAL_CHUNK = 16384;
+
+static int check_dims(int D, int H, int C, int G) {
+    DBMM_CHECK_SHAPE(D >= 4 && D % 4 == 0, "D=%d must be a positive multiple of 4", D);
+    DBMM_CHECK_SHAPE(H >= 1 && H <= DBMM_MAX_H, "H=%d outside [1, %d]", H, DBMM_MAX_H);
+    DBMM_CHECK_SHAPE(C >= 1 && C <= DBMM_MAX_C, "C=%d outside [1, %d]", C, DBMM_MAX_C);
+    DBMM_CHECK_SHAPE(G >= 1 && G <= DBMM_MAX_G, "G=%d outside [1, %d]", G, DBMM_MAX_G);
+    return DBMM_OK;
+}
+
+static int check_adapter(const dbmm_adapter* a, const char* name) {
+    DBMM_CHECK_ARG(a != nullptr, "%s adapter is NULL", name);
+    DBMM_CHECK_ARG(a->W1 && a->b1 && a->gamma && a->beta && a->running_mean && a->running_var &&
+                   a->num_batches_tracked && a->W2 && a->b2, "%s adapter has a NULL tensor", name);
+    return DBMM_OK;
+}
+
+template <bool TRAIN>
+static int launch_rows(const RowsArgs& ra, int nad, int H, int C, cudaStream_t st) {
+    const int CT = C <= 4 ? 4 : 16;
+    const size_t smem = rows_smem_bytes(H, C, nad, CT);
+    DBMM_CHECK_SHAPE(smem <= 227 * 1024, "row kernel needs %zu bytes of shared memory", smem);
+    int grid = ceil_div(ra.N, RK_ROWS);
+    if (grid > 148 * 4) grid = 148 * 4;
+    if (grid < 1) grid = 1;
+#define DBMM_ROWS_CASE(NAD_, CT_)                                                                         \
+    do {                                                                                                  \
+        auto kern = k_rows<TRAIN, NAD_, CT_>;                                                             \
+        DBMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        kern<<<grid, RK_WARPS * 32, smem, st>>>(ra);                                                      \
+    } while (0)
+    if (nad == 1 && CT == 4) DBMM_ROWS_CASE(1, 4);
+    else if (nad == 1) DBMM_ROWS_CASE(1, 16);
+    else if (CT == 4) DBMM_ROWS_CASE(2, 4);
+    else DBMM_ROWS_CASE(2, 16);
+#undef DBMM_ROWS_CASE
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+static int launch_gram(const dbmm_adapter* old_ad, const dbmm_adapter* ad, const float* That, float* gram,
+                       int D, int H, int C, cudaStream_t st) {
+    GramArgs ga;
+    const int nad = old_ad ? 2 : 1;
+    ga.W2[0] = old_ad ? old_ad->W2 : ad->W2; ga.b2[0] = old_ad ? old_ad->b2 : ad->b2;
+    ga.W2[1] = ad->W2; ga.b2[1] = ad->b2;
+    ga.That = That; ga.gram = gram; ga.D = D; ga.H = H; ga.C = C; ga.nad = nad;
+    dim3 grid(ceil_div(H + 1, GT_BM), ceil_div(H + 1 + C, GT_BN), nad);
+    k_gram<<<grid, GT_THREADS, 0, st>>>(ga);
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+static void fill_gemm1(Gemm1Args& g, const float* X, int64_t ldx, const int32_t* idx, int64_t pos0, int B, int D, int H,
+                       const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, double* colsum) {
+    g.X = X; g.ldx = ldx; g.idx = idx; g.pos0 = pos0; g.B = B; g.D = D; g.H = H;
+    g.nad = old_ad ? 2 : 1;
+    g.W1[0] = old_ad ? old_ad->W1 : ad->W1; g.b1[0] = old_ad ? old_ad->b1 : ad->b1;
+    g.W1[1] = ad->W1; g.b1[1] = ad->b1;
+    g.A = A; g.colsum = colsum;
+}
+
+}  // namespace dbmm
+
+using namespace dbmm;
+
+extern "C" {
+
+int dbmm_abi_version(void) { return DBMM_ABI_VERSION; }
+
+const char* dbmm_last_error(void) { return g_err; }
+
+const char* dbmm_build_info(void) {
+    return "libdbmm: sm_100a, fp32 SIMT H-space adapter kernels (round 1), built " __DATE__ " " __TIME__;
+}
+
+size_t dbmm_workspace_bytes(int op, int64_t rows, int D, int H, int C, int n_adapters) {
+    if (rows < 1 || D < 1 || H < 1 || C < 1 || n_adapters < 1 || n_adapters > 2) return 0;
+    if (op == DBMM_OP_TRAIN) return carve_train_ws(nullptr, rows, D, H, C, n_adapters).total;
+    if (op == DBMM_OP_EVAL) {
+        const int64_t chunk = rows < EVAL_CHUNK ? rows : EVAL_CHUNK;
+        return align_up(sizeof(float) * (size_t)n_adapters * (H + 1) * (H + 1 + C), 256) +
+               align_up(sizeof(float) * (size_t)n_adapters * chunk * H, 256);
+    }
+    return 0;
+}
+
+int dbmm_normalize_text(const float* T, float* That, int D, int C, void* stream) {
+    DBMM_CHECK_ARG(T && That, "NULL text matrix");
+    DBMM_CHECK_SHAPE(D >= 1 && C >= 1, "bad text shape [%d, %d]", D, C);
+    k_normalize_text<<<C, 256, 0, (cudaStream_t)stream>>>(T, That, D, C);
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                  int64_t N, int D, int H, int C, int G,
+                  const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                  const float* That, float inv_tau, int64_t batch_size,
+                  dbmm_batch_stats stats, float* logits_out, int32_t* pred_out,
+                  void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_dims(D, H, C, G)) return rc;
+    if (int rc = check_adapter(ad, "eval")) return rc;
+    if (old_ad) if (int rc = check_adapter(old_ad, "old")) return rc;
+    DBMM_CHECK_ARG(X && y && That && ws, "NULL X / y / That / workspace");
+    DBMM_CHECK_ARG(N >= 0 && ldx >= D && batch_size >= 1, "bad N=%lld ldx=%lld batch_size=%lld",
+                   (long long)N, (long long)ldx, (long long)batch_size);
+    if (N == 0) return DBMM_OK;
+    const int nad = old_ad ? 2 : 1;
+    DBMM_CHECK_ARG(dbmm_workspace_bytes(DBMM_OP_EVAL, N, D, H, C, nad) <= ws_bytes, "workspace too small");
+    float* gram = (float*)ws;
+    float* A = (float*)((char*)ws + align_up(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C), 256));
+    if (int rc = launch_gram(old_ad, ad, That, gram, D, H, C, st)) return rc;
+    for (int64_t pos0 = 0; pos0 < N; pos0 += EVAL_CHUNK) {
+        const int B = (int)((N - pos0) < EVAL_CHUNK ? (N - pos0) : EVAL_CHUNK);
+        Gemm1Args g;
+        fill_gemm1(g, X, ldx, idx, pos0, B, D, H, old_ad, ad, A, nullptr);
+        dim3 grid(ceil_div(B, GT_BM), ceil_div(nad * H, GT_BN));
+        k_gemm1<<<grid, GT_THREADS, 0, st>>>(g);
+        DBMM_LAUNCH_CHECK();
+        RowsArgs ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.N = B; ra.pos0 = pos0; ra.idx = idx; ra.y = y; ra.grp = grp; ra.H = H; ra.C = C; ra.G = G;
+        ra.A = A; ra.strideA = (int64_t)B * H; ra.gram = gram; ra.colsum = nullptr; ra.Bg = 0;
+        ra.ad[0] = view_of(old_ad ? old_ad : ad); ra.ad[1] = view_of(ad);
+        ra.w_old = ebd_weight; ra.inv_tau = inv_tau; ra.inv_B = 0.f;
+        ra.logits_out = logits_out; ra.pred_out = pred_out;
+        ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.batch_size = batch_size; ra.slot_fixed = -1;
+        if (int rc = launch_rows<false>(ra, nad, H, C, st)) return rc;
+    }
+    return DBMM_OK;
+}
+
+int dbmm_train_step(int phases,
+                    const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                    int B_local, int64_t B_global, int D, int H, int C, int G,
+                    const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                    const float* That, float inv_tau,
+                    float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
+                    dbmm_batch_stats stats, int64_t slot,
+                    void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_dims(D, H, C, G)) return rc;
+    if (int rc = check_adapter(ad, "trainable")) return rc;
+    if (old_ad) if (int rc = check_adapter(old_ad, "old")) return rc;
+    DBMM_CHECK_ARG(X && y && That && ws && grads, "NULL X / y / That / workspace / grads");
+    DBMM_CHECK_ARG(B_local >= 1 && B_global >= B_local && ldx >= D, "bad B_local=%d B_global=%lld ldx=%lld",
+                   B_local, (long long)B_global, (long long)ldx);
+    // torch.nn.BatchNorm1d in train mode: "Expected more than 1 value per channel when training"
+    DBMM_CHECK_ARG(B_global > 1, "BatchNorm needs more than 1 row per batch in training (got %lld)", (long long)B_global);
+    const int nad = old_ad ? 2 : 1;
+    const int B = B_local;
+    TrainWs w = carve_train_ws(ws, B, D, H, C, nad);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    const size_t np = dbmm_param_count(D, H);
+    const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
+    const int ksplit = B > 4096 ? (B + 4095) / 4096 : 1;
+
+    if (phases & DBMM_PHASE_GEMM1) {
+        DBMM_CUDA(cudaMemsetAsync(ws, 0, w.accum_bytes, st));
+        if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
+        Gemm1Args g;
+        fill_gemm1(g, X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum);
+        dim3 grid(ceil_div(B, GT_BM), ceil_div(nad * H, GT_BN));
+        k_gemm1<<<grid, GT_THREADS, 0, st>>>(g);
+        DBMM_LAUNCH_CHECK();
+    }
+    if (phases & DBMM_PHASE_ROWS) {
+        RowsArgs ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.N = B; ra.pos0 = 0; ra.idx = idx; ra.y = y; ra.grp = grp; ra.H = H; ra.C = C; ra.G = G;
+        ra.A = w.A; ra.strideA = (int64_t)B * H; ra.gram = w.gram; ra.colsum = w.colsum; ra.Bg = B_global;
+        ra.ad[0] = view_of(old_ad ? old_ad : ad); ra.ad[1] = view_of(ad);
+        ra.w_old = ebd_weight; ra.inv_tau = inv_tau; ra.inv_B = 1.0f / (float)B_global;
+        ra.logits_out = nullptr; ra.pred_out = nullptr;
+        ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.batch_size = 1; ra.slot_fixed = slot;
+        ra.hbuf = w.hbuf; ra.dahat = w.dahat; ra.cvec = w.cvec; ra.ds = w.ds; ra.dgb = w.dgb;
+        if (int rc = launch_rows<true>(ra, nad, H, C, st)) return rc;
+    }
+    if (phases & DBMM_PHASE_WGRAD) {
+        WgradArgs wa;
+        wa.X = X; wa.ldx = ldx; wa.idx = idx; wa.B = B; wa.Bg = B_global; wa.D = D; wa.H = H; wa.C = C;
+        wa.A = w.A + (size_t)(nad - 1) * B * H; wa.dahat = w.dahat; wa.hbuf = w.hbuf; wa.cvec = w.cvec; wa.ds = w.ds;
+        wa.colsum = w.colsum + (size_t)(nad - 1) * 2 * H; wa.dgb = w.dgb; wa.gamma = ad->gamma;
+        wa.gW1 = grads + oW1; wa.S = w.S;
+        wa.tiles_w1_m = ceil_div(H, GT_BM); wa.tiles_w1_n = ceil_div(D, GT_BN);
+        wa.tiles_s_m = ceil_div(H + 1 + C, GT_BM); wa.tiles_s_n = ceil_div(H + 1, GT_BN);
+        wa.ksplit = ksplit;
+        if (ksplit > 1) {
+            DBMM_CUDA(cudaMemsetAsync(grads + oW1, 0, sizeof(float) * (size_t)H * D, st));
+            DBMM_CUDA(cudaMemsetAsync(w.S, 0, sizeof(float) * (size_t)(H + 1 + C) * (H + 1), st));
+        }
+        dim3 grid(wa.tiles_w1_m * wa.tiles_w1_n + wa.tiles_s_m * wa.tiles_s_n, ksplit);
+        k_wgrad<<<grid, GT_THREADS, 0, st>>>(wa);
+        DBMM_LAUNCH_CHECK();
+        W2gradArgs w2;
+        w2.W2 = ad->W2; w2.b2 = ad->b2; w2.That = That; w2.S = w.S; w2.dgb = w.dgb;
+        w2.gW2 = grads + oW2; w2.gb2 = grads + ob2; w2.ggamma = grads + og; w2.gbeta = grads + obeta; w2.gb1 = grads + ob1;
+        w2.D = D; w2.H = H; w2.C = C;
+        dim3 grid2(ceil_div(D, GT_BM), ceil_div(H + 1, GT_BN));
+        k_w2grad<<<grid2, GT_THREADS, 0, st>>>(w2);
+        DBMM_LAUNCH_CHECK();
+    }
+    if (phases & DBMM_PHASE_UPDATE) {
+        DBMM_CHECK_ARG(momentum_buf != nullptr, "NULL momentum buffer");
+        SgdArgs sa;
+        sa.p[0] = ad->W1; sa.p[1] = ad->b1; sa.p[2] = ad->gamma; sa.p[3] = ad->beta; sa.p[4] = ad->W2; sa.p[5] = ad->b2;
+        sa.off[0] = oW1; sa.off[1] = ob1; sa.off[2] = og; sa.off[3] = obeta; sa.off[4] = oW2; sa.off[5] = ob2; sa.off[6] = np;
+        sa.g = grads; sa.v = momentum_buf; sa.lr = lr; sa.momentum = momentum; sa.wd = weight_decay; sa.first = first_step;
+        sa.nad = nad; sa.H = H; sa.Bg = B_global; sa.colsum = w.colsum;
+        const dbmm_adapter* a0 = old_ad ? old_ad : ad;
+        sa.rm[0] = a0->running_mean; sa.rv[0] = a0->running_var; sa.nbt[0] = (long long*)a0->num_batches_tracked;
+        sa.rm[1] = ad->running_mean; sa.rv[1] = ad->running_var; sa.nbt[1] = (long long*)ad->num_batches_tracked;
+        k_sgd<<<148, 256, 0, st>>>(sa);
+        DBMM_LAUNCH_CHECK();
+    }
+    return DBMM_OK;
+}
+
+int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                     const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
+                     const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                     const float* That, float inv_tau,
+                     float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
+                     int first_step, dbmm_batch_stats stats,
+                     void* ws, size_t ws_bytes, void* stream) {
+    DBMM_CHECK_ARG(order && lr_host, "NULL order / lr table");
+    DBMM_CHECK_ARG(n_rows >= 1 && batch_size >= 1, "bad n_rows=%lld batch_size=%d", (long long)n_rows, batch_size);
+    const int64_t steps = (n_rows + batch_size - 1) / batch_size;
+    for (int64_t s = 0; s < steps; ++s) {
+        const int64_t p0 = s * batch_size;
+        const int B = (int)((n_rows - p0) < batch_size ? (n_rows - p0) : batch_size);
+        int rc = dbmm_train_step(DBMM_PHASE_ALL, X, ldx, order + p0, y, grp, B, B, D, H, C, G, old_ad, ad, ebd_weight,
+                                 That, inv_tau, grads, momentum_buf, lr_host[s], momentum, weight_decay,
+                                 (first_step && s == 0) ? 1 : 0, stats, s, ws, ws_bytes, stream);
+        if (rc) return rc;
+    }
+    return DBMM_OK;
+}
+
+int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float momentum, float weight_decay,
+                  int first_step, void* stream) {
+    DBMM_CHECK_ARG(p && g && v && n >= 0, "NULL buffer or negative n");
+    if (n == 0) return DBMM_OK;
+    int grid = ceil_div(n, 256 * 4);
+    if (grid > 148 * 8) grid = 148 * 8;
+    k_sgd_flat<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, v, n, lr, momentum, weight_decay, first_step);
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+int dbmm_group_counts(const float* logits, const int32_t* y, const int32_t* grp, int64_t N, int C, int G,
+                      int64_t batch_size, dbmm_batch_stats stats, int32_t* pred_out, void* stream) {
+    DBMM_CHECK_ARG(logits && y && N >= 0 && C >= 1 && G >= 1 && batch_size >= 1, "bad arguments");
+    if (N == 0) return DBMM_OK;
+    int grid = ceil_div(N, 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    k_group_counts<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, y, grp, N, C, G, batch_size, stats.loss_sum,
+                                                           stats.counts, pred_out);
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""Operator layer: torch tensors in, libdbmm.so (C ABI, include/dbmm.h) calls out.
+
+torch is used for device memory and streams only; every arithmetic step of the hot path runs in
+the hand-written kernels.  Each wrapper names the reference code it stands in for.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AdapterPtrs, BatchStats, DbmmError
+
+_workspaces: dict = {}
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _check(t: torch.Tensor, dtype, name: str, contiguous=True):
+    if not t.is_cuda:
+        raise DbmmError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise DbmmError(f"{name} must be {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise DbmmError(f"{name} must be contiguous")
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (the C ABI never allocates)."""
+    key = torch.device(device).index or 0
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+@dataclass
+class AdapterTensors:
+    """Device tensors of one Adapter (final_main.py:160-174); shapes as in the state_dict."""
+    W1: torch.Tensor
+    b1: torch.Tensor
+    gamma: torch.Tensor
+    beta: torch.Tensor
+    running_mean: torch.Tensor
+    running_var: torch.Tensor
+    num_batches_tracked: torch.Tensor
+    W2: torch.Tensor
+    b2: torch.Tensor
+
+    @property
+    def D(self):
+        return self.W1.shape[1]
+
+    @property
+    def H(self):
+        return self.W1.shape[0]
+
+    def validate(self):
+        H, D = self.W1.shape
+        for n, shape, dt in (("W1", (H, D), torch.float32), ("b1", (H,), torch.float32), ("gamma", (H,), torch.float32),
+                             ("beta", (H,), torch.float32), ("running_mean", (H,), torch.float32),
+                             ("running_var", (H,), torch.float32), ("num_batches_tracked", (), torch.int64),
+                             ("W2", (D, H), torch.float32), ("b2", (D,), torch.float32)):
+            t = getattr(self, n)
+            _check(t, dt, n)
+            if tuple(t.shape) != shape:
+                raise DbmmError(f"{n} has shape {tuple(t.shape)}, expected {shape}")
+
+    def ptrs(self) -> AdapterPtrs:
+        self.validate()
+        return AdapterPtrs(*(getattr(self, n).data_ptr() for n in (
+            "W1", "b1", "gamma", "beta", "running_mean", "running_var", "num_batches_tracked", "W2", "b2")))
+
+    @staticmethod
+    def from_numpy(p: dict, device="cuda") -> "AdapterTensors":
+        def f(k):
+            return torch.from_numpy(np.ascontiguousarray(p[k], dtype=np.float32)).to(device)
+        return AdapterTensors(f("W1"), f("b1"), f("gamma"), f("beta"), f("running_mean"), f("running_var"),
+                              torch.tensor(int(p["num_batches_tracked"]), dtype=torch.int64, device=device),
+                              f("W2"), f("b2"))
+
+    def to_numpy(self) -> dict:
+        d = {k: getattr(self, k).detach().cpu().numpy().copy() for k in (
+            "W1", "b1", "gamma", "beta", "running_mean", "running_var", "W2", "b2")}
+        d["num_batches_tracked"] = np.int64(self.num_batches_tracked.item())
+        return d
+
+
+def param_count(D: int, H: int) -> int:
+    return 2 * D * H + 3 * H + D
+
+
+def flat_param_slices(D: int, H: int) -> dict:
+    """Offsets of W1 | b1 | gamma | beta | W2 | b2 inside the flat gradient / momentum buffers."""
+    o, out = 0, {}
+    for k, n in (("W1", H * D), ("b1", H), ("gamma", H), ("beta", H), ("W2", D * H), ("b2", D)):
+        out[k] = slice(o, o + n)
+        o += n
+    return out
+
+
+class BatchStatsBuffers:
+    """Per-batch loss sums and per-group correct/total counters (update_dict, final_main.py:383-391)."""
+
+    def __init__(self, n_slots: int, G: int, device="cuda"):
+        self.n_slots, self.G = n_slots, G
+        self.loss_sum = torch.zeros(n_slots, dtype=torch.float64, device=device)
+        self.counts = torch.zeros(n_slots, 2, G, dtype=torch.int64, device=device)
+
+    def zero_(self):
+        self.loss_sum.zero_()
+        self.counts.zero_()
+
+    def c(self) -> BatchStats:
+        return BatchStats(self.loss_sum.data_ptr(), self.counts.data_ptr())
+
+    def host(self):
+        """One device->host read per epoch (the reference syncs 6-10 times per batch)."""
+        return self.loss_sum.cpu().numpy(), self.counts.cpu().numpy()
+
+
+def normalize_text(T: torch.Tensor) -> torch.Tensor:
+    """final_main.py:77 / 136: text / text.norm(dim=0, keepdim=True), computed once instead of per forward."""
+    lib = _lib.load()
+    _check(T, torch.float32, "T")
+    out = torch.empty_like(T)
+    _lib.check(lib.dbmm_normalize_text(T.data_ptr(), out.data_ptr(), T.shape[0], T.shape[1], _stream_ptr()))
+    return out
+
+
+def _label_args(y, grp, G):
+    _check(y, torch.int32, "y")
+    if grp is not None:
+        _check(grp, torch.int32, "grp")
+    return (G if grp is not None else 1)
+
+
+def eval_fwd(X: torch.Tensor, y: torch.Tensor, grp, ad: AdapterTensors, That: torch.Tensor, inv_tau: float,
+             stats: BatchStatsBuffers | None, batch_size: int, *, idx=None, n_rows=None, old_ad: AdapterTensors | None = None,
+             ebd_weight: float = 0.5, G: int = 4, want_logits=False, want_pred=False):
+    """validate()/validate_zs() forward over many rows (final_main.py:655-803)."""
+    lib = _lib.load()
+    _check(X, torch.float32, "X", contiguous=False)
+    if X.stride(1) != 1:
+        raise DbmmError("X rows must be contiguous")
+    _check(That, torch.float32, "That")
+    D, H, Cn = X.shape[1], ad.H, That.shape[1]
+    if That.shape[0] != D or ad.D != D:
+        raise DbmmError("dimension mismatch between X, adapter and text prompts")
+    G = _label_args(y, grp, G)
+    if idx is not None:
+        _check(idx, torch.int32, "idx")
+    N = int(n_rows if n_rows is not None else (idx.numel() if idx is not None else X.shape[0]))
+    nad = 2 if old_ad is not None else 1
+    nbytes = lib.dbmm_workspace_bytes(_lib.OP_EVAL, max(N, 1), D, H, Cn, nad)
+    ws = workspace(nbytes, X.device)
+    logits = torch.empty((N, Cn), dtype=torch.float32, device=X.device) if want_logits else None
+    pred = torch.empty((N,), dtype=torch.int32, device=X.device) if want_pred else None
+    st = stats.c() if stats is not None else BatchStats(None, None)
+    old_p = old_ad.ptrs() if old_ad is not None else None
+    _lib.check(lib.dbmm_eval_fwd(X.data_ptr(), X.stride(0), _ptr(idx), y.data_ptr(), _ptr(grp), N, D, H, Cn, G,
+                                 C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()), ebd_weight,
+                                 That.data_ptr(), inv_tau, batch_size, st, _ptr(logits), _ptr(pred),
+                                 ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return logits, pred
+
+
+class TrainBuffers:
+    """Flat gradient + momentum of one optimizer (torch.optim.SGD state, demo/util.py:118-136)."""
+
+    def __init__(self, D: int, H: int, device="cuda"):
+        n = param_count(D, H)
+        self.grads = torch.zeros(n, dtype=torch.float32, device=device)
+        self.momentum = torch.zeros(n, dtype=torch.float32, device=device)
+        self.first_step = True
+
+
+def train_step(X, y, grp, ad: AdapterTensors, That, inv_tau, buf: TrainBuffers, lr: float, stats: BatchStatsBuffers,
+               slot: int = 0, *, idx=None, n_rows=None, B_global=None, old_ad=None, ebd_weight=0.5, G=4,
+               momentum=0.9, weight_decay=5e-5, phases=_lib.PHASE_ALL):
+    """One iteration of the train loops' body (final_main.py:455-466 / 610-623)."""
+    lib = _lib.load()
+    _check(X, torch.float32, "X", contiguous=False)
+    _check(That, torch.float32, "That")
+    D, H, Cn = X.shape[1], ad.H, That.shape[1]
+    G = _label_args(y, grp, G)
+    if idx is not None:
+        _check(idx, torch.int32, "idx")
+    B = int(n_rows if n_rows is not None else (idx.numel() if idx is not None else X.shape[0]))
+    Bg = int(B_global if B_global is not None else B)
+    nad = 2 if old_ad is not None else 1
+    ws = workspace(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, B, D, H, Cn, nad), X.device)
+    old_p = old_ad.ptrs() if old_ad is not None else None
+    _lib.check(lib.dbmm_train_step(phases, X.data_ptr(), X.stride(0), _ptr(idx), y.data_ptr(), _ptr(grp), B, Bg,
+                                   D, H, Cn, G, C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()),
+                                   ebd_weight, That.data_ptr(), inv_tau, buf.grads.data_ptr(), buf.momentum.data_ptr(),
+                                   lr, momentum, weight_decay, 1 if buf.first_step else 0, stats.c(), slot,
+                                   ws.data_ptr(), ws.numel(), _stream_ptr()))
+    if phases & _lib.PHASE_UPDATE:
+        buf.first_step = False
+
+
+def train_epoch(X, order: torch.Tensor, batch_size: int, y, grp, ad: AdapterTensors, That, inv_tau, buf: TrainBuffers,
+                lrs, stats: BatchStatsBuffers, *, old_ad=None, ebd_weight=0.5, G=4, momentum=0.9, weight_decay=5e-5):
+    """All steps of one epoch in a single C call (train_one_epoch / train_reg_seq_one_epoch loops)."""
+    lib = _lib.load()
+    _check(X, torch.float32, "X", contiguous=False)
+    _check(order, torch.int32, "order")
+    _check(That, torch.float32, "That")
+    D, H, Cn = X.shape[1], ad.H, That.shape[1]
+    G = _label_args(y, grp, G)
+    n = order.numel()
+    steps = (n + batch_size - 1) // batch_size
+    lrs = np.ascontiguousarray(lrs, dtype=np.float32)
+    if len(lrs) != steps or stats.n_slots < steps:
+        raise DbmmError(f"need {steps} learning rates / stat slots, got {len(lrs)} / {stats.n_slots}")
+    nad = 2 if old_ad is not None else 1
+    ws = workspace(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, min(batch_size, n), D, H, Cn, nad), X.device)
+    old_p = old_ad.ptrs() if old_ad is not None else None
+    _lib.check(lib.dbmm_train_epoch(X.data_ptr(), X.stride(0), order.data_ptr(), n, batch_size, y.data_ptr(), _ptr(grp),
+                                    D, H, Cn, G, C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()),
+                                    ebd_weight, That.data_ptr(), inv_tau, buf.grads.data_ptr(), buf.momentum.data_ptr(),
+                                    lrs.ctypes.data_as(C.POINTER(C.c_float)), momentum, weight_decay,
+                                    1 if buf.first_step else 0, stats.c(), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    buf.first_step = False
+    return steps
+
+
+def sgd_step(p: torch.Tensor, g: torch.Tensor, v: torch.Tensor, lr, momentum=0.9, weight_decay=5e-5, first_step=False):
+    """torch.optim.SGD on flat fp32 buffers (demo/util.py:118-136)."""
+    lib = _lib.load()
+    for t, n in ((p, "p"), (g, "g"), (v, "v")):
+        _check(t, torch.float32, n)
+    _lib.check(lib.dbmm_sgd_step(p.data_ptr(), g.data_ptr(), v.data_ptr(), p.numel(), lr, momentum, weight_decay,
+                                 1 if first_step else 0, _stream_ptr()))
+
+
+def group_counts(logits: torch.Tensor, y, grp, stats: BatchStatsBuffers, batch_size: int, G=4, want_pred=False):
+    """update_dict (final_main.py:383-391) on given logits."""
+    lib = _lib.load()
+    _check(logits, torch.float32, "logits")
+    G = _label_args(y, grp, G)
+    N, Cn = logits.shape
+    pred = torch.empty((N,), dtype=torch.int32, device=logits.device) if want_pred else None
+    _lib.check(lib.dbmm_group_counts(logits.data_ptr(), y.data_ptr(), _ptr(grp), N, Cn, G, batch_size, stats.c(),
+                                     _ptr(pred), _stream_ptr()))
+    return pred

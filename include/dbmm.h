@@ -1,0 +1,160 @@
+/*
+ * dbmm.h -- C ABI of the B200-native adapter hot path (libdbmm.so).
+ *
+ * The reference (Lainshower/debiasing-multi-modal) is pure Python/PyTorch and has no FFI of its own;
+ * the entry points below are the operators its epoch loops call, one C function per operator,
+ * each citing the reference code it replaces (paths are into the reference repository):
+ *
+ *   dbmm_normalize_text   final_main.py:77,136      text / text.norm(dim=0)
+ *   dbmm_eval_fwd         final_main.py:655-719     validate(): eval-mode CustomCLIP/MultipleAdapter forward
+ *                         final_main.py:66-92,121-158 + CE (302) + accuracy/update_dict (383-391)
+ *   dbmm_train_step       final_main.py:455-466, 610-623   forward + CE + backward (+ optim step)
+ *                         demo/util.py:118-136      optim.SGD (momentum 0.9, weight decay)
+ *   dbmm_train_epoch      final_main.py:426-496, 571-653   the per-batch loop of one epoch
+ *   dbmm_sgd_step         demo/util.py:118-136      SGD on a flat buffer (data-parallel path)
+ *   dbmm_group_counts     final_main.py:383-391     update_dict on given logits
+ *   dbmm_logits_ce        final_main.py:757-759,768 raw-embedding cosine logits + CE (zero-shot head)
+ *   dbmm_supcon_fwd_bwd   demo/visualizer_supcon.py:1532-1571  contrastive loss, all anchors at once
+ *
+ * Conventions: all pointers are DEVICE pointers unless the name ends in _host; fp32 storage,
+ * int32 labels/indices, int64 counters.  No allocation, no exceptions: every function returns 0 on
+ * success or a negative dbmm_status and records a message readable via dbmm_last_error()
+ * (thread-local).  The caller owns every buffer including the workspace, whose size comes from
+ * dbmm_workspace_bytes().  Work is enqueued on `stream` (a cudaStream_t passed as void*) and is
+ * asynchronous with respect to the host.
+ */
+#ifndef DBMM_H
+#define DBMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBMM_ABI_VERSION 1
+#define DBMM_MAX_H 128      /* --adapter_feat_dim (final_main.py:241) supported up to 128 */
+#define DBMM_MAX_C 16       /* prompts per head on the adapter path (2 class / 2 spurious / 4 group) */
+#define DBMM_MAX_G 16       /* groups */
+
+typedef enum dbmm_status {
+    DBMM_OK = 0,
+    DBMM_ERR_INVALID_ARG = -1,
+    DBMM_ERR_UNSUPPORTED_SHAPE = -2,
+    DBMM_ERR_WORKSPACE_TOO_SMALL = -3,
+    DBMM_ERR_CUDA = -4
+} dbmm_status;
+
+/* One Adapter (final_main.py:160-174): Linear(D,H) -> BatchNorm1d(H) -> ReLU -> Linear(H,D).
+ * Field order = state_dict order (layers.0.weight, layers.0.bias, layers.1.{weight,bias,
+ * running_mean,running_var,num_batches_tracked}, layers.3.weight, layers.3.bias). */
+typedef struct dbmm_adapter {
+    float* W1;                  /* [H, D] */
+    float* b1;                  /* [H]    */
+    float* gamma;               /* [H]    */
+    float* beta;                /* [H]    */
+    float* running_mean;        /* [H]    */
+    float* running_var;         /* [H]    */
+    int64_t* num_batches_tracked; /* [1]  */
+    float* W2;                  /* [D, H] */
+    float* b2;                  /* [D]    */
+} dbmm_adapter;
+
+/* Trainable tensors in the flat order used by gradients / momentum:  W1 | b1 | gamma | beta | W2 | b2 */
+static inline size_t dbmm_param_count(int D, int H) { return (size_t)2 * D * H + 3 * (size_t)H + D; }
+
+/* phases of one training step (bit mask).  A single-GPU caller passes DBMM_PHASE_ALL; the
+ * data-parallel caller interleaves all-reduces between the phases. */
+#define DBMM_PHASE_GEMM1   1   /* a = x W1^T + b1, per-column sum / sum-of-squares            */
+#define DBMM_PHASE_ROWS    2   /* BN, ReLU, logits, CE, row-wise backward, dgamma/dbeta sums  */
+#define DBMM_PHASE_WGRAD   4   /* dW1, db1, dW2, db2, dgamma, dbeta -> flat gradient          */
+#define DBMM_PHASE_UPDATE  8   /* SGD on the six tensors + BatchNorm running-stat update      */
+#define DBMM_PHASE_ALL     15
+
+/* workspace ops */
+#define DBMM_OP_EVAL   1
+#define DBMM_OP_TRAIN  2
+#define DBMM_OP_HEAD   3
+#define DBMM_OP_SUPCON 4
+
+int dbmm_abi_version(void);
+const char* dbmm_last_error(void);
+const char* dbmm_build_info(void);
+
+/* rows = rows per call (eval: chunk size used internally is bounded, pass N), n_adapters = 1 or 2 */
+size_t dbmm_workspace_bytes(int op, int64_t rows, int D, int H, int C, int n_adapters);
+
+/* That[:, c] = T[:, c] / ||T[:, c]||_2 ;  T, That: [D, C] row-major */
+int dbmm_normalize_text(const float* T, float* That, int D, int C, void* stream);
+
+/* Per-batch accumulators, one slot per batch (train step or eval batch):
+ *   loss_sum[slot]        sum over the batch's rows of -log softmax(logits)[y]
+ *   counts[slot][0][g]    #rows of group g whose argmax == y        (update_dict's `corr`)
+ *   counts[slot][1][g]    #rows of group g                          (update_dict's `n`)
+ * The kernels ADD into the slot; the caller zeroes the arrays before an epoch. */
+typedef struct dbmm_batch_stats {
+    double* loss_sum;           /* [n_slots]          */
+    int64_t* counts;            /* [n_slots][2][G]    */
+} dbmm_batch_stats;
+
+/*
+ * Eval-mode forward over N rows (validate / validate_zs, final_main.py:655-803).
+ *   X[N_total, D] with row stride ldx (floats); idx == NULL -> rows 0..N-1, else rows idx[0..N-1].
+ *   y, grp: labels per DATASET row (indexed like X), int32.  grp may be NULL (G = 0: no group counts).
+ *   old_ad == NULL: CustomCLIP(ad).  old_ad != NULL: MultipleAdapter(old_ad, ad) with ebd_weight.
+ *   That: [D, C] column-normalised prompts; logits = (u . That) * inv_tau.
+ *   batch_size: rows per stats slot (the reference's val/test loader batch size); slot = row / batch_size.
+ *   logits_out [N, C] and pred_out [N] are optional (NULL to skip).
+ */
+int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                  int64_t N, int D, int H, int C, int G,
+                  const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                  const float* That, float inv_tau, int64_t batch_size,
+                  dbmm_batch_stats stats, float* logits_out, int32_t* pred_out,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * One training step on B_local rows (train_one_epoch / train_reg_seq_one_epoch body).
+ *   B_global: rows of the whole (possibly multi-GPU) batch -- BatchNorm statistics and the CE mean use it.
+ *   old_ad != NULL selects the stage-2 MultipleAdapter step: both adapters run batch-stat BatchNorm and
+ *   update their running stats, only `ad` receives gradients (final_main.py:121-140, demo/util.py:128).
+ *   grads: [dbmm_param_count] flat gradient (written by WGRAD, read by UPDATE).
+ *   momentum_buf: [dbmm_param_count]; first_step != 0 initialises it with the gradient (torch SGD).
+ *   stats slot `slot` receives loss / group counts of this batch.
+ */
+int dbmm_train_step(int phases,
+                    const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                    int B_local, int64_t B_global, int D, int H, int C, int G,
+                    const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                    const float* That, float inv_tau,
+                    float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
+                    dbmm_batch_stats stats, int64_t slot,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * A whole single-GPU epoch: ceil(n_rows / batch_size) steps over rows order[0..n_rows-1] (device int32,
+ * the injected batch order), learning rate per step from lr_host[] (HOST array, one entry per step:
+ * adjust_learning_rate + warmup_learning_rate[_reg], demo/util.py:70-115).  `first_step` applies to step 0.
+ * Stats slot s receives step s.  A trailing batch of one row is rejected like torch's BatchNorm1d does.
+ */
+int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                     const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
+                     const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                     const float* That, float inv_tau,
+                     float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
+                     int first_step, dbmm_batch_stats stats,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* torch.optim.SGD on a flat buffer: g += wd*p; v = g (first_step) or momentum*v + g; p -= lr*v */
+int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float momentum, float weight_decay,
+                  int first_step, void* stream);
+
+/* update_dict (final_main.py:383-391) on given logits [N, C]: adds into stats slot row/batch_size. */
+int dbmm_group_counts(const float* logits, const int32_t* y, const int32_t* grp, int64_t N, int C, int G,
+                      int64_t batch_size, dbmm_batch_stats stats, int32_t* pred_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBMM_H */
