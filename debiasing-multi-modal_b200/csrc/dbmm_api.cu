@@ -120,7 +120,8 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
     if (int rc = check_dims(D, H, C, G)) return rc;
     if (int rc = check_adapter(ad, "eval")) return rc;
     if (old_ad) if (int rc = check_adapter(old_ad, "old")) return rc;
-    DBMM_CHECK_ARG(X && y && That && ws, "NULL X / y / That / workspace");
+    DBMM_CHECK_ARG(X && That && ws, "NULL X / That / workspace");
+    DBMM_CHECK_ARG(y || (!stats.loss_sum && !stats.counts), "labels are required when batch statistics are requested");
     DBMM_CHECK_ARG(N >= 0 && ldx >= D && batch_size >= 1, "bad N=%lld ldx=%lld batch_size=%lld",
                    (long long)N, (long long)ldx, (long long)batch_size);
     if (N == 0) return DBMM_OK;

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(RK_WARPS * 32) k_rows(RowsArgs a) {
             if (valid) {
                 const int64_t pos = a.pos0 + r;
                 const int64_t dsrow = a.idx ? (int64_t)a.idx[pos] : pos;
-                const int yv = a.y[dsrow];
+                const int yv = a.y ? a.y[dsrow] : -1;     // y == NULL: logits / argmax only
                 gval = a.grp ? a.grp[dsrow] : 0;
                 const float nn = sqrtf(n2[rb]);
                 const float inv_n = 1.0f / nn;

@@ -1,0 +1,205 @@
+"""Epoch loops of the adapter path with the reference's function names and return values
+(final_main.py:346-379, 426-803), rebuilt around one C call per epoch.
+
+Per epoch the reference issues ~40 tiny ATen kernels and 6-10 host syncs per batch; here an epoch is
+(1) draw the batch order (same RNG protocol as DataLoader), (2) one `dbmm_train_epoch` / `dbmm_eval_fwd`
+call that runs every batch on the device, (3) one device->host read of the per-batch loss sums and
+per-group counters, replayed through the reference's meter arithmetic on the host (metrics.py).
+"""
+from __future__ import annotations
+
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import ops
+from .data import EmbeddingLoader, Subset, resolve
+from .metrics import eval_group_acc, get_y_p, replay_epoch, train_group_acc  # noqa: F401
+from .optim import warmup_learning_rate, warmup_learning_rate_reg
+
+
+def set_seed(seed):
+    """demo/util.py:61-68."""
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+
+
+def _n_groups(loader):
+    base, _ = resolve(loader.dataset)
+    return base.n_groups
+
+
+def _check_criterion(criterion):
+    if criterion is not None and not isinstance(criterion, torch.nn.CrossEntropyLoss):
+        raise NotImplementedError("the fused step implements nn.CrossEntropyLoss() (mean), the reference's criterion")
+
+
+def _order_to_device(base, rows):
+    return torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int32)).to(base.device)
+
+
+def _batch_sizes(n, bs):
+    return [min(bs, n - s) for s in range(0, n, bs)]
+
+
+def _lr_table(n_batches, optimizer, warm_fn):
+    """Learning rate of every step of the epoch: call the per-batch warm-up hook exactly as the reference's
+    loop does and record what it leaves in the optimizer."""
+    lrs = []
+    for idx in range(n_batches):
+        warm_fn(idx)
+        lrs.append(optimizer.param_groups[0]["lr"])
+    return np.asarray(lrs, dtype=np.float64)
+
+
+def _print_batches(opt, print_label, epoch, n_batches, losses_b, accs_b, elapsed, with_groups=None):
+    if not getattr(opt, "watch_batch_results", False):
+        return
+    bt = elapsed / max(n_batches, 1)
+    for idx in range(n_batches):
+        if (idx + 1) % opt.print_freq == 0:
+            line = (f"{print_label}: [{epoch}][{idx + 1}/{n_batches}]\tBT {bt:.3f} ({bt:.3f})\tDT 0.000 (0.000)\t"
+                    f"loss {losses_b[idx][0]:.3f} ({losses_b[idx][1]:.3f})\tAcc@1 {accs_b[idx][0]:.3f} ({accs_b[idx][1]:.3f})")
+            if with_groups is not None:
+                line += f"\tGroup Acc {with_groups[idx]}"
+            print(line)
+    sys.stdout.flush()
+
+
+def _run_train_epoch(opt, loader, classifier, optimizer, target, use_group, warm_fn, get_yp_func, print_label, epoch,
+                     count_metrics=True):
+    classifier.train()
+    base, rows = loader.base_rows(loader.draw_order())
+    n = len(rows)
+    bs = loader.batch_size
+    sizes = _batch_sizes(n, bs)
+    lrs = _lr_table(len(sizes), optimizer, warm_fn)
+    old, ad, w = classifier.kernel_adapters()
+    That = classifier.prompt_matrix(use_group=use_group)
+    labels = base.labels["group"] if use_group else base.labels[target]
+    stats = ops.BatchStatsBuffers(len(sizes), base.n_groups, device=base.device)
+    t0 = time.time()
+    ops.train_epoch(base.x, _order_to_device(base, rows), bs, labels, base.labels["group"], ad, That,
+                    1.0 / classifier.temperature, optimizer.buffers, lrs, stats, old_ad=old, ebd_weight=w,
+                    G=base.n_groups, momentum=optimizer.momentum, weight_decay=optimizer.weight_decay)
+    loss_sum, counts = stats.host()
+    elapsed = time.time() - t0
+    return loss_sum, counts, sizes, elapsed
+
+
+def train_one_epoch(opt, train_loader, classifier, criterion, optimizer, epoch, get_yp_func, target,
+                    print_label='Train', predict_group=True):
+    """Stage-1 / plain adapter epoch (final_main.py:426-496)."""
+    _check_criterion(criterion)
+    loss_sum, counts, sizes, elapsed = _run_train_epoch(
+        opt, train_loader, classifier, optimizer, target, False,
+        lambda idx: warmup_learning_rate(opt, epoch, idx, len(train_loader), optimizer), get_yp_func, print_label, epoch)
+    losses, acc, acc_groups = replay_epoch(loss_sum, counts, sizes, _n_groups(train_loader))
+    group_acc = train_group_acc(acc_groups, get_yp_func)
+    print(f"{print_label}:", str(group_acc))
+    return losses.avg, acc.avg, group_acc
+
+
+def train_reg_seq_one_epoch(opt, train_loader, classifier, criterion, optimizer, epoch, get_yp_func, target,
+                            print_label='Train', predict_group=True, use_group=False):
+    """Stage-2 epoch on the held-out regularisation split (final_main.py:571-653): labels are the group ids when
+    `use_group`, and the warm-up hook is the `_reg` one with the stage-relative epoch."""
+    _check_criterion(criterion)
+    rel_epoch = epoch - opt.epochs_feature_learning
+    loss_sum, counts, sizes, elapsed = _run_train_epoch(
+        opt, train_loader, classifier, optimizer, target, use_group,
+        lambda idx: warmup_learning_rate_reg(opt, rel_epoch, idx, len(train_loader), optimizer),
+        get_yp_func, print_label, epoch)
+    losses, acc, acc_groups = replay_epoch(loss_sum, counts, sizes, _n_groups(train_loader))
+    group_acc = train_group_acc(acc_groups, get_yp_func)
+    print(f"{print_label}:", str(group_acc))
+    return losses.avg, acc.avg, group_acc
+
+
+def train_reg_one_epoch(opt, train_loader1, train_loader2, classifier, criterion, optimizer, epoch, get_yp_func, target,
+                        group_prompt=True, print_label='Train'):
+    """`adapter_reg` epoch (final_main.py:498-569): a pass over the train loader with class prompts, then a pass
+    over the reg loader with group (or class) prompts, one optimizer; only the first pass feeds the meters."""
+    _check_criterion(criterion)
+    n_groups = _n_groups(train_loader1)
+    merged = None
+    for loader, use_group in ((train_loader1, False), (train_loader2, group_prompt)):
+        loss_sum, counts, sizes, _ = _run_train_epoch(
+            opt, loader, classifier, optimizer, target, use_group is True,
+            lambda idx, L=loader: warmup_learning_rate(opt, epoch, idx, len(L), optimizer), get_yp_func, print_label, epoch)
+        if use_group is False:
+            part = (loss_sum, counts, sizes)
+            merged = part if merged is None else (np.concatenate([merged[0], part[0]]),
+                                                  np.concatenate([merged[1], part[1]]), merged[2] + part[2])
+    losses, acc, acc_groups = replay_epoch(merged[0], merged[1], merged[2], n_groups)
+    group_acc = train_group_acc(acc_groups, get_yp_func)
+    print(f"{print_label}:", str(group_acc))
+    return losses.avg, acc.avg, group_acc
+
+
+def _run_eval(loader, classifier, target, spurious_prompts=False):
+    classifier.eval()
+    base, rows = loader.base_rows(loader.draw_order())
+    n, bs = len(rows), loader.batch_size
+    sizes = _batch_sizes(n, bs)
+    old, ad, w = classifier.kernel_adapters()
+    That = classifier.prompt_matrix(spurious=spurious_prompts)
+    stats = ops.BatchStatsBuffers(len(sizes), base.n_groups, device=base.device)
+    contiguous = len(rows) == len(base) and np.array_equal(rows, np.arange(len(base)))
+    idx = None if contiguous else _order_to_device(base, rows)
+    ops.eval_fwd(base.x, base.labels[target], base.labels["group"], ad, That, 1.0 / classifier.temperature, stats, bs,
+                 idx=idx, n_rows=n, old_ad=old, ebd_weight=w, G=base.n_groups)
+    loss_sum, counts = stats.host()
+    return loss_sum, counts, sizes, base.n_groups
+
+
+def validate(opt, val_loader, classifier, criterion, get_yp_func, train_group_ratio, target, print_label='Test'):
+    """Eval-mode pass with group meters and the train-ratio-weighted mean (final_main.py:655-719)."""
+    _check_criterion(criterion)
+    loss_sum, counts, sizes, n_groups = _run_eval(val_loader, classifier, target)
+    losses, acc, acc_groups = replay_epoch(loss_sum, counts, sizes, n_groups)
+    group_acc = eval_group_acc(acc_groups, get_yp_func, train_group_ratio)
+    print(f"{print_label}:", str(group_acc))
+    return losses.avg, acc.avg, group_acc
+
+
+def validate_zs(opt, val_loader, classifier, criterion, get_yp_func, train_group_ratio, target,
+                print_label='Zero-shot Prediction (Test) (Class)'):
+    """Feature-quality check with class or spurious prompts (final_main.py:725-803)."""
+    _check_criterion(criterion)
+    if opt.tl_method == "linear_probing":
+        raise NotImplementedError("linear_probing is not on the B200 path yet (SURVEY.md section 8 row a4)")
+    if target not in ("class", "spurious"):
+        raise ValueError(target)
+    loss_sum, counts, sizes, n_groups = _run_eval(val_loader, classifier, target, spurious_prompts=(target == "spurious"))
+    losses, acc, acc_groups = replay_epoch(loss_sum, counts, sizes, n_groups)
+    group_acc = eval_group_acc(acc_groups, get_yp_func, train_group_ratio)
+    print(f"{print_label}:", str(group_acc))
+    return losses.avg, acc.avg, group_acc
+
+
+def balance_val(val_loader, opt, print_procedure=False):
+    """Per-epoch group-balanced resampling of the regularisation split (final_main.py:346-379): each group's
+    positions are shuffled with the GLOBAL numpy RNG, cut to the smallest group, interleaved g0,g1,g2,g3,...;
+    the loader is sequential with batch size min(batch_size_reg, #balanced)."""
+    sub_dataset = val_loader.dataset
+    n_groups = sub_dataset.dataset.n_groups
+    groups_here = sub_dataset.dataset.group_array[sub_dataset.indices]
+    per_group = [np.where(groups_here == g)[0] for g in range(n_groups)]
+    smallest = min(len(ix) for ix in per_group)
+    for i, ix in enumerate(per_group):
+        np.random.shuffle(ix)
+        if print_procedure:
+            print(f"(Group {i}): ", len(ix), ix[:10])
+        per_group[i] = ix[:smallest]
+    balanced_indices = np.stack(per_group, axis=1).reshape(-1)
+    if print_procedure:
+        print(f"Balanced sample indices : {len(balanced_indices)} per epoch ({balanced_indices[:16]})")
+    bs = opt.batch_size_reg if opt.batch_size_reg <= len(balanced_indices) else len(balanced_indices)
+    return EmbeddingLoader(Subset(sub_dataset, balanced_indices), shuffle=False, batch_size=bs)

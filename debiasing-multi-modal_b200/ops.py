@@ -139,7 +139,8 @@ def normalize_text(T: torch.Tensor) -> torch.Tensor:
 
 
 def _label_args(y, grp, G):
-    _check(y, torch.int32, "y")
+    if y is not None:
+        _check(y, torch.int32, "y")
     if grp is not None:
         _check(grp, torch.int32, "grp")
     return (G if grp is not None else 1)
@@ -168,7 +169,7 @@ def eval_fwd(X: torch.Tensor, y: torch.Tensor, grp, ad: AdapterTensors, That: to
     pred = torch.empty((N,), dtype=torch.int32, device=X.device) if want_pred else None
     st = stats.c() if stats is not None else BatchStats(None, None)
     old_p = old_ad.ptrs() if old_ad is not None else None
-    _lib.check(lib.dbmm_eval_fwd(X.data_ptr(), X.stride(0), _ptr(idx), y.data_ptr(), _ptr(grp), N, D, H, Cn, G,
+    _lib.check(lib.dbmm_eval_fwd(X.data_ptr(), X.stride(0), _ptr(idx), _ptr(y), _ptr(grp), N, D, H, Cn, G,
                                  C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()), ebd_weight,
                                  That.data_ptr(), inv_tau, batch_size, st, _ptr(logits), _ptr(pred),
                                  ws.data_ptr(), ws.numel(), _stream_ptr()))

@@ -101,7 +101,8 @@ typedef struct dbmm_batch_stats {
 /*
  * Eval-mode forward over N rows (validate / validate_zs, final_main.py:655-803).
  *   X[N_total, D] with row stride ldx (floats); idx == NULL -> rows 0..N-1, else rows idx[0..N-1].
- *   y, grp: labels per DATASET row (indexed like X), int32.  grp may be NULL (G = 0: no group counts).
+ *   y, grp: labels per DATASET row (indexed like X), int32.  grp may be NULL (all rows count as group 0,
+ *   pass G = 1); y may be NULL when no statistics are requested (logits / argmax only).
  *   old_ad == NULL: CustomCLIP(ad).  old_ad != NULL: MultipleAdapter(old_ad, ad) with ebd_weight.
  *   That: [D, C] column-normalised prompts; logits = (u . That) * inv_tau.
  *   batch_size: rows per stats slot (the reference's val/test loader batch size); slot = row / batch_size.

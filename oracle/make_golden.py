@@ -303,6 +303,87 @@ def gen_checkpoint_layout(fm, ru):
     print("checkpoint_layout.json:", len(layout), "keys")
 
 
+# ------------------------------------------------------------------------------------------------------
+# whole-run fixtures: the reference's train_all_epochs on synthetic files, same seed as the test will use
+# ------------------------------------------------------------------------------------------------------
+E2E_CASES = {
+    "waterbirds_small": dict(
+        synth=dict(name="waterbirds", dim=1024, seed=1234, scale=0.5, k=0.085, k_text=0.5, text_noise=0.02),
+        argv=["--dataset", "waterbirds", "--tl_method", "adapter_reg_seq_alter", "--add_adapter", "--warm_reg",
+              "--batch_size", "256", "--batch_size_reg", "64", "--learning_rate", "1.0", "--learning_rate_reg", "1.0",
+              "--epochs", "12", "--epochs_feature_learning", "6", "--lr_decay_rate", "0.1", "--lr_decay_epochs", "10,11",
+              "--train_target", "class", "--save_results", "--random_seed", "42"]),
+    "celeba_small_balval": dict(
+        synth=dict(name="celeba", dim=1024, seed=4321, k=0.085, k_text=0.5, text_noise=0.02,
+                   group_sizes=[[1400, 1300, 450, 60], [340, 330, 115, 24], [390, 300, 100, 24]]),
+        argv=["--dataset", "celeba", "--tl_method", "adapter_reg_seq_alter", "--add_adapter", "--warm_reg", "--balance_val",
+              "--batch_size", "512", "--batch_size_reg", "4", "--learning_rate", "0.1", "--learning_rate_reg", "1.0",
+              "--epochs", "10", "--epochs_feature_learning", "5", "--lr_decay_rate", "0.1", "--lr_decay_epochs", "8,9",
+              "--train_target", "class", "--save_results", "--random_seed", "32"]),
+}
+
+
+def e2e_paths_argv(case, root):
+    ds = synth.make_dataset(**case["synth"])
+    paths = synth.write_reference_files(ds, root)
+    argv = list(case["argv"])
+    for k, v in paths.items():
+        argv += [f"--{k}", v]
+    return ds, argv
+
+
+def gen_e2e(fm, ru):
+    import io
+    import contextlib
+    out = {}
+    for name, case in E2E_CASES.items():
+        root = tempfile.mkdtemp(prefix=f"dbmm_e2e_{name}_")
+        ds, argv = e2e_paths_argv(case, root)
+        old_argv = sys.argv
+        sys.argv = ["final_main.py"] + argv
+        try:
+            opt = fm.parse_option()
+        finally:
+            sys.argv = old_argv
+        # record what train_all_epochs computes per epoch by wrapping the reference's own epoch functions
+        log = dict(train=[], val_test=[], zs=[])
+        t1, t2, tv, tz = fm.train_one_epoch, fm.train_reg_seq_one_epoch, fm.validate, fm.validate_zs
+
+        def wrap(fn, key):
+            def inner(*a, **k):
+                r = fn(*a, **k)
+                log[key].append(dict(label=k.get("print_label", ""), loss=float(r[0]), acc=float(r[1]),
+                                     group_acc={kk: float(vv) for kk, vv in r[2].items()}))
+                return r
+            return inner
+        fm.train_one_epoch, fm.train_reg_seq_one_epoch = wrap(t1, "train"), wrap(t2, "train")
+        fm.validate, fm.validate_zs = wrap(tv, "val_test"), wrap(tz, "zs")
+        buf = io.StringIO()
+        try:
+            with contextlib.redirect_stdout(buf):
+                res = fm.train_all_epochs(opt)
+        finally:
+            fm.train_one_epoch, fm.train_reg_seq_one_epoch, fm.validate, fm.validate_zs = t1, t2, tv, tz
+        stdout = buf.getvalue()
+        best_epoch = int([ln for ln in stdout.splitlines() if ln.startswith("best epoch")][0].split(":")[1])
+        folder = os.path.dirname(opt.image_embedding_dir).replace("data", "results")
+        files = sorted(os.listdir(folder))
+        sd = torch.load(os.path.join(folder, [f for f in files if f.endswith(".pth")][0]), map_location="cpu")
+        results_json = json.load(open(os.path.join(folder, [f for f in files if f.endswith(".json")][0])))
+        out[name] = dict(
+            synth=case["synth"], argv=case["argv"], best_epoch=best_epoch, files=files,
+            train=log["train"], val_test=log["val_test"], zs=log["zs"],
+            final={k: float(v) for part in res[0] for k, v in part.items()} and
+                  [{k: float(v) for k, v in part.items()} for part in res[0]],
+            state_dict_keys=list(sd.keys()),
+            state_dict_abs_sums={k: float(v.double().abs().sum()) for k, v in sd.items()},
+            results_json=results_json)
+        print(name, "best epoch", best_epoch, "val/test dicts", len(log["val_test"]), files)
+    with open(os.path.join(GOLD, "e2e_cases.json"), "w") as f:
+        json.dump(out, f)
+    print("e2e_cases.json written")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
@@ -311,7 +392,7 @@ def main():
     fm, ru = import_reference()
     torch.set_num_threads(8)
     todo = dict(kernels=gen_kernels, metrics=gen_metrics, schedule=gen_schedule, sampling=gen_sampling,
-                supcon=gen_supcon, layout=gen_checkpoint_layout)
+                supcon=gen_supcon, layout=gen_checkpoint_layout, e2e=gen_e2e)
     for k, fn in todo.items():
         if a.only in ("all", k):
             fn(fm, ru)
@@ -319,3 +400,5 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+

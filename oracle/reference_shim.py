@@ -31,6 +31,14 @@ def import_reference():
         torch.nn.Module.cuda = lambda self, *a, **k: self
         torch.cuda.is_available = lambda: True
         torch.cuda.manual_seed = lambda *a, **k: None
+    # pandas >= 3 hands out read-only `.values` (copy-on-write); data/celeba_embeddings.py:35-36 assigns
+    # into them in place (written for pandas 1.x).  Give the reference writable copies.
+    import numpy as np
+    import pandas as pd
+    if not getattr(pd.Series, "_dbmm_writable_values", False):
+        _orig_values = pd.Series.values.fget
+        pd.Series.values = property(lambda self: np.array(_orig_values(self)))
+        pd.Series._dbmm_writable_values = True
     import final_main  # noqa: E402  (the reference's module)
     import demo.util as ref_util  # noqa: E402
     return final_main, ref_util

@@ -1,0 +1,162 @@
+"""CPU-only checks of the host side of the drop-in: CLI surface, schedules, sampling, metric replay, the
+DataLoader-compatible RNG protocol, and the C-ABI library's exported symbols.  No compute calls."""
+import ctypes
+import json
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import dbmm
+from dbmm import cli, data, engine, metrics, optim
+
+
+def test_cli_defaults_match_reference_surface():
+    opt = cli.parse_option([])
+    expect = dict(print_freq=10, save_freq=50, batch_size=128, batch_size_reg=128, num_workers=16, epochs=10,
+                  learning_rate=0.1, learning_rate_reg=1e-3, lr_decay_rate=1, weight_decay=5e-5, momentum=0.9,
+                  model="resnet50", dataset="waterbirds", cosine=False, warm=False, warm_reg=False, train_target="class",
+                  tl_method="linear_probing", balance_val=False, resample_ce=False, use_cls_prompt_in_reg=False,
+                  add_adapter=False, init_near_identity=False, epochs_feature_learning=None, continue_from_best=False,
+                  adapter_feat_dim=128, zs_temperature=0.01, watch_batch_results=False, save_results=False, random_seed=42)
+    for k, v in expect.items():
+        assert getattr(opt, k) == v, k
+    assert opt.lr_decay_epochs == [60, 75, 90] and opt.n_cls == 2
+    opt = cli.parse_option(["--dataset", "celeba", "--warm_reg", "--learning_rate_reg", "1.0", "--tl_method",
+                            "adapter_reg_seq_alter", "--epochs", "65", "--epochs_feature_learning", "40"])
+    assert (opt.warmup_from_reg, opt.warm_epochs_reg, opt.warmup_to_reg) == (0.01, 2, 1.0)
+    with pytest.raises(AssertionError):
+        cli.parse_option(["--tl_method", "adapter", "--add_adapter"])
+
+
+def test_result_file_names():
+    opt = cli.parse_option(["--tl_method", "adapter_reg_seq_alter", "--add_adapter", "--batch_size", "1024",
+                            "--batch_size_reg", "256", "--learning_rate", "1.0", "--learning_rate_reg", "1.0",
+                            "--image_embedding_dir", "/x/data/embeddings_unnormalized/waterbirds/RN50/clip.json",
+                            "--text_embedding_dir", "/x/data/embeddings_unnormalized/waterbirds/clip_class.json"])
+    folder, stem = cli.result_file_stem(opt)
+    # the shipped artefact of the reference: trained_model/im_clip_t_clip_class_..._MA+rn.{json,pth}
+    assert stem == "im_clip_t_clip_class_tl_adapter_reg_seq_alter_t_class_lr_1.0_bs_1024_lrr1.0_bsr_256_MA+rn"
+    assert folder == "/x/results/embeddings_unnormalized/waterbirds/RN50"
+
+
+def test_schedules_match_reference(golden_dir):
+    gold = json.load(open(os.path.join(golden_dir, "schedule_cases.json")))
+    for name, c in gold.items():
+        cfg = c["config"]
+        argv = ["--dataset", cfg["dataset"], "--tl_method", "adapter_reg_seq_alter", "--warm_reg",
+                "--learning_rate", str(cfg["learning_rate"]), "--learning_rate_reg", str(cfg["learning_rate_reg"]),
+                "--epochs", str(cfg["epochs"]), "--epochs_feature_learning", str(cfg["epochs_feature_learning"]),
+                "--lr_decay_rate", str(cfg["lr_decay_rate"]), "--lr_decay_epochs", ",".join(map(str, cfg["lr_decay_epochs"]))]
+        opt = cli.parse_option(argv)
+        o1 = types.SimpleNamespace(param_groups=[{"lr": None}]); o2 = types.SimpleNamespace(param_groups=[{"lr": None}])
+        for e, per_batch in enumerate(c["lrs"], start=1):
+            optim.adjust_learning_rate(opt, o1, e)
+            if e <= opt.epochs_feature_learning:
+                got = engine._lr_table(cfg["n_train"], o1, lambda i: optim.warmup_learning_rate(opt, e, i, cfg["n_train"], o1))
+            else:
+                optim.adjust_learning_rate_reg(opt, o2, e)
+                got = engine._lr_table(cfg["n_reg"], o2, lambda i: optim.warmup_learning_rate_reg(
+                    opt, e - opt.epochs_feature_learning, i, cfg["n_reg"], o2))
+            assert list(got) == per_batch, (name, e)
+
+
+def test_sampling_matches_reference(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "sampling_cases.npz"))
+    for name in ("waterbirds", "celeba"):
+        g = gold[f"{name}/group_array"].astype(np.int64)
+        ds = types.SimpleNamespace(group_array=g, n_groups=4)
+        reg, val = data.stratified_split_dataset(ds)
+        assert np.array_equal(reg.indices, gold[f"{name}/reg_idx"]) and np.array_equal(val.indices, gold[f"{name}/val_idx"])
+        loader = data.EmbeddingLoader(reg, batch_size=7, shuffle=True)
+        np.random.seed(42)
+        for bsr in (4, 256, 100000):
+            opt = types.SimpleNamespace(batch_size_reg=bsr)
+            for ep in range(3):
+                bl = engine.balance_val(loader, opt)
+                assert np.array_equal(bl.dataset.indices, gold[f"{name}/balanced_bsr{bsr}_ep{ep}"])
+                assert bl.batch_size == gold[f"{name}/balanced_bsr{bsr}_ep{ep}_bs"]
+                assert bl.shuffle is False
+
+
+def test_metric_replay_matches_reference(golden_dir):
+    from functools import partial
+    gold = json.load(open(os.path.join(golden_dir, "metrics_cases.json")))
+    get_yp = partial(metrics.get_y_p, n_places=2)
+    for name, c in gold.items():
+        loss_sum, counts, sizes = [], [], []
+        for b in c["batches"]:
+            logits = np.array(b["logits"], np.float64); y = np.array(b["y"]); g = np.array(b["g"])
+            m = logits.max(1, keepdims=True)
+            lse = np.log(np.exp(logits - m).sum(1)) + m[:, 0]
+            loss_sum.append((lse - logits[np.arange(len(y)), y]).sum())
+            corr = logits.argmax(1) == y
+            counts.append([[int((corr & (g == k)).sum()) for k in range(4)], [int((g == k).sum()) for k in range(4)]])
+            sizes.append(len(y))
+        losses, acc, groups = metrics.replay_epoch(np.array(loss_sum), np.array(counts), sizes, 4)
+        ga = metrics.eval_group_acc(groups, get_yp, torch.tensor(c["train_group_ratio"]))
+        assert acc.avg == pytest.approx(c["acc_avg"], abs=1e-12)
+        assert losses.avg == pytest.approx(c["loss_avg"], rel=1e-5)
+        assert list(ga) == metrics.new_order_for_print
+        for k, v in c["group_acc"].items():
+            assert float(ga[k]) == v, (name, k)     # identical after the 4-decimal rounding
+
+
+def test_order_protocol_matches_torch_dataloader():
+    """EmbeddingLoader.draw_order consumes the global RNG like DataLoader(+RandomSampler) does, including
+    interleaved sequential loaders, so the same --random_seed visits the same batches as the reference."""
+    from torch.utils.data import DataLoader, TensorDataset
+    n = 1237
+    ds = TensorDataset(torch.arange(n))
+    fake = types.SimpleNamespace(__len__=lambda: n)
+
+    class L(list):
+        pass
+    torch.manual_seed(42)
+    ref_orders = []
+    for ep in range(3):
+        ref_orders.append(torch.cat([b[0] for b in DataLoader(ds, batch_size=100, shuffle=True, num_workers=0)]).numpy())
+        for _ in DataLoader(ds, batch_size=500, shuffle=False):      # a validation pass in between
+            pass
+    ref_after = torch.rand(1).item()
+    torch.manual_seed(42)
+    tr = data.EmbeddingLoader(list(range(n)), 100, shuffle=True)
+    va = data.EmbeddingLoader(list(range(n)), 500, shuffle=False)
+    for ep in range(3):
+        assert np.array_equal(tr.draw_order(), ref_orders[ep])
+        assert np.array_equal(va.draw_order(), np.arange(n))
+    assert torch.rand(1).item() == ref_after
+
+
+def test_library_exports_every_declared_symbol():
+    from dbmm import _lib
+    header = open(os.path.join(os.path.dirname(_lib.INCLUDE + "/"), "dbmm.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|size_t|const char\*)\s+(dbmm_\w+)\s*\(", header, flags=re.M))
+    assert {"dbmm_eval_fwd", "dbmm_train_step", "dbmm_train_epoch", "dbmm_sgd_step", "dbmm_group_counts"} <= declared
+    assert os.path.exists(_lib.LIB_PATH), "libdbmm.so not built (run __graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert set(_lib.SIGNATURES) == declared
+    lib.dbmm_abi_version.restype = ctypes.c_int
+    assert lib.dbmm_abi_version() == 1
+
+
+def test_product_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dbmm._lib import DbmmError
+    with pytest.raises(DbmmError):
+        dbmm.ops.normalize_text(torch.zeros(8, 2))
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.abspath(dbmm.__file__))
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
