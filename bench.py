@@ -1,0 +1,385 @@
+"""bench.py -- adapter-train embeddings/sec on CelebA-shaped synthetic RN50 embeddings (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one stage-1 training epoch of the reference (train_one_epoch, final_main.py:426-496) over the
+GPU-resident 162,770 x 1024 fp32 embedding matrix at batch size 1024 (159 SGD steps) -- 667 MB per pass, larger
+than the 126 MB L2, so consecutive timed steps cannot reuse cached inputs.  N > 1 (launched by torchrun, one
+process per GPU): data parallel, weak scaling -- every rank holds its own 162,770-row shard and contributes 1024
+rows to each global batch of N x 1024; BatchNorm statistics and gradients are all-reduced over NCCL.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: `roofline` (dominant kernel, live CUDA-event
+timing), `cpu_baseline` (oracle port of the reference step on the host cores), `e2e` (host buffers, H2D/D2H
+inside the timed region), `eval` (validate()-style forward throughput, the HBM-bound half of the path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRAIN, D, H, C, G = 162770, 1024, 128, 2, 4
+BATCH = 1024
+TRAIN_GROUPS = (71629, 66874, 22880, 1387)
+ALG_BYTES_PER_EMB = 4096                       # one fp32 row of X
+ALG_FLOP_TRAIN = 1.319e6                       # fwd 528,384 + bwd 786,432 + logits grad
+ALG_FLOP_EVAL = 528384
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tc_burst=p["bf16_tflops"], tc_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+def synth_rows(n, seed, dim=D):
+    """CelebA-shaped rows: x = base + k*mu_group + eps, rounded through fp16."""
+    rng = np.random.default_rng(seed)
+    base = rng.standard_normal(dim).astype(np.float32)
+    mu = rng.standard_normal((4, dim)).astype(np.float32)
+    pr = np.array(TRAIN_GROUPS, np.float64) / sum(TRAIN_GROUPS)
+    g = rng.choice(4, size=n, p=pr).astype(np.int32)
+    x = np.empty((n, dim), np.float32)
+    for s in range(0, n, 16384):
+        e = min(n, s + 16384)
+        x[s:e] = base + 0.25 * mu[g[s:e]] + rng.standard_normal((e - s, dim), dtype=np.float32)
+    x = x.astype(np.float16).astype(np.float32)
+    T = np.stack([base + mu[[0, 1]].mean(0), base + mu[[2, 3]].mean(0)], 1).astype(np.float32)
+    return x, (g // 2).astype(np.int32), g, T
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.samples, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].startswith("Active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def cpu_reference_step(rows_x, rows_y, rows_g, T, n_sgd_steps):
+    """The reference's step body (oracle port, torch CPU, all host threads) on a bounded sample."""
+    from oracle import ref_port
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    return ref_port.time_train_steps(rows_x, rows_y.astype(np.int64), rows_g.astype(np.int64), T, H, BATCH, n_sgd_steps)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sgd = 12                                  # bounded sample per step: 12 SGD steps of 1024 rows
+    x, y, g, T = synth_rows(n_sgd * BATCH, seed=1234)
+    cpu_reference_step(x, y, g, T, 2)           # page-in / thread pool warm-up
+    for _ in range(args.warmup):
+        cpu_reference_step(x, y, g, T, n_sgd)
+    t0 = time.perf_counter()
+    rows = 0
+    for _ in range(args.steps):
+        r = cpu_reference_step(x, y, g, T, n_sgd)
+        rows += r["rows"]
+    dt = time.perf_counter() - t0
+    val = rows / dt
+    sample = f"{n_sgd} SGD steps of {BATCH} rows per bench step (reference step body, tensors pre-loaded, torch CPU)"
+    print(json.dumps({
+        "impl": "reference", "metric": "adapter-train embeddings/sec", "value": val, "unit": "embeddings/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "embeddings/s", "cores": r["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": "celeba-shaped synthetic CLIP-RN50 embeddings, stage-1 adapter training epoch "
+                        "(train_one_epoch: Linear-BN-ReLU-Linear adapter, L2-norm, cosine logits/0.01 vs 2 class prompts, "
+                        "CE, SGD momentum 0.9 wd 5e-5, per-group counters)",
+            "rows_per_gpu": N_TRAIN, "dim": D, "adapter_feat_dim": H, "classes": C, "groups": G,
+            "batch_size_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "sgd_steps_per_step": (N_TRAIN + BATCH - 1) // BATCH,
+            "parallelism": f"dp{n_gpus}", "l2_policy": "inputs (667 MB per step) larger than L2 (126 MB)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dbmm", choices=["dbmm", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import dbmm
+    from dbmm import ops, parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    P = peaks()
+
+    # ---- data: this rank's shard, resident in HBM; pinned host copy for the e2e leg
+    x_np, y_np, g_np, T_np = synth_rows(N_TRAIN, seed=1234 + rank)
+    if world > 1:
+        T_np = synth_rows(8, seed=1234)[3] if rank else T_np        # same prompts everywhere
+    X = torch.from_numpy(x_np).to(dev)
+    y = torch.from_numpy(y_np).to(dev)
+    g = torch.from_numpy(g_np).to(dev)
+    That = ops.normalize_text(torch.from_numpy(T_np).to(dev))
+    steps_per_epoch = (N_TRAIN + BATCH - 1) // BATCH
+
+    def fresh_model():
+        torch.manual_seed(42)
+        from dbmm.modules import Adapter
+        a = Adapter(D, H).to(dev)
+        return a, a.tensors()
+
+    mod, ad = fresh_model()
+    buf = ops.TrainBuffers(D, H, device=dev)
+    stats = ops.BatchStatsBuffers(steps_per_epoch, G, device=dev)
+    lrs = np.full(steps_per_epoch, 0.1, np.float32)      # CelebA setting of the reference: lr 0.1
+    gen = torch.Generator().manual_seed(7)
+    orders = [torch.randperm(N_TRAIN, generator=gen).to(torch.int32).to(dev) for _ in range(4)]
+    dp = parallel.DataParallelTrainer() if world > 1 else None
+
+    def train_epoch(i):
+        stats.zero_()
+        if world == 1:
+            ops.train_epoch(X, orders[i % 4], BATCH, y, g, ad, That, 100.0, buf, lrs, stats, G=G)
+        else:
+            # global batch = concatenation of every rank's 1024 local rows; this rank processes its own rows and the
+            # kernels are told B_global = world * B_local (BatchNorm / CE mean over the global batch)
+            order = orders[i % 4]
+            for s in range(steps_per_epoch):
+                idx = order[s * BATCH:(s + 1) * BATCH]
+                dp_step(idx, float(lrs[s]), s)
+
+    def dp_step(idx, lr, slot):
+        Bg = idx.numel() * world       # every rank's batch has the same size at every step (same N_TRAIN, same BATCH)
+        kw = dict(idx=idx, B_global=Bg, G=G)
+        ops.train_step(X, y, g, ad, That, 100.0, buf, lr, stats, slot, phases=1, **kw)
+        colsum, dgb = parallel.accum_views(ops.workspace(0, dev), H, 1)
+        dist.all_reduce(colsum)
+        ops.train_step(X, y, g, ad, That, 100.0, buf, lr, stats, slot, phases=2, **kw)
+        dist.all_reduce(dgb)
+        ops.train_step(X, y, g, ad, That, 100.0, buf, lr, stats, slot, phases=4, **kw)
+        dist.all_reduce(buf.grads)
+        ops.train_step(X, y, g, ad, That, 100.0, buf, lr, stats, slot, phases=8, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up epochs, then exactly K timed epochs
+    for i in range(args.warmup):
+        train_epoch(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        train_epoch(args.warmup + i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    loss_sum, counts = stats.host()
+    final_loss = float(loss_sum.sum() / N_TRAIN)
+    value = world * N_TRAIN * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+
+    out = None
+    if rank == 0:
+        out = {"metric": "adapter-train embeddings/sec", "value": value, "unit": "embeddings/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": workload_config(world), "clocks": clocks,
+               "us_per_sgd_step": 1e3 * ms_per_step / steps_per_epoch, "final_epoch_mean_loss": final_loss,
+               "gpu_launches": args.steps * steps_per_epoch * 6}
+
+    # ---- per-phase timing of the same epoch (CUDA events on the launch stream) -> roofline of the dominant kernel
+    phase_ms = np.zeros(4)
+    n_prof = min(steps_per_epoch, 64)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n_prof)]
+    order = orders[0]
+    torch.cuda.synchronize()
+    for s in range(n_prof):
+        idx = order[s * BATCH:(s + 1) * BATCH]
+        kw = dict(idx=idx, B_global=idx.numel(), G=G)
+        for ph in range(4):
+            evs[s][ph].record()
+            ops.train_step(X, y, g, ad, That, 100.0, buf, 0.0, stats, s, phases=1 << ph, **kw)
+        evs[s][4].record()
+    torch.cuda.synchronize()
+    for s in range(n_prof):
+        for ph in range(4):
+            phase_ms[ph] += evs[s][ph].elapsed_time(evs[s][ph + 1])
+    phase_ms /= n_prof
+    names = ["gemm1(+gram,memset)", "rows", "wgrad(dW1,S,dW2)", "sgd"]
+    dom = int(np.argmax(phase_ms))
+    if rank == 0:
+        # GEMM-1 and dW1 each stream the batch's X once (4096 B/emb) and do 2*D*H flop/emb
+        dom_flop = {0: 2.0 * D * H * BATCH, 2: 2.0 * D * H * BATCH + 2.0 * H * H * BATCH, 1: 4.0 * H * (H + C) * BATCH,
+                    3: 4.0 * (2 * D * H)}[dom]
+        dom_bytes = {0: ALG_BYTES_PER_EMB * BATCH, 2: ALG_BYTES_PER_EMB * BATCH, 1: 2 * 4 * H * BATCH,
+                     3: 5 * 4 * (2 * D * H + 3 * H + D)}[dom]
+        t_dom = phase_ms[dom] * 1e-3
+        t_hbm, t_tc = dom_bytes / (P["hbm"] * 1e9), dom_flop / (P["tc_sustained"] * 1e12)
+        if t_tc >= t_hbm:
+            roof = {"bound": "tensor", "achieved": dom_flop / t_dom / 1e12, "peak": P["tc_sustained"], "unit": "TFLOP/s"}
+        else:
+            roof = {"bound": "hbm", "achieved": dom_bytes / t_dom / 1e9, "peak": P["hbm"], "unit": "GB/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["traffic"] = None
+        roof["kernel"] = names[dom]
+        roof["peak_source"] = P["src"] + (" (sustained bf16 figure: kernel timed inside a long step)" if roof["bound"] == "tensor" else "")
+        roof["phase_us"] = {n: float(1e3 * t) for n, t in zip(names, phase_ms)}
+        # whole training step against its binding roof (tensor roof binds the train step)
+        t_step = ms_per_step * 1e-3 / steps_per_epoch
+        roof["step"] = {"bound": "tensor", "achieved_tflops": ALG_FLOP_TRAIN * BATCH / t_step / 1e12,
+                        "frac": ALG_FLOP_TRAIN * BATCH / t_step / 1e12 / P["tc_sustained"],
+                        "hbm_gbs": ALG_BYTES_PER_EMB * BATCH / t_step / 1e9,
+                        "hbm_frac": ALG_BYTES_PER_EMB * BATCH / t_step / 1e9 / P["hbm"]}
+        out["roofline"] = roof
+
+    # ---- eval leg: validate()-style forward over the resident matrix (HBM-bound half of the path)
+    st_e = ops.BatchStatsBuffers((N_TRAIN + 511) // 512, G, device=dev)
+    for _ in range(2):
+        ops.eval_fwd(X, y, g, ad, That, 100.0, st_e, 512, G=G)
+    barrier()
+    e0.record()
+    n_eval = 5
+    for _ in range(n_eval):
+        ops.eval_fwd(X, y, g, ad, That, 100.0, st_e, 512, G=G)
+    e1.record()
+    barrier()
+    ms_e = e0.elapsed_time(e1) / n_eval
+    if rank == 0:
+        ev = N_TRAIN / (ms_e * 1e-3)
+        out["eval"] = {"value": ev * world, "unit": "embeddings/s", "ms_per_pass": ms_e,
+                       "roofline": {"bound": "hbm", "achieved": ev * ALG_BYTES_PER_EMB / 1e9, "peak": P["hbm"], "unit": "GB/s",
+                                    "frac": ev * ALG_BYTES_PER_EMB / 1e9 / P["hbm"], "traffic": None}}
+
+    # ---- e2e leg: host buffers in, statistics out, copies inside the timed region
+    xh = torch.from_numpy(x_np).pin_memory()
+    yh, gh = torch.from_numpy(y_np).pin_memory(), torch.from_numpy(g_np).pin_memory()
+    oh = [o.cpu().pin_memory() for o in orders]
+    Xd, yd, gd, od = torch.empty_like(X), torch.empty_like(y), torch.empty_like(g), torch.empty_like(orders[0])
+    loss_h = torch.empty(steps_per_epoch, dtype=torch.float64).pin_memory()
+    cnt_h = torch.empty(steps_per_epoch, 2, G, dtype=torch.int64).pin_memory()
+
+    def e2e_epoch(i):
+        Xd.copy_(xh, non_blocking=True); yd.copy_(yh, non_blocking=True); gd.copy_(gh, non_blocking=True)
+        od.copy_(oh[i % 4], non_blocking=True)
+        stats.zero_()
+        if world == 1:
+            ops.train_epoch(Xd, od, BATCH, yd, gd, ad, That, 100.0, buf, lrs, stats, G=G)
+        else:
+            for s in range(steps_per_epoch):
+                dp_step_on(Xd, yd, gd, od[s * BATCH:(s + 1) * BATCH], float(lrs[s]), s)
+        loss_h.copy_(stats.loss_sum, non_blocking=True); cnt_h.copy_(stats.counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_h.sum())
+
+    def dp_step_on(Xs, ys, gs, idx, lr, slot):
+        kw = dict(idx=idx, B_global=idx.numel() * world, G=G)
+        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, stats, slot, phases=1, **kw)
+        colsum, dgb = parallel.accum_views(ops.workspace(0, dev), H, 1)
+        dist.all_reduce(colsum)
+        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, stats, slot, phases=2, **kw)
+        dist.all_reduce(dgb)
+        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, stats, slot, phases=4, **kw)
+        dist.all_reduce(buf.grads)
+        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, stats, slot, phases=8, **kw)
+
+    n_e2e = max(3, min(args.steps, 5))
+    e2e_epoch(0)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(n_e2e):
+        e2e_epoch(i)
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms2], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+    if rank == 0:
+        h2d = x_np.nbytes + y_np.nbytes + g_np.nbytes + 4 * N_TRAIN
+        d2h = loss_h.numel() * 8 + cnt_h.numel() * 8
+        out["e2e"] = {"value": world * N_TRAIN * n_e2e / (ms2 * 1e-3), "unit": "embeddings/s",
+                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2 / n_e2e,
+                      "api": "dbmm_train_epoch (C ABI) on pinned host buffers copied per step"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port of the reference step on the host cores
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_sgd = 24
+        r = cpu_reference_step(x_np[:n_sgd * BATCH], y_np[:n_sgd * BATCH], g_np[:n_sgd * BATCH], T_np, 2)
+        r = cpu_reference_step(x_np[:n_sgd * BATCH], y_np[:n_sgd * BATCH], g_np[:n_sgd * BATCH], T_np, n_sgd)
+        out["cpu_baseline"] = {"value": r["emb_per_s"], "unit": "embeddings/s", "cores": r["threads"], "kind": "port",
+                               "sample": f"{n_sgd} SGD steps of {BATCH} rows of the same workload ({r['seconds']:.1f} s), "
+                                         "reference step body restated in torch-CPU (oracle/ref_port.py), tensors pre-loaded"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

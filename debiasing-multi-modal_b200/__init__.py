@@ -3,6 +3,6 @@
 The directory name follows the project's naming rule (`debiasing-multi-modal_b200`); because of the
 hyphens it is imported through the top-level alias module `dbmm` (``import dbmm``).
 """
-from . import _lib, ops, synth, metrics, data, optim, modules, engine, cli  # noqa: F401
+from . import _lib, ops, synth, metrics, data, optim, modules, engine, cli, parallel  # noqa: F401
 
-__all__ = ["_lib", "ops", "synth", "metrics", "data", "optim", "modules", "engine", "cli"]
+__all__ = ["_lib", "ops", "synth", "metrics", "data", "optim", "modules", "engine", "cli", "parallel"]

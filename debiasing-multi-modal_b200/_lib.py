@@ -71,6 +71,7 @@ SIGNATURES = {
     "dbmm_last_error": (C.c_char_p, []),
     "dbmm_build_info": (C.c_char_p, []),
     "dbmm_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
+    "dbmm_train_accum_layout": (C.c_int, [_i32, _i32, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "dbmm_normalize_text": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "dbmm_eval_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32, _vp, _f32,
                                 _i64, BatchStats, _vp, _vp, _vp, _sz, _vp]),

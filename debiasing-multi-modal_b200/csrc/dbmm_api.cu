@@ -102,6 +102,17 @@ size_t dbmm_workspace_bytes(int op, int64_t rows, int D, int H, int C, int n_ada
     return 0;
 }
 
+int dbmm_train_accum_layout(int H, int n_adapters, size_t* colsum_offset, size_t* colsum_count,
+                            size_t* dgb_offset, size_t* dgb_count) {
+    DBMM_CHECK_ARG(H >= 1 && H <= DBMM_MAX_H && n_adapters >= 1 && n_adapters <= 2, "bad H / n_adapters");
+    DBMM_CHECK_ARG(colsum_offset && colsum_count && dgb_offset && dgb_count, "NULL output");
+    char* base = nullptr;
+    TrainWs w = carve_train_ws(base, 2, 4, H, 1, n_adapters);
+    *colsum_offset = (size_t)((char*)w.colsum - base); *colsum_count = (size_t)n_adapters * 2 * H;
+    *dgb_offset = (size_t)((char*)w.dgb - base); *dgb_count = (size_t)2 * H;
+    return DBMM_OK;
+}
+
 int dbmm_normalize_text(const float* T, float* That, int D, int C, void* stream) {
     DBMM_CHECK_ARG(T && That, "NULL text matrix");
     DBMM_CHECK_SHAPE(D >= 1 && C >= 1, "bad text shape [%d, %d]", D, C);

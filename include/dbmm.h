@@ -85,6 +85,12 @@ const char* dbmm_build_info(void);
 /* rows = rows per call (eval: chunk size used internally is bounded, pass N), n_adapters = 1 or 2 */
 size_t dbmm_workspace_bytes(int op, int64_t rows, int D, int H, int C, int n_adapters);
 
+/* Byte offsets (from the start of a DBMM_OP_TRAIN workspace) and element counts of the two fp64 accumulator blocks
+ * a data-parallel caller must all-reduce between phases: column sums [n_adapters][2][H] after DBMM_PHASE_GEMM1 and
+ * (dgamma, dbeta) [2][H] after DBMM_PHASE_ROWS. */
+int dbmm_train_accum_layout(int H, int n_adapters, size_t* colsum_offset, size_t* colsum_count,
+                            size_t* dgb_offset, size_t* dgb_count);
+
 /* That[:, c] = T[:, c] / ||T[:, c]||_2 ;  T, That: [D, C] row-major */
 int dbmm_normalize_text(const float* T, float* That, int D, int C, void* stream);
 
