@@ -97,6 +97,8 @@ struct TrainWs {
     float* ds;        // [B][C]        dL/ds
     float* gram;      // [nad][H+1][H+1+C]
     float* S;         // [H+1+C][H+1]
+    float* whi;       // [nad][H][D]   tf32-exact part of W1 (tensor-core GEMM-1 operand)
+    float* wlo;       // [nad][H][D]   W1 - whi
     size_t accum_bytes;  // bytes of the zeroed region at the start (colsum + dgb)
     size_t total;
 };
@@ -116,10 +118,13 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     size_t o_ds = take(sizeof(float) * (size_t)B * C);
     size_t o_gram = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));
     size_t o_S = take(sizeof(float) * (size_t)(H + 1 + C) * (H + 1));
+    size_t o_whi = take(sizeof(float) * (size_t)nad * H * D);
+    size_t o_wlo = take(sizeof(float) * (size_t)nad * H * D);
     w.total = off;
     w.colsum = (double*)(p + o_colsum); w.dgb = (double*)(p + o_dgb);
     w.A = (float*)(p + o_A); w.hbuf = (float*)(p + o_h); w.dahat = (float*)(p + o_da);
     w.cvec = (float*)(p + o_c); w.ds = (float*)(p + o_ds); w.gram = (float*)(p + o_gram); w.S = (float*)(p + o_S);
+    w.whi = (float*)(p + o_whi); w.wlo = (float*)(p + o_wlo);
     return w;
 }
 

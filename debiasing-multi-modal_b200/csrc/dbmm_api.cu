@@ -2,6 +2,9 @@
 // kernel launches; no allocation, no exceptions, errors via return code + dbmm_last_error().
 #include <stdarg.h>
 
+#include <stdlib.h>
+
+#include "gemm1_tc.cuh"
 #include "kernels_simt.cuh"
 
 namespace dbmm {
@@ -77,6 +80,42 @@ static void fill_gemm1(Gemm1Args& g, const float* X, int64_t ldx, const int32_t*
     g.A = A; g.colsum = colsum;
 }
 
+static bool use_tc_gemm1(int D, int H) {
+    const char* e = getenv("DBMM_GEMM1");          // debugging switch: DBMM_GEMM1=simt forces the fp32 SIMT kernel
+    if (e && strcmp(e, "simt") == 0) return false;
+    return (D % G1_BK == 0) && (H % 32 == 0);
+}
+
+// a = x W1^T + b1 for one or two adapters (+ fp64 column sums).  whi/wlo: scratch [nad][H][D] each.
+static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t pos0, int B, int D, int H,
+                        const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, double* colsum,
+                        float* whi, float* wlo, bool split_weights, cudaStream_t st) {
+    const int nad = old_ad ? 2 : 1;
+    if (!use_tc_gemm1(D, H)) {
+        Gemm1Args g;
+        fill_gemm1(g, X, ldx, idx, pos0, B, D, H, old_ad, ad, A, colsum);
+        dim3 grid(ceil_div(B, GT_BM), ceil_div(nad * H, GT_BN));
+        k_gemm1<<<grid, GT_THREADS, 0, st>>>(g);
+        DBMM_LAUNCH_CHECK();
+        return DBMM_OK;
+    }
+    Gemm1TcArgs t;
+    t.X = X; t.ldx = ldx; t.idx = idx; t.pos0 = pos0; t.B = B; t.D = D; t.H = H; t.nad = nad;
+    const dbmm_adapter* ads[2] = {old_ad ? old_ad : ad, ad};
+    for (int i = 0; i < nad; ++i) {
+        t.Whi[i] = whi + (size_t)i * H * D; t.Wlo[i] = wlo + (size_t)i * H * D; t.b1[i] = ads[i]->b1;
+        if (split_weights) {
+            k_split_tf32<<<148, 256, 0, st>>>(ads[i]->W1, whi + (size_t)i * H * D, wlo + (size_t)i * H * D, (int64_t)H * D);
+            DBMM_LAUNCH_CHECK();
+        }
+    }
+    if (nad == 1) { t.Whi[1] = t.Whi[0]; t.Wlo[1] = t.Wlo[0]; t.b1[1] = t.b1[0]; }
+    t.A = A; t.colsum = colsum;
+    int bn = 128;
+    if (B <= 4096) bn = (H % 32 == 0) ? 32 : H;      // few row tiles: narrow hidden slices -> more CTAs pulling operands
+    return launch_gemm1_tc(t, bn, st);
+}
+
 }  // namespace dbmm
 
 using namespace dbmm;
@@ -97,7 +136,8 @@ size_t dbmm_workspace_bytes(int op, int64_t rows, int D, int H, int C, int n_ada
     if (op == DBMM_OP_EVAL) {
         const int64_t chunk = rows < EVAL_CHUNK ? rows : EVAL_CHUNK;
         return align_up(sizeof(float) * (size_t)n_adapters * (H + 1) * (H + 1 + C), 256) +
-               align_up(sizeof(float) * (size_t)n_adapters * chunk * H, 256);
+               align_up(sizeof(float) * (size_t)n_adapters * chunk * H, 256) +
+               2 * align_up(sizeof(float) * (size_t)n_adapters * H * D, 256);
     }
     return 0;
 }
@@ -140,14 +180,13 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
     DBMM_CHECK_ARG(dbmm_workspace_bytes(DBMM_OP_EVAL, N, D, H, C, nad) <= ws_bytes, "workspace too small");
     float* gram = (float*)ws;
     float* A = (float*)((char*)ws + align_up(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C), 256));
+    const int64_t chunk_rows = N < EVAL_CHUNK ? N : EVAL_CHUNK;
+    float* whi = (float*)((char*)A + align_up(sizeof(float) * (size_t)nad * chunk_rows * H, 256));
+    float* wlo = (float*)((char*)whi + align_up(sizeof(float) * (size_t)nad * H * D, 256));
     if (int rc = launch_gram(old_ad, ad, That, gram, D, H, C, st)) return rc;
     for (int64_t pos0 = 0; pos0 < N; pos0 += EVAL_CHUNK) {
         const int B = (int)((N - pos0) < EVAL_CHUNK ? (N - pos0) : EVAL_CHUNK);
-        Gemm1Args g;
-        fill_gemm1(g, X, ldx, idx, pos0, B, D, H, old_ad, ad, A, nullptr);
-        dim3 grid(ceil_div(B, GT_BM), ceil_div(nad * H, GT_BN));
-        k_gemm1<<<grid, GT_THREADS, 0, st>>>(g);
-        DBMM_LAUNCH_CHECK();
+        if (int rc = launch_gemm1(X, ldx, idx, pos0, B, D, H, old_ad, ad, A, nullptr, whi, wlo, pos0 == 0, st)) return rc;
         RowsArgs ra;
         memset(&ra, 0, sizeof(ra));
         ra.N = B; ra.pos0 = pos0; ra.idx = idx; ra.y = y; ra.grp = grp; ra.H = H; ra.C = C; ra.G = G;
@@ -189,11 +228,7 @@ int dbmm_train_step(int phases,
     if (phases & DBMM_PHASE_GEMM1) {
         DBMM_CUDA(cudaMemsetAsync(ws, 0, w.accum_bytes, st));
         if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
-        Gemm1Args g;
-        fill_gemm1(g, X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum);
-        dim3 grid(ceil_div(B, GT_BM), ceil_div(nad * H, GT_BN));
-        k_gemm1<<<grid, GT_THREADS, 0, st>>>(g);
-        DBMM_LAUNCH_CHECK();
+        if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, true, st)) return rc;
     }
     if (phases & DBMM_PHASE_ROWS) {
         RowsArgs ra;

@@ -1,0 +1,213 @@
+// GEMM-1 on the 5th-generation tensor cores:   A[b][j] = sum_k X[row(b)][k] * W1[j][k] + b1[j]
+//
+//   * tcgen05.mma kind::tf32, M = 128 rows per CTA, N = BN hidden units, K = 8 per instruction; fp32 accumulator in TMEM.
+//   * X is used as stored (fp32 containers; CLIP embeddings are fp16-valued, hence exact in tf32).  W1 is split
+//     W1 = hi + lo with hi = W1 & 0xffffe000 (tf32-exact) and lo = W1 - hi, and two MMAs accumulate x*hi + x*lo,
+//     which restores fp32-level accuracy (the tensor core truncates lo to its top 19 bits: ~2^-22 relative to W1).
+//   * operands are staged in shared memory as SWIZZLE_128B K-major tiles (128-byte rows = 32 floats of K) by four
+//     producer warps with 16-byte cp.async (rows are gathered through the batch's index list), multi-stage ring
+//     with full/empty mbarriers; one thread of a fifth warp issues the MMAs; the four producer warps then drain
+//     TMEM (tcgen05.ld 32x32b: one accumulator row per thread), add the bias, write A and reduce the BatchNorm
+//     column sums (fp64 across CTAs).
+#pragma once
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace dbmm {
+
+constexpr int G1_BM = 128, G1_BK = 32, G1_PRODUCERS = 128, G1_THREADS = 160, G1_LAG = 2;
+
+struct Gemm1TcArgs {
+    const float* X; int64_t ldx; const int32_t* idx; int64_t pos0;
+    int B, D, H, nad;
+    const float* Whi[2]; const float* Wlo[2]; const float* b1[2];   // per adapter, [H][D] / [H]
+    float* A;          // [nad][B][H]
+    double* colsum;    // [nad][2][H] or nullptr
+};
+
+__global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ w, float* __restrict__ hi,
+                                                    float* __restrict__ lo, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = w[i];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        hi[i] = h;
+        lo[i] = v - h;
+    }
+}
+
+template <int BN, int TERMS>
+struct G1Cfg {
+    static constexpr int A_BYTES = G1_BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + TERMS * B_BYTES;
+    static constexpr int STAGES = (STAGE_BYTES * 6 <= 196608) ? 6 : (196608 / STAGE_BYTES);
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int TERMS>
+__global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
+    using Cfg = G1Cfg<BN, TERMS>;
+    constexpr int S = Cfg::STAGES;
+    extern __shared__ uint8_t g1_smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)g1_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + (size_t)S * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + S;
+    uint64_t* tmem_full = empty + S;
+    uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
+    __shared__ int64_t sRowOff[G1_BM];
+    __shared__ double sCol[2][BN];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * G1_BM;
+    const int slices = a.H / BN;                        // hidden slices per adapter
+    const int ad = blockIdx.y / slices;
+    const int n0 = (blockIdx.y - ad * slices) * BN;     // first hidden unit of this CTA
+    const int KB = a.D / G1_BK;
+
+    if (tid < G1_BM) {
+        int m = m0 + tid;
+        if (m >= a.B) m = a.B - 1;                      // clamp: tail rows read a valid row, masked in the epilogue
+        const int64_t r = a.idx ? (int64_t)a.idx[a.pos0 + m] : (a.pos0 + m);
+        sRowOff[tid] = r * a.ldx;
+    }
+    if (tid < BN) { sCol[0][tid] = 0.0; sCol[1][tid] = 0.0; }
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { ptx::mbar_init(&full[s], G1_PRODUCERS); ptx::mbar_init(&empty[s], 1); }
+        ptx::mbar_init(tmem_full, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 4) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 4) {
+        // ===================== producers: gather X rows + W1 hi/lo slices into swizzled K-major tiles =====================
+        const float* whi = a.Whi[ad] + (size_t)n0 * a.D;
+        const float* wlo = a.Wlo[ad] + (size_t)n0 * a.D;
+        auto signal = [&](int kb) {
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&full[kb % S]);
+        };
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % S;
+            ptx::mbar_wait(&empty[s], ((kb / S) & 1) ^ 1);
+            uint8_t* stage = smem + (size_t)s * Cfg::STAGE_BYTES;
+            const uint32_t sA = ptx::smem_u32(stage);
+            const int k0 = kb * G1_BK;
+#pragma unroll
+            for (int id = tid; id < G1_BM * 8; id += G1_PRODUCERS) {
+                const int row = id >> 3, c = id & 7;
+                ptx::cp_async16(sA + ptx::sw128_offset(row, c), a.X + sRowOff[row] + k0 + c * 4);
+            }
+#pragma unroll
+            for (int t = 0; t < TERMS; ++t) {
+                const uint32_t sB = sA + Cfg::A_BYTES + t * Cfg::B_BYTES;
+                const float* w = t == 0 ? whi : wlo;
+#pragma unroll
+                for (int id = tid; id < BN * 8; id += G1_PRODUCERS) {
+                    const int row = id >> 3, c = id & 7;
+                    ptx::cp_async16(sB + ptx::sw128_offset(row, c), w + (size_t)row * a.D + k0 + c * 4);
+                }
+            }
+            ptx::cp_async_commit();
+            if (kb >= G1_LAG) { ptx::cp_async_wait<G1_LAG>(); signal(kb - G1_LAG); }
+        }
+        // drain the last LAG groups
+        if (KB >= 2) { ptx::cp_async_wait<1>(); signal(KB - 2); }
+        ptx::cp_async_wait<0>();
+        signal(KB - 1);
+
+        // ===================== epilogue: TMEM -> registers -> A (+ bias) and BatchNorm column sums =====================
+        ptx::mbar_wait(tmem_full, 0);
+        ptx::tc_fence_after_sync();
+        float* scr = (float*)smem + warp * (32 * 33);            // stage memory is free once every MMA has completed
+        const int m = m0 + warp * 32 + lane;
+        const bool row_ok = m < a.B;
+        const int rows_here = min(32, max(0, a.B - (m0 + warp * 32)));
+        const float* bias = a.b1[ad] + n0;
+        float* arow = a.A + ((size_t)ad * a.B + (row_ok ? m : 0)) * a.H + n0;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + ch * 32, r);
+            ptx::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(bias + ch * 32 + j);
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(arow + ch * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (a.colsum) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = v[j];
+                __syncwarp();
+                float s1 = 0.f, s2 = 0.f;
+                for (int rr = 0; rr < rows_here; ++rr) { const float x = scr[rr * 33 + lane]; s1 += x; s2 = fmaf(x, x, s2); }
+                __syncwarp();
+                atomicAdd(&sCol[0][ch * 32 + lane], (double)s1);
+                atomicAdd(&sCol[1][ch * 32 + lane], (double)s2);
+            }
+        }
+        ptx::tc_fence_before_sync();
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+        if (a.colsum && tid < BN) {
+            atomicAdd(&a.colsum[((size_t)ad * 2 + 0) * a.H + n0 + tid], sCol[0][tid]);
+            atomicAdd(&a.colsum[((size_t)ad * 2 + 1) * a.H + n0 + tid], sCol[1][tid]);
+        }
+    } else {
+        // ===================== MMA issuer: one thread =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc(/*tf32*/ 2, G1_BM, BN, 0, 0);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % S;
+                ptx::mbar_wait(&full[s], (kb / S) & 1);
+                ptx::tc_fence_after_sync();
+                const uint32_t sA = ptx::smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < G1_BK / 8; ++kk) {
+                    const uint64_t adesc = ptx::umma_smem_desc(sA + kk * 32, 0, 1024);
+#pragma unroll
+                    for (int t = 0; t < TERMS; ++t) {
+                        const uint64_t bdesc = ptx::umma_smem_desc(sA + Cfg::A_BYTES + t * Cfg::B_BYTES + kk * 32, 0, 1024);
+                        ptx::mma_tf32_ss(tmem_base, adesc, bdesc, idesc, (kb | kk | t) != 0 ? 1u : 0u);
+                    }
+                }
+                ptx::mma_commit(&empty[s]);          // smem slot reusable once these MMAs have read it
+            }
+            ptx::mma_commit(tmem_full);              // accumulator complete
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int TERMS>
+static int launch_gemm1_tc_impl(const Gemm1TcArgs& a, cudaStream_t st) {
+    using Cfg = G1Cfg<BN, TERMS>;
+    auto kern = k_gemm1_tc<BN, TERMS>;
+    DBMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    dim3 grid(ceil_div(a.B, G1_BM), a.nad * (a.H / BN));
+    kern<<<grid, G1_THREADS, Cfg::SMEM, st>>>(a);
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+// BN: hidden units per CTA.  Small batches use narrow slices so that more SMs pull operands concurrently.
+static int launch_gemm1_tc(const Gemm1TcArgs& a, int bn, cudaStream_t st) {
+    DBMM_CHECK_SHAPE(a.D % G1_BK == 0, "tensor-core GEMM-1 needs D %% 32 == 0 (D=%d)", a.D);
+    DBMM_CHECK_SHAPE(a.H % bn == 0, "H=%d not divisible by the hidden slice %d", a.H, bn);
+    switch (bn) {
+        case 128: return launch_gemm1_tc_impl<128, 2>(a, st);
+        case 64: return launch_gemm1_tc_impl<64, 2>(a, st);
+        case 32: return launch_gemm1_tc_impl<32, 2>(a, st);
+        default: set_error("unsupported hidden slice %d", bn); return DBMM_ERR_UNSUPPORTED_SHAPE;
+    }
+}
+
+}  // namespace dbmm
