@@ -99,7 +99,7 @@ struct TrainWs {
     float* S;         // [H+1+C][H+1]
     float* whi;       // [nad][H][D]   tf32-exact part of W1 (tensor-core GEMM-1 operand)
     float* wlo;       // [nad][H][D]   W1 - whi
-    size_t accum_bytes;  // bytes of the zeroed region at the start (colsum + dgb)
+    size_t accum_bytes;  // bytes of the zeroed region at the start (colsum, dgb, gram, S)
     size_t total;
 };
 
@@ -110,14 +110,14 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_colsum = take(sizeof(double) * nad * 2 * H);
     size_t o_dgb = take(sizeof(double) * 2 * H);
+    size_t o_gram = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));     // split-K targets: zeroed with the sums
+    size_t o_S = take(sizeof(float) * (size_t)(H + 1 + C) * (H + 1));
     w.accum_bytes = off;
     size_t o_A = take(sizeof(float) * (size_t)nad * B * H);
     size_t o_h = take(sizeof(float) * (size_t)B * H);
     size_t o_da = take(sizeof(float) * (size_t)B * H);
     size_t o_c = take(sizeof(float) * (size_t)B);
     size_t o_ds = take(sizeof(float) * (size_t)B * C);
-    size_t o_gram = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));
-    size_t o_S = take(sizeof(float) * (size_t)(H + 1 + C) * (H + 1));
     size_t o_whi = take(sizeof(float) * (size_t)nad * H * D);
     size_t o_wlo = take(sizeof(float) * (size_t)nad * H * D);
     w.total = off;

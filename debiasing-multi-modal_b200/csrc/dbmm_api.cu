@@ -38,22 +38,30 @@ static int check_adapter(const dbmm_adapter* a, const char* name) {
 template <bool TRAIN>
 static int launch_rows(const RowsArgs& ra, int nad, int H, int C, cudaStream_t st) {
     const int CT = C <= 4 ? 4 : 16;
-    const size_t smem = rows_smem_bytes(H, C, nad, CT);
+    // small batches: 8 rows per CTA (4 warps x 2 rows) so ~B/8 SMs work; large batches: 32 rows per CTA (8 x 4)
+    const bool small = ra.N <= 148 * 32;
+    const int rows_per_cta = small ? 8 : 32;
+    const size_t smem = rows_smem_bytes(H, C, nad, CT, rows_per_cta);
     DBMM_CHECK_SHAPE(smem <= 227 * 1024, "row kernel needs %zu bytes of shared memory", smem);
-    int grid = ceil_div(ra.N, RK_ROWS);
-    if (grid > 148 * 4) grid = 148 * 4;
+    int grid = ceil_div(ra.N, rows_per_cta);
+    if (grid > 148 * 2) grid = 148 * 2;
     if (grid < 1) grid = 1;
+#define DBMM_ROWS_LAUNCH(NAD_, CT_, RB_, NW_)                                                             \
+    do {                                                                                                  \
+        auto kern = k_rows<TRAIN, NAD_, CT_, RB_, NW_>;                                                   \
+        DBMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        kern<<<grid, NW_ * 32, smem, st>>>(ra);                                                           \
+    } while (0)
 #define DBMM_ROWS_CASE(NAD_, CT_)                                                                         \
     do {                                                                                                  \
-        auto kern = k_rows<TRAIN, NAD_, CT_>;                                                             \
-        DBMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        kern<<<grid, RK_WARPS * 32, smem, st>>>(ra);                                                      \
+        if (small) DBMM_ROWS_LAUNCH(NAD_, CT_, 2, 4); else DBMM_ROWS_LAUNCH(NAD_, CT_, 4, 8);             \
     } while (0)
     if (nad == 1 && CT == 4) DBMM_ROWS_CASE(1, 4);
     else if (nad == 1) DBMM_ROWS_CASE(1, 16);
     else if (CT == 4) DBMM_ROWS_CASE(2, 4);
     else DBMM_ROWS_CASE(2, 16);
 #undef DBMM_ROWS_CASE
+#undef DBMM_ROWS_LAUNCH
     DBMM_LAUNCH_CHECK();
     return DBMM_OK;
 }
@@ -65,7 +73,8 @@ static int launch_gram(const dbmm_adapter* old_ad, const dbmm_adapter* ad, const
     ga.W2[0] = old_ad ? old_ad->W2 : ad->W2; ga.b2[0] = old_ad ? old_ad->b2 : ad->b2;
     ga.W2[1] = ad->W2; ga.b2[1] = ad->b2;
     ga.That = That; ga.gram = gram; ga.D = D; ga.H = H; ga.C = C; ga.nad = nad;
-    dim3 grid(ceil_div(H + 1, GT_BM), ceil_div(H + 1 + C, GT_BN), nad);
+    ga.ksplit = D >= 256 ? 16 : 1;           // the caller zeroes `gram` when ksplit > 1 (see gram_needs_zero)
+    dim3 grid(ceil_div(H + 1, GT_BM), ceil_div(H + 1 + C, GT_BN), nad * ga.ksplit);
     k_gram<<<grid, GT_THREADS, 0, st>>>(ga);
     DBMM_LAUNCH_CHECK();
     return DBMM_OK;
@@ -183,6 +192,7 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
     const int64_t chunk_rows = N < EVAL_CHUNK ? N : EVAL_CHUNK;
     float* whi = (float*)((char*)A + align_up(sizeof(float) * (size_t)nad * chunk_rows * H, 256));
     float* wlo = (float*)((char*)whi + align_up(sizeof(float) * (size_t)nad * H * D, 256));
+    DBMM_CUDA(cudaMemsetAsync(gram, 0, sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C), st));
     if (int rc = launch_gram(old_ad, ad, That, gram, D, H, C, st)) return rc;
     for (int64_t pos0 = 0; pos0 < N; pos0 += EVAL_CHUNK) {
         const int B = (int)((N - pos0) < EVAL_CHUNK ? (N - pos0) : EVAL_CHUNK);
@@ -223,7 +233,7 @@ int dbmm_train_step(int phases,
     DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
     const size_t np = dbmm_param_count(D, H);
     const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
-    const int ksplit = B > 4096 ? (B + 4095) / 4096 : 1;
+    const int ksplit = B >= 512 ? (B / 256 > 16 ? 16 : B / 256) : 1;   // split the batch reduction over more CTAs
 
     if (phases & DBMM_PHASE_GEMM1) {
         DBMM_CUDA(cudaMemsetAsync(ws, 0, w.accum_bytes, st));
@@ -251,10 +261,7 @@ int dbmm_train_step(int phases,
         wa.tiles_w1_m = ceil_div(H, GT_BM); wa.tiles_w1_n = ceil_div(D, GT_BN);
         wa.tiles_s_m = ceil_div(H + 1 + C, GT_BM); wa.tiles_s_n = ceil_div(H + 1, GT_BN);
         wa.ksplit = ksplit;
-        if (ksplit > 1) {
-            DBMM_CUDA(cudaMemsetAsync(grads + oW1, 0, sizeof(float) * (size_t)H * D, st));
-            DBMM_CUDA(cudaMemsetAsync(w.S, 0, sizeof(float) * (size_t)(H + 1 + C) * (H + 1), st));
-        }
+        if (ksplit > 1) DBMM_CUDA(cudaMemsetAsync(grads + oW1, 0, sizeof(float) * (size_t)H * D, st));   // S is zeroed with the sums
         dim3 grid(wa.tiles_w1_m * wa.tiles_w1_n + wa.tiles_s_m * wa.tiles_s_n, ksplit);
         k_wgrad<<<grid, GT_THREADS, 0, st>>>(wa);
         DBMM_LAUNCH_CHECK();
@@ -271,12 +278,12 @@ int dbmm_train_step(int phases,
         SgdArgs sa;
         sa.p[0] = ad->W1; sa.p[1] = ad->b1; sa.p[2] = ad->gamma; sa.p[3] = ad->beta; sa.p[4] = ad->W2; sa.p[5] = ad->b2;
         sa.off[0] = oW1; sa.off[1] = ob1; sa.off[2] = og; sa.off[3] = obeta; sa.off[4] = oW2; sa.off[5] = ob2; sa.off[6] = np;
-        sa.g = grads; sa.v = momentum_buf; sa.lr = lr; sa.momentum = momentum; sa.wd = weight_decay; sa.first = first_step;
+        sa.g = grads; sa.v = momentum_buf; sa.lr = lr; sa.momentum = momentum; sa.wd = weight_decay; sa.first = first_step; sa.vec4 = (H % 4 == 0 && D % 4 == 0) ? 1 : 0;
         sa.nad = nad; sa.H = H; sa.Bg = B_global; sa.colsum = w.colsum;
         const dbmm_adapter* a0 = old_ad ? old_ad : ad;
         sa.rm[0] = a0->running_mean; sa.rv[0] = a0->running_var; sa.nbt[0] = (long long*)a0->num_batches_tracked;
         sa.rm[1] = ad->running_mean; sa.rv[1] = ad->running_var; sa.nbt[1] = (long long*)ad->num_batches_tracked;
-        k_sgd<<<148, 256, 0, st>>>(sa);
+        k_sgd<<<ceil_div((int64_t)np, 4 * 256) < 1 ? 1 : ceil_div((int64_t)np, 4 * 256), 256, 0, st>>>(sa);
         DBMM_LAUNCH_CHECK();
     }
     return DBMM_OK;

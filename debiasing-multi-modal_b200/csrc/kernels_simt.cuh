@@ -115,30 +115,33 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm1(Gemm1Args a) {
 
 // ------------------------------------------------------------------------------------------------
 // Gram matrices:  gram[ad] = [W2 | b2]^T [W2 | b2 | That]      ((H+1) x (H+1+C), K = D)
+// split-K over gridDim.z / nad partial products, accumulated with fp32 atomics into a zeroed buffer.
 // ------------------------------------------------------------------------------------------------
 struct GramArgs {
     const float* W2[2]; const float* b2[2]; const float* That;
-    float* gram; int D, H, C, nad;
+    float* gram; int D, H, C, nad, ksplit;
 };
 
 __global__ void __launch_bounds__(GT_THREADS) k_gram(GramArgs a) {
     __shared__ __align__(16) float smem[GT_SMEM_FLOATS];
-    const int ad = blockIdx.z;
+    const int ad = blockIdx.z / a.ksplit, part = blockIdx.z - ad * a.ksplit;
     const int H = a.H, C = a.C, M = H + 1, N = H + 1 + C;
     const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * GT_BN;
-    const float* W2 = a.W2[ad];
-    const float* b2 = a.b2[ad];
-    auto fa = [&](int i, int d) -> float {
-        if (i < H) return __ldg(W2 + (size_t)d * H + i);
-        return i == H ? __ldg(b2 + d) : 0.f;
+    const float* W2 = ad == 0 ? a.W2[0] : a.W2[1];
+    const float* b2 = ad == 0 ? a.b2[0] : a.b2[1];
+    const float* That = a.That;
+    auto fa = [=](int i, int d) -> float {
+        const float* p = (i < H) ? (W2 + (size_t)d * H + i) : (b2 + d);
+        return (i <= H) ? __ldg(p) : 0.f;
     };
-    auto fb = [&](int d, int j) -> float {
-        if (j < H) return __ldg(W2 + (size_t)d * H + j);
-        if (j == H) return __ldg(b2 + d);
-        return j < N ? __ldg(a.That + (size_t)d * C + (j - H - 1)) : 0.f;
+    auto fb = [=](int d, int j) -> float {
+        const float* p = (j < H) ? (W2 + (size_t)d * H + j) : (j == H ? (b2 + d) : (That + (size_t)d * C + (j - H - 1)));
+        return (j < N) ? __ldg(p) : 0.f;
     };
+    int k0, k1;
+    gt_split_k(a.D, a.ksplit, part, k0, k1);
     float acc[GT_TM][GT_TN];
-    simt_gemm_tile<false, true>(acc, m0, n0, 0, a.D, fa, fb, smem);
+    simt_gemm_tile<false, true>(acc, m0, n0, k0, k1, fa, fb, smem);
     float* out = a.gram + (size_t)ad * M * N;
 #pragma unroll
     for (int i = 0; i < GT_TM; ++i) {
@@ -147,7 +150,10 @@ __global__ void __launch_bounds__(GT_THREADS) k_gram(GramArgs a) {
 #pragma unroll
         for (int j = 0; j < GT_TN; ++j) {
             const int n = gt_col(n0, j);
-            if (n < N) out[(size_t)m * N + n] = acc[i][j];
+            if (n < N) {
+                if (a.ksplit > 1) atomicAdd(&out[(size_t)m * N + n], acc[i][j]);
+                else out[(size_t)m * N + n] = acc[i][j];
+            }
         }
     }
 }
@@ -155,7 +161,11 @@ __global__ void __launch_bounds__(GT_THREADS) k_gram(GramArgs a) {
 // ------------------------------------------------------------------------------------------------
 // Row kernel: BatchNorm -> ReLU -> H-space logits -> CE / argmax / group counters (-> row backward)
 // ------------------------------------------------------------------------------------------------
-constexpr int RK_WARPS = 8, RK_RB = 4, RK_ROWS = RK_WARPS * RK_RB, RK_NSLOT = 5, RK_HSLOT = 4;
+constexpr int RK_NSLOT = 5, RK_HSLOT = 4;     // 32-wide column slots: Gram columns (<= 160) / hidden units (<= 128)
+
+__host__ __device__ inline size_t rows_gram_floats_dev(int H, int C, int nad) {
+    return ((size_t)nad * (H + 1) * (H + 1 + C) + 3) / 4 * 4;
+}
 
 struct RowsArgs {
     int64_t N;            // rows in this launch
@@ -172,20 +182,26 @@ struct RowsArgs {
     float* hbuf; float* dahat; float* cvec; float* ds; double* dgb;
 };
 
-static inline size_t rows_smem_bytes(int H, int C, int nad, int CT) {
-    size_t fl = (size_t)nad * (H + 1) * (H + 1 + C) + (size_t)nad * 4 * H + (size_t)RK_ROWS * (H + 1)
-              + 32 + 32 + 32 + (size_t)RK_ROWS * CT + 2 * (size_t)H;
+static inline size_t rows_gram_floats(int H, int C, int nad) {
+    return ((size_t)nad * (H + 1) * (H + 1 + C) + 3) / 4 * 4;          // padded to 16 bytes
+}
+static inline size_t rows_smem_bytes(int H, int C, int nad, int CT, int rows_per_cta) {
+    size_t fl = rows_gram_floats(H, C, nad) + (size_t)nad * 4 * H + (size_t)rows_per_cta * (H + 1)
+              + 32 + 32 + 32 + (size_t)rows_per_cta * CT + 2 * (size_t)H;
     return fl * 4;
 }
 
-template <bool TRAIN, int NAD, int CT>
+// RK_RB rows per warp (they share every Gram element read from shared memory), RK_WARPS warps per CTA.
+template <bool TRAIN, int NAD, int CT, int RK_RB, int RK_WARPS>
 __global__ void __launch_bounds__(RK_WARPS * 32) k_rows(RowsArgs a) {
+    constexpr int RK_ROWS = RK_RB * RK_WARPS;
+    static_assert(RK_ROWS <= 32, "the group reduction maps one CTA row to one lane of warp 0");
     extern __shared__ __align__(16) float dyn_smem[];
     const int H = a.H, C = a.C, ldg = H + 1 + C;
     const int HS = (H + 31) >> 5;             // slots holding hidden units
     const int NS = (ldg + 31) >> 5;           // slots holding Gram columns
     float* sG = dyn_smem;                                     // [NAD][H+1][ldg]
-    float* sBN = sG + (size_t)NAD * (H + 1) * ldg;            // [NAD][4][H]: mu, rstd, gamma, beta
+    float* sBN = sG + rows_gram_floats_dev(H, C, NAD);        // [NAD][4][H]: mu, rstd, gamma, beta
     float* sH = sBN + (size_t)NAD * 4 * H;                    // [RK_ROWS][H+1]
     float* sRowNll = sH + (size_t)RK_ROWS * (H + 1);          // [32]
     int* sRowG = reinterpret_cast<int*>(sRowNll + 32);        // [32]
@@ -196,7 +212,14 @@ __global__ void __launch_bounds__(RK_WARPS * 32) k_rows(RowsArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int ADT = NAD - 1;              // the trainable / only adapter
 
-    for (int e = tid; e < NAD * (H + 1) * ldg; e += blockDim.x) sG[e] = a.gram[e];
+    {   // Gram matrices -> shared memory: 16-byte cp.async, everything in flight at once
+        const int n = NAD * (H + 1) * ldg, n4 = n >> 2;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sG);
+        for (int e = tid; e < n4; e += blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + e * 16), "l"(a.gram + e * 4) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int e = (n4 << 2) + tid; e < n; e += blockDim.x) sG[e] = a.gram[e];
+    }
     for (int e = tid; e < NAD * H; e += blockDim.x) {
         const int ad = e / H, j = e - ad * H;
         float mu, var;
@@ -214,6 +237,7 @@ __global__ void __launch_bounds__(RK_WARPS * 32) k_rows(RowsArgs a) {
         bn[2 * H + j] = a.ad[ad].gamma[j]; bn[3 * H + j] = a.ad[ad].beta[j];
     }
     if (TRAIN) for (int e = tid; e < 2 * H; e += blockDim.x) sDgb[e] = 0.f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     float dg_acc[RK_HSLOT], db_acc[RK_HSLOT];
@@ -260,6 +284,7 @@ __global__ void __launch_bounds__(RK_WARPS * 32) k_rows(RowsArgs a) {
 #pragma unroll
                 for (int s = 0; s < RK_NSLOT; ++s) t[rb][s] = 0.f;
             const float* hbase = sH + (size_t)(warp * RK_RB) * (H + 1);
+#pragma unroll 4
             for (int i = 0; i <= H; ++i) {
                 float g[RK_NSLOT];
 #pragma unroll
@@ -400,13 +425,13 @@ __global__ void __launch_bounds__(RK_WARPS * 32) k_rows(RowsArgs a) {
         // ---- warp-shuffle group reduction over this CTA's 32 rows: one atomic per group
         if (warp == 0) {
             const int64_t r = base + lane;
-            const bool valid = r < a.N;
+            const bool valid = lane < RK_ROWS && r < a.N;
             const int64_t slot = a.slot_fixed >= 0 ? a.slot_fixed : (valid ? (a.pos0 + r) / a.batch_size : -1);
             const int64_t slot0 = __shfl_sync(0xffffffffu, slot, 0);
             const bool uniform = __all_sync(0xffffffffu, !valid || slot == slot0);
-            const int gv = sRowG[lane];
-            const int cr = sRowCorr[lane];
-            const float nl = sRowNll[lane];
+            const int gv = lane < RK_ROWS ? sRowG[lane] : -1;
+            const int cr = lane < RK_ROWS ? sRowCorr[lane] : 0;
+            const float nl = lane < RK_ROWS ? sRowNll[lane] : 0.f;
             if (uniform) {
                 const double tot = warp_sum((double)nl);
                 if (lane == 0 && a.loss_sum) atomicAdd(&a.loss_sum[slot0], tot);
@@ -482,16 +507,20 @@ __global__ void __launch_bounds__(GT_THREADS) k_wgrad(WgradArgs a) {
             sCst[0][i] = mu; sCst[1][i] = rstd; sCst[2][i] = m1; sCst[3][i] = m2;
         }
         __syncthreads();
-        auto fa = [&](int j, int b) -> float {          // da[b][j]
-            if (j >= H) return 0.f;
-            const int i = j - m0;
-            const float ah = (__ldg(a.A + (size_t)b * H + j) - sCst[0][i]) * sCst[1][i];
-            return (__ldg(a.dahat + (size_t)b * H + j) - sCst[2][i] - ah * sCst[3][i]) * sCst[1][i];
+        const float* Ap = a.A; const float* dap = a.dahat; const float* Xp = a.X; const int32_t* idxp = a.idx;
+        const int64_t ldx = a.ldx; const int Dd = a.D;
+        auto fa = [=](int j, int b) -> float {          // da[b][j]  (sCst is static shared: referenced directly)
+            const int jj = j < H ? j : H - 1;
+            const int i = jj - m0;
+            const float ah = (__ldg(Ap + (size_t)b * H + jj) - sCst[0][i]) * sCst[1][i];
+            const float v = (__ldg(dap + (size_t)b * H + jj) - sCst[2][i] - ah * sCst[3][i]) * sCst[1][i];
+            return j < H ? v : 0.f;
         };
-        auto fb = [&](int b, int k) -> float {
-            if (k >= a.D) return 0.f;
-            const int64_t r = a.idx ? (int64_t)__ldg(a.idx + b) : (int64_t)b;
-            return __ldg(a.X + r * a.ldx + k);
+        auto fb = [=](int b, int k) -> float {
+            const int64_t r = idxp ? (int64_t)__ldg(idxp + b) : (int64_t)b;
+            const int kk = k < Dd ? k : Dd - 1;
+            const float v = __ldg(Xp + r * ldx + kk);
+            return k < Dd ? v : 0.f;
         };
         simt_gemm_tile<false, true>(acc, m0, n0, k0, k1, fa, fb, smem);
 #pragma unroll
@@ -511,14 +540,16 @@ __global__ void __launch_bounds__(GT_THREADS) k_wgrad(WgradArgs a) {
         tile -= n_w1;
         const int M = H + 1 + C, N = H + 1;
         const int m0 = (tile / a.tiles_s_n) * GT_BM, n0 = (tile % a.tiles_s_n) * GT_BN;
-        auto fa = [&](int i, int b) -> float {          // L[b][i]
-            if (i < H) return __ldg(a.cvec + b) * __ldg(a.hbuf + (size_t)b * H + i);
-            if (i == H) return __ldg(a.cvec + b);
-            return i < M ? __ldg(a.ds + (size_t)b * C + (i - H - 1)) : 0.f;
+        const float* cv = a.cvec; const float* hb = a.hbuf; const float* dsp = a.ds;
+        auto fa = [=](int i, int b) -> float {          // L[b][i] = c*h | c | ds
+            const float c = __ldg(cv + b);
+            const float* p = (i < H) ? (hb + (size_t)b * H + i) : (dsp + (size_t)b * C + (i > H && i < M ? i - H - 1 : 0));
+            const float v = __ldg(p);
+            return i < H ? c * v : (i == H ? c : (i < M ? v : 0.f));
         };
-        auto fb = [&](int b, int j) -> float {          // R[b][j]
-            if (j < H) return __ldg(a.hbuf + (size_t)b * H + j);
-            return j == H ? 1.f : 0.f;
+        auto fb = [=](int b, int j) -> float {          // R[b][j] = h | 1
+            const float v = __ldg(hb + (size_t)b * H + (j < H ? j : 0));
+            return j < H ? v : (j == H ? 1.f : 0.f);
         };
         simt_gemm_tile<false, true>(acc, m0, n0, k0, k1, fa, fb, smem);
 #pragma unroll
@@ -551,13 +582,17 @@ __global__ void __launch_bounds__(GT_THREADS) k_w2grad(W2gradArgs a) {
     __shared__ __align__(16) float smem[GT_SMEM_FLOATS];
     const int H = a.H, C = a.C, K = H + 1 + C, N = H + 1;
     const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * GT_BN;
-    auto fa = [&](int d, int kk) -> float {
-        if (d >= a.D) return 0.f;
-        if (kk < H) return __ldg(a.W2 + (size_t)d * H + kk);
-        if (kk == H) return __ldg(a.b2 + d);
-        return kk < K ? __ldg(a.That + (size_t)d * C + (kk - H - 1)) : 0.f;
+    const float* W2 = a.W2; const float* b2 = a.b2; const float* That = a.That; const float* Sp = a.S; const int Dd = a.D;
+    auto fa = [=](int d, int kk) -> float {
+        const int dd = d < Dd ? d : Dd - 1;
+        const float* p = (kk < H) ? (W2 + (size_t)dd * H + kk) : (kk == H ? (b2 + dd) : (That + (size_t)dd * C + (kk < K ? kk - H - 1 : 0)));
+        const float v = __ldg(p);
+        return (d < Dd && kk < K) ? v : 0.f;
     };
-    auto fb = [&](int kk, int j) -> float { return j < N ? __ldg(a.S + (size_t)kk * N + j) : 0.f; };
+    auto fb = [=](int kk, int j) -> float {
+        const float v = __ldg(Sp + (size_t)kk * N + (j < N ? j : 0));
+        return j < N ? v : 0.f;
+    };
     float acc[GT_TM][GT_TN];
     simt_gemm_tile<true, true>(acc, m0, n0, 0, K, fa, fb, smem);
 #pragma unroll
@@ -588,13 +623,35 @@ __global__ void __launch_bounds__(GT_THREADS) k_w2grad(W2gradArgs a) {
 struct SgdArgs {
     float* p[6]; int64_t off[7];
     const float* g; float* v;
-    float lr, momentum, wd; int first;
+    float lr, momentum, wd; int first; int vec4;
     int nad, H; int64_t Bg; const double* colsum;
     float* rm[2]; float* rv[2]; long long* nbt[2];
 };
 
 __global__ void __launch_bounds__(256) k_sgd(SgdArgs a) {
     const int64_t n = a.off[6];
+    if (a.vec4) {          // every tensor size (and so every flat offset) is a multiple of 4: 16-byte accesses
+        for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 * 4 < n; i4 += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t i = i4 * 4;
+            int seg = 0;
+#pragma unroll
+            for (int s = 1; s < 6; ++s) seg += (i >= a.off[s]) ? 1 : 0;
+            float4* pp = reinterpret_cast<float4*>(a.p[seg] + (i - a.off[seg]));
+            const float4 pv = *pp;
+            const float4 gv = *reinterpret_cast<const float4*>(a.g + i);
+            float4 vv = a.first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(a.v + i);
+            const float px[4] = {pv.x, pv.y, pv.z, pv.w}, gx[4] = {gv.x, gv.y, gv.z, gv.w}, vx[4] = {vv.x, vv.y, vv.z, vv.w};
+            float po[4], vo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float g = gx[q] + a.wd * px[q];
+                vo[q] = a.first ? g : (a.momentum * vx[q] + g);
+                po[q] = px[q] - a.lr * vo[q];
+            }
+            *reinterpret_cast<float4*>(a.v + i) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+            *pp = make_float4(po[0], po[1], po[2], po[3]);
+        }
+    } else
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int seg = 0;
 #pragma unroll
@@ -606,7 +663,7 @@ __global__ void __launch_bounds__(256) k_sgd(SgdArgs a) {
         a.v[i] = v;
         *pp = pv - a.lr * v;
     }
-    if (blockIdx.x == 0 && a.colsum) {
+    if (blockIdx.x == gridDim.x - 1 && a.colsum) {
         for (int e = threadIdx.x; e < a.nad * a.H; e += blockDim.x) {
             const int ad = e / a.H, j = e - ad * a.H;
             const double m = a.colsum[((size_t)ad * 2 + 0) * a.H + j] / (double)a.Bg;
