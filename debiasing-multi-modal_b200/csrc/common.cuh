@@ -99,6 +99,7 @@ struct TrainWs {
     float* S;         // [H+1+C][H+1]
     float* whi;       // [nad][H][D]   tf32-exact part of W1 (tensor-core GEMM-1 operand)
     float* wlo;       // [nad][H][D]   W1 - whi
+    float* part;      // [16][H][D]    batch-chunk partial tiles of dW1 (tensor-core path)
     size_t accum_bytes;  // bytes of the zeroed region at the start (colsum, dgb, gram, S)
     size_t total;
 };
@@ -120,11 +121,12 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     size_t o_ds = take(sizeof(float) * (size_t)B * C);
     size_t o_whi = take(sizeof(float) * (size_t)nad * H * D);
     size_t o_wlo = take(sizeof(float) * (size_t)nad * H * D);
+    size_t o_part = take(sizeof(float) * (size_t)16 * H * D);
     w.total = off;
     w.colsum = (double*)(p + o_colsum); w.dgb = (double*)(p + o_dgb);
     w.A = (float*)(p + o_A); w.hbuf = (float*)(p + o_h); w.dahat = (float*)(p + o_da);
     w.cvec = (float*)(p + o_c); w.ds = (float*)(p + o_ds); w.gram = (float*)(p + o_gram); w.S = (float*)(p + o_S);
-    w.whi = (float*)(p + o_whi); w.wlo = (float*)(p + o_wlo);
+    w.whi = (float*)(p + o_whi); w.wlo = (float*)(p + o_wlo); w.part = (float*)(p + o_part);
     return w;
 }
 

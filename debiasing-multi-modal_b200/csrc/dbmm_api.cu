@@ -6,6 +6,8 @@
 
 #include "gemm1_tc.cuh"
 #include "kernels_simt.cuh"
+#include "rows_train.cuh"
+#include "wgrad_tc.cuh"
 
 namespace dbmm {
 
@@ -93,6 +95,12 @@ static bool use_tc_gemm1(int D, int H) {
     const char* e = getenv("DBMM_GEMM1");          // debugging switch: DBMM_GEMM1=simt forces the fp32 SIMT kernel
     if (e && strcmp(e, "simt") == 0) return false;
     return (D % G1_BK == 0) && (H % 32 == 0);
+}
+
+static bool use_tc_wgrad(int D, int H) {
+    const char* e = getenv("DBMM_WGRAD");          // debugging switch: DBMM_WGRAD=simt forces the fp32 SIMT kernel
+    if (e && strcmp(e, "simt") == 0) return false;
+    return (D % WG_TILE == 0) && (H % 4 == 0) && H <= WG_TILE;
 }
 
 // a = x W1^T + b1 for one or two adapters (+ fp64 column sums).  whi/wlo: scratch [nad][H][D] each.
@@ -241,37 +249,43 @@ int dbmm_train_step(int phases,
         if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, true, st)) return rc;
     }
     if (phases & DBMM_PHASE_ROWS) {
-        RowsArgs ra;
+        RowsTrainArgs ra;
         memset(&ra, 0, sizeof(ra));
-        ra.N = B; ra.pos0 = 0; ra.idx = idx; ra.y = y; ra.grp = grp; ra.H = H; ra.C = C; ra.G = G;
-        ra.A = w.A; ra.strideA = (int64_t)B * H; ra.gram = w.gram; ra.colsum = w.colsum; ra.Bg = B_global;
+        ra.B = B; ra.Bg = B_global; ra.idx = idx; ra.y = y; ra.grp = grp; ra.H = H; ra.C = C; ra.G = G;
+        ra.A = w.A; ra.strideA = (int64_t)B * H; ra.gram = w.gram; ra.colsum = w.colsum;
         ra.ad[0] = view_of(old_ad ? old_ad : ad); ra.ad[1] = view_of(ad);
         ra.w_old = ebd_weight; ra.inv_tau = inv_tau; ra.inv_B = 1.0f / (float)B_global;
-        ra.logits_out = nullptr; ra.pred_out = nullptr;
-        ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.batch_size = 1; ra.slot_fixed = slot;
-        ra.hbuf = w.hbuf; ra.dahat = w.dahat; ra.cvec = w.cvec; ra.ds = w.ds; ra.dgb = w.dgb;
-        if (int rc = launch_rows<true>(ra, nad, H, C, st)) return rc;
+        ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.slot = slot;
+        ra.dahat = w.dahat; ra.dgb = w.dgb; ra.S = w.S;
+        if (int rc = launch_rows_train(ra, nad, st)) return rc;
     }
     if (phases & DBMM_PHASE_WGRAD) {
-        WgradArgs wa;
-        wa.X = X; wa.ldx = ldx; wa.idx = idx; wa.B = B; wa.Bg = B_global; wa.D = D; wa.H = H; wa.C = C;
-        wa.A = w.A + (size_t)(nad - 1) * B * H; wa.dahat = w.dahat; wa.hbuf = w.hbuf; wa.cvec = w.cvec; wa.ds = w.ds;
-        wa.colsum = w.colsum + (size_t)(nad - 1) * 2 * H; wa.dgb = w.dgb; wa.gamma = ad->gamma;
-        wa.gW1 = grads + oW1; wa.S = w.S;
-        wa.tiles_w1_m = ceil_div(H, GT_BM); wa.tiles_w1_n = ceil_div(D, GT_BN);
-        wa.tiles_s_m = ceil_div(H + 1 + C, GT_BM); wa.tiles_s_n = ceil_div(H + 1, GT_BN);
-        wa.ksplit = ksplit;
-        if (ksplit > 1) DBMM_CUDA(cudaMemsetAsync(grads + oW1, 0, sizeof(float) * (size_t)H * D, st));   // S is zeroed with the sums
-        dim3 grid(wa.tiles_w1_m * wa.tiles_w1_n + wa.tiles_s_m * wa.tiles_s_n, ksplit);
-        k_wgrad<<<grid, GT_THREADS, 0, st>>>(wa);
-        DBMM_LAUNCH_CHECK();
-        W2gradArgs w2;
-        w2.W2 = ad->W2; w2.b2 = ad->b2; w2.That = That; w2.S = w.S; w2.dgb = w.dgb;
-        w2.gW2 = grads + oW2; w2.gb2 = grads + ob2; w2.ggamma = grads + og; w2.gbeta = grads + obeta; w2.gb1 = grads + ob1;
-        w2.D = D; w2.H = H; w2.C = C;
-        dim3 grid2(ceil_div(D, GT_BM), ceil_div(H + 1, GT_BN));
-        k_w2grad<<<grid2, GT_THREADS, 0, st>>>(w2);
-        DBMM_LAUNCH_CHECK();
+        const bool tc = use_tc_wgrad(D, H);
+        int nchunk = 0;
+        const float* A_t = w.A + (size_t)(nad - 1) * B * H;
+        const double* colsum_t = w.colsum + (size_t)(nad - 1) * 2 * H;
+        if (tc) {
+            WgradTcArgs t;
+            t.X = X; t.ldx = ldx; t.idx = idx; t.B = B; t.Bg = B_global; t.D = D; t.H = H;
+            t.A = A_t; t.dahat = w.dahat; t.colsum = colsum_t; t.dgb = w.dgb; t.gamma = ad->gamma; t.part = w.part;
+            nchunk = wgrad_tc_chunks(B, &t.rows_per_chunk);
+            if (int rc = launch_wgrad_tc(t, nchunk, st)) return rc;
+        } else {
+            WgradArgs wa;
+            wa.X = X; wa.ldx = ldx; wa.idx = idx; wa.B = B; wa.Bg = B_global; wa.D = D; wa.H = H;
+            wa.A = A_t; wa.dahat = w.dahat; wa.colsum = colsum_t; wa.dgb = w.dgb; wa.gamma = ad->gamma;
+            wa.gW1 = grads + oW1; wa.tiles_m = ceil_div(H, GT_BM); wa.tiles_n = ceil_div(D, GT_BN); wa.ksplit = ksplit;
+            if (ksplit > 1) DBMM_CUDA(cudaMemsetAsync(grads + oW1, 0, sizeof(float) * (size_t)H * D, st));
+            dim3 grid(wa.tiles_m * wa.tiles_n, ksplit);
+            k_wgrad<<<grid, GT_THREADS, 0, st>>>(wa);
+            DBMM_LAUNCH_CHECK();
+        }
+        FinalizeArgs fa;
+        fa.part = tc ? w.part : nullptr; fa.nchunk = nchunk;
+        fa.W2 = ad->W2; fa.b2 = ad->b2; fa.That = That; fa.S = w.S; fa.dgb = w.dgb;
+        fa.gW1 = grads + oW1; fa.gb1 = grads + ob1; fa.ggamma = grads + og; fa.gbeta = grads + obeta;
+        fa.gW2 = grads + oW2; fa.gb2 = grads + ob2; fa.D = D; fa.H = H; fa.C = C; fa.n_w1_ctas = 0;
+        if (int rc = launch_finalize(fa, st)) return rc;
     }
     if (phases & DBMM_PHASE_UPDATE) {
         DBMM_CHECK_ARG(momentum_buf != nullptr, "NULL momentum buffer");

@@ -1,0 +1,340 @@
+// Training row kernel (H-space, see kernels_simt.cuh header):  BatchNorm -> ReLU -> t = [h,1] G -> logits -> CE ->
+// row backward (dL/d ahat) -> per-batch reductions (dgamma, dbeta, S = [c*h | c | ds]^T [h | 1]) in ONE launch.
+//
+// A CTA owns RT_ROWS = 8 batch rows and 8 warps.  The (H+1)-long contraction t = [h,1] G is split over the WARPS
+// (17 Gram rows each, all 8 batch rows at once, 40 accumulators per lane) and combined through shared memory, so the
+// dependent-FMA chain per warp is 17 long instead of 129.  Afterwards warp w finishes row w (softmax-CE, argmax,
+// group counters, dh, BatchNorm-backward inputs), and the CTA adds its 8-row share of S with coalesced fp32 reds.
+#pragma once
+#include "kernels_simt.cuh"
+
+namespace dbmm {
+
+constexpr int RT_ROWS = 8, RT_WARPS = 8, RT_THREADS = RT_WARPS * 32;
+
+struct RowsTrainArgs {
+    int B; int64_t Bg;
+    const int32_t* idx; const int32_t* y; const int32_t* grp;
+    int H, C, G;
+    const float* A; int64_t strideA;      // [nad][B][H]
+    const float* gram;                    // [nad][H+1][H+1+C]
+    const double* colsum;                 // [nad][2][H]
+    AdapterView ad[2];
+    float w_old, inv_tau, inv_B;
+    double* loss_sum; int64_t* counts; int64_t slot;
+    float* dahat; double* dgb; float* S;  // outputs: [B][H], [2][H] (+=), [H+1+C][H+1] (+=)
+};
+
+static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT) {
+    const size_t ldg = H + 1 + C;
+    size_t fl = rows_gram_floats(H, C, nad) + (size_t)nad * 4 * H + (size_t)RT_ROWS * (H + 1)      // sG, sBN, sH
+              + (size_t)RT_WARPS * RT_ROWS * RK_NSLOT * 32                                          // sT
+              + (size_t)RT_ROWS * ldg + 3 * 32 + (size_t)RT_ROWS * CT + 2 * (size_t)H;              // sL, row stats, sLo, sDgb
+    return fl * 4 + 16;
+}
+
+template <int NAD, int CT>
+__global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
+    extern __shared__ __align__(16) float dyn_smem[];
+    const int H = a.H, C = a.C, ldg = H + 1 + C, HP = H + 1;
+    const int HS = (H + 31) >> 5, NS = (ldg + 31) >> 5;
+    float* sG = dyn_smem;
+    float* sBN = sG + rows_gram_floats_dev(H, C, NAD);
+    float* sH = sBN + (size_t)NAD * 4 * H;                               // [RT_ROWS][H+1]
+    float* sT = sH + (size_t)RT_ROWS * HP;                               // [RT_WARPS][RT_ROWS][RK_NSLOT*32]
+    float* sL = sT + (size_t)RT_WARPS * RT_ROWS * RK_NSLOT * 32;         // [RT_ROWS][ldg]
+    float* sRowNll = sL + (size_t)RT_ROWS * ldg;
+    int* sRowG = reinterpret_cast<int*>(sRowNll + 32);
+    int* sRowCorr = sRowG + 32;
+    float* sLo = reinterpret_cast<float*>(sRowCorr + 32);                // [RT_ROWS][CT]
+    float* sDgb = sLo + (size_t)RT_ROWS * CT;                            // [2][H]
+    constexpr int TSTR = RK_NSLOT * 32;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int ADT = NAD - 1;
+
+    {
+        const int n = NAD * HP * ldg, n4 = n >> 2;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sG);
+        for (int e = tid; e < n4; e += RT_THREADS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + e * 16), "l"(a.gram + e * 4) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int e = (n4 << 2) + tid; e < n; e += RT_THREADS) sG[e] = a.gram[e];
+    }
+    for (int e = tid; e < NAD * H; e += RT_THREADS) {
+        const int ad = e / H, j = e - ad * H;
+        const double s1 = a.colsum[((size_t)ad * 2 + 0) * H + j], s2 = a.colsum[((size_t)ad * 2 + 1) * H + j];
+        const double m = s1 / (double)a.Bg;
+        double v = s2 / (double)a.Bg - m * m;
+        if (v < 0.0) v = 0.0;
+        float* bn = sBN + (size_t)ad * 4 * H;
+        bn[j] = (float)m; bn[H + j] = 1.0f / sqrtf((float)v + DBMM_BN_EPS);
+        bn[2 * H + j] = a.ad[ad].gamma[j]; bn[3 * H + j] = a.ad[ad].beta[j];
+    }
+    for (int e = tid; e < 2 * H; e += RT_THREADS) sDgb[e] = 0.f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    float dg_acc[RK_HSLOT], db_acc[RK_HSLOT];
+#pragma unroll
+    for (int s = 0; s < RK_HSLOT; ++s) { dg_acc[s] = 0.f; db_acc[s] = 0.f; }
+    const float coef = (NAD == 2) ? (1.0f - a.w_old) : 1.0f;
+    const int IR = (HP + RT_WARPS - 1) / RT_WARPS;             // Gram rows per warp
+    const int MR = (ldg + RT_WARPS - 1) / RT_WARPS;            // S rows per warp
+
+    for (int base = blockIdx.x * RT_ROWS; base < a.B; base += gridDim.x * RT_ROWS) {
+        const int r = base + warp;                             // this warp's batch row
+        const bool valid = r < a.B;
+        float t[RK_NSLOT], hv[RK_HSLOT], ahat[RK_HSLOT];
+        unsigned prepos = 0u;
+        float n2 = 1.f, sc[CT];
+
+#pragma unroll
+        for (int ad = 0; ad < NAD; ++ad) {
+            const float* bn = sBN + (size_t)ad * 4 * H;
+            const float* G = sG + (size_t)ad * HP * ldg;
+            // ---- phase 1: h = relu(BN(a)) for row `warp`
+            prepos = 0u;
+            float* hrow = sH + (size_t)warp * HP;
+#pragma unroll
+            for (int s = 0; s < RK_HSLOT; ++s) {
+                const int j = lane + 32 * s;
+                float h = 0.f, ah = 0.f;
+                if (s < HS && j < H && valid) {
+                    const float av = __ldcg(a.A + (size_t)ad * a.strideA + (size_t)r * H + j);
+                    ah = (av - bn[j]) * bn[H + j];
+                    const float pre = fmaf(ah, bn[2 * H + j], bn[3 * H + j]);
+                    if (pre > 0.f) { h = pre; prepos |= (1u << s); }
+                }
+                hv[s] = h; ahat[s] = ah;
+                if (s < HS && j < H) hrow[j] = h;
+            }
+            if (lane == 0) hrow[H] = valid ? 1.0f : 0.f;
+            __syncthreads();
+            // ---- phase 2: partial t over this warp's Gram rows, all RT_ROWS batch rows
+            {
+                float acc[RT_ROWS][RK_NSLOT];
+#pragma unroll
+                for (int rr = 0; rr < RT_ROWS; ++rr)
+#pragma unroll
+                    for (int s = 0; s < RK_NSLOT; ++s) acc[rr][s] = 0.f;
+                const int i0 = warp * IR, i1 = min(HP, i0 + IR);
+#pragma unroll 2
+                for (int i = i0; i < i1; ++i) {
+                    float g[RK_NSLOT];
+#pragma unroll
+                    for (int s = 0; s < RK_NSLOT; ++s) {
+                        const int j = lane + 32 * s;
+                        g[s] = (s < NS && j < ldg) ? G[(size_t)i * ldg + j] : 0.f;
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < RT_ROWS; ++rr) {
+                        const float hh = sH[(size_t)rr * HP + i];
+#pragma unroll
+                        for (int s = 0; s < RK_NSLOT; ++s) acc[rr][s] = fmaf(hh, g[s], acc[rr][s]);
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < RT_ROWS; ++rr)
+#pragma unroll
+                    for (int s = 0; s < RK_NSLOT; ++s) sT[((size_t)warp * RT_ROWS + rr) * TSTR + lane + 32 * s] = acc[rr][s];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < RK_NSLOT; ++s) {
+                float v = 0.f;
+#pragma unroll
+                for (int w2 = 0; w2 < RT_WARPS; ++w2) v += sT[((size_t)w2 * RT_ROWS + warp) * TSTR + lane + 32 * s];
+                t[s] = v;
+            }
+            // ---- n^2 and the C prompt scores of this adapter (row `warp`)
+            {
+                float part = 0.f;
+#pragma unroll
+                for (int s = 0; s < RK_HSLOT; ++s) part = fmaf(t[s], hv[s], part);
+#pragma unroll
+                for (int s = 0; s < RK_NSLOT; ++s)
+                    if (lane + 32 * s == H) part += t[s];
+                n2 = warp_sum(part);
+#pragma unroll
+                for (int c = 0; c < CT; ++c) {
+                    float v = 0.f;
+                    if (c < C) {
+                        const int col = H + 1 + c;
+#pragma unroll
+                        for (int s = 0; s < RK_NSLOT; ++s) {
+                            const float tmp = __shfl_sync(0xffffffffu, t[s], col & 31);
+                            if (s == (col >> 5)) v = tmp;
+                        }
+                    }
+                    sc[c] = v;
+                }
+                if (NAD == 2 && ad == 0) {
+                    const float inv_n = 1.0f / sqrtf(n2);
+                    if (lane < CT) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int c = 0; c < CT; ++c) if (c == lane) v = sc[c];
+                        sLo[(size_t)warp * CT + lane] = a.w_old * a.inv_tau * v * inv_n;
+                    }
+                    __syncthreads();          // sH / sT are rewritten by the next adapter
+                }
+            }
+        }
+
+        // ---- phase 3: row epilogue (trainable adapter)
+        float nll = 0.f; int gval = -1, corr = 0;
+        float cc = 0.f, dsv[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) dsv[c] = 0.f;
+        if (valid) {
+            const int64_t dsrow = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
+            const int yv = a.y[dsrow];
+            gval = a.grp ? a.grp[dsrow] : 0;
+            const float inv_n = 1.0f / sqrtf(n2);
+            float lnew[CT], l[CT];
+            float mx = -INFINITY; int am = 0;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                lnew[c] = 0.f; l[c] = -INFINITY;
+                if (c < C) {
+                    lnew[c] = a.inv_tau * sc[c] * inv_n;
+                    l[c] = (NAD == 2) ? fmaf(coef, lnew[c], sLo[(size_t)warp * CT + c]) : lnew[c];
+                    if (l[c] > mx) { mx = l[c]; am = c; }
+                }
+            }
+            float se = 0.f, ly = 0.f, p[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                p[c] = 0.f;
+                if (c < C) { p[c] = expf(l[c] - mx); se += p[c]; if (c == yv) ly = l[c]; }
+            }
+            nll = logf(se) + mx - ly;
+            corr = (am == yv) ? 1 : 0;
+            const float inv_se = 1.0f / se;
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                if (c < C) {
+                    const float dl = (p[c] * inv_se - (c == yv ? 1.f : 0.f)) * a.inv_B;
+                    dot = fmaf(dl, lnew[c], dot);
+                    dsv[c] = coef * dl * a.inv_tau * inv_n;
+                }
+            }
+            cc = -coef * dot / n2;
+            const float* G = sG + (size_t)ADT * HP * ldg;
+            const float* bn = sBN + (size_t)ADT * 4 * H;
+#pragma unroll
+            for (int s = 0; s < RK_HSLOT; ++s) {
+                const int j = lane + 32 * s;
+                if (s < HS && j < H) {
+                    float dh = cc * t[s];
+#pragma unroll
+                    for (int c = 0; c < CT; ++c)
+                        if (c < C) dh = fmaf(dsv[c], G[(size_t)j * ldg + H + 1 + c], dh);
+                    const float dpre = ((prepos >> s) & 1u) ? dh : 0.f;
+                    dg_acc[s] = fmaf(dpre, ahat[s], dg_acc[s]);
+                    db_acc[s] += dpre;
+                    a.dahat[(size_t)r * H + j] = dpre * bn[2 * H + j];
+                }
+            }
+        }
+        // L row = [c*h | c | ds] for the S reduction (zeros for rows past the batch end)
+        {
+            float* lrow = sL + (size_t)warp * ldg;
+#pragma unroll
+            for (int s = 0; s < RK_HSLOT; ++s) {
+                const int j = lane + 32 * s;
+                if (s < HS && j < H) lrow[j] = cc * hv[s];
+            }
+            if (lane == 0) lrow[H] = cc;
+            if (lane < C) {
+                float v = 0.f;
+#pragma unroll
+                for (int c = 0; c < CT; ++c) if (c == lane) v = dsv[c];
+                lrow[H + 1 + lane] = v;
+            }
+        }
+        if (lane == 0) { sRowNll[warp] = nll; sRowG[warp] = gval; sRowCorr[warp] = corr; }
+        __syncthreads();
+
+        // ---- loss / group counters of these 8 rows: one atomic per group (update_dict, final_main.py:383-391)
+        if (warp == 0) {
+            const int gv = lane < RT_ROWS ? sRowG[lane] : -1;
+            const int cr = lane < RT_ROWS ? sRowCorr[lane] : 0;
+            const float nl = lane < RT_ROWS ? sRowNll[lane] : 0.f;
+            const double tot = warp_sum((double)nl);
+            if (lane == 0 && a.loss_sum) atomicAdd(&a.loss_sum[a.slot], tot);
+            const unsigned cmask = __ballot_sync(0xffffffffu, cr != 0);
+            for (int g = 0; g < a.G; ++g) {
+                const unsigned gm = __ballot_sync(0xffffffffu, gv == g);
+                if (lane == 0 && gm && a.counts) {
+                    int64_t* cnt = a.counts + (size_t)a.slot * 2 * a.G;
+                    const int nc = __popc(gm & cmask);
+                    if (nc) atomicAdd((unsigned long long*)&cnt[g], (unsigned long long)nc);
+                    atomicAdd((unsigned long long*)&cnt[a.G + g], (unsigned long long)__popc(gm));
+                }
+            }
+        }
+        // ---- phase 4: S[m][n] += sum_rows L[row][m] * [h | 1][row][n]   (warp w owns MR rows m; lanes own n)
+        {
+            float Rr[RT_ROWS][RK_NSLOT];
+#pragma unroll
+            for (int rr = 0; rr < RT_ROWS; ++rr)
+#pragma unroll
+                for (int s = 0; s < RK_NSLOT; ++s) {
+                    const int n = lane + 32 * s;
+                    Rr[rr][s] = (n < HP) ? sH[(size_t)rr * HP + n] : 0.f;
+                }
+            const int m0 = warp * MR, m1 = min(ldg, m0 + MR);
+            for (int m = m0; m < m1; ++m) {
+                float v[RK_NSLOT];
+#pragma unroll
+                for (int s = 0; s < RK_NSLOT; ++s) v[s] = 0.f;
+#pragma unroll
+                for (int rr = 0; rr < RT_ROWS; ++rr) {
+                    const float l = sL[(size_t)rr * ldg + m];
+#pragma unroll
+                    for (int s = 0; s < RK_NSLOT; ++s) v[s] = fmaf(l, Rr[rr][s], v[s]);
+                }
+#pragma unroll
+                for (int s = 0; s < RK_NSLOT; ++s) {
+                    const int n = lane + 32 * s;
+                    if (n < HP) atomicAdd(&a.S[(size_t)m * HP + n], v[s]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int s = 0; s < RK_HSLOT; ++s) {
+        const int j = lane + 32 * s;
+        if (s < HS && j < H) { atomicAdd(&sDgb[j], dg_acc[s]); atomicAdd(&sDgb[H + j], db_acc[s]); }
+    }
+    __syncthreads();
+    for (int e = tid; e < 2 * H; e += RT_THREADS) atomicAdd(&a.dgb[e], (double)sDgb[e]);
+}
+
+static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) {
+    const int CT = ra.C <= 4 ? 4 : 16;
+    const size_t smem = rows_train_smem_bytes(ra.H, ra.C, nad, CT);
+    DBMM_CHECK_SHAPE(smem <= 227 * 1024, "train row kernel needs %zu bytes of shared memory", smem);
+    int grid = ceil_div(ra.B, RT_ROWS);
+    if (grid > 148 * 2) grid = 148 * 2;
+#define DBMM_RT_CASE(NAD_, CT_)                                                                           \
+    do {                                                                                                  \
+        auto kern = k_rows_train<NAD_, CT_>;                                                              \
+        DBMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        kern<<<grid, RT_THREADS, smem, st>>>(ra);                                                         \
+    } while (0)
+    if (nad == 1 && CT == 4) DBMM_RT_CASE(1, 4);
+    else if (nad == 1) DBMM_RT_CASE(1, 16);
+    else if (CT == 4) DBMM_RT_CASE(2, 4);
+    else DBMM_RT_CASE(2, 16);
+#undef DBMM_RT_CASE
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+}  // namespace dbmm
