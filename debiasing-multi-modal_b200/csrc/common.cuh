@@ -62,6 +62,17 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Every kernel of the training step asks for the same L1 / shared-memory split (maximum shared): consecutive kernels
+// with different carve-outs force the SMs to drain and reconfigure between launches.
+template <typename K>
+static inline cudaError_t set_smem(K kern, size_t dyn_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes);
+}
+
+__host__ __device__ static inline int s_stride(int H) { return (H + 1 + 3) & ~3; }     // row stride of the S matrix
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -87,20 +98,22 @@ static inline AdapterView view_of(const dbmm_adapter* a) {
 }
 
 // Train-step workspace carve-up (all offsets in bytes, 256-byte aligned).
+constexpr int DBMM_LR_TABLE = 65536;          // learning rates (one per step) a single epoch graph can address
+constexpr int DBMM_G1_PART_ROWS = 16384;      // ksplit * nad * ceil128(B) never exceeds this (see gemm1_ksplit)
+
 struct TrainWs {
-    double* colsum;   // [nad][2][H]   sum a, sum a^2         (zeroed every step)
-    double* dgb;      // [2][H]        dgamma, dbeta          (zeroed every step)
-    float* A;         // [nad][B][H]   pre-BatchNorm activations
-    float* hbuf;      // [B][H]        relu output of the trainable adapter
-    float* dahat;     // [B][H]        dL/d(normalised activation)
-    float* cvec;      // [B]           c = -(dl . l_new) / n^2
-    float* ds;        // [B][C]        dL/ds
+    double* colsum;   // [nad][2][H]   sum a, sum a^2         (zero at the start of every step)
+    double* dgb;      // [2][H]        dgamma, dbeta          (zero at the start of every step)
+    float* S;         // [H+1+C][SP]   batch reduction for dW2, SP = H+1 rounded up to 4 (zero at the start of every step)
     float* gram;      // [nad][H+1][H+1+C]
-    float* S;         // [H+1+C][H+1]
+    float* A;         // [nad][B][H]   pre-BatchNorm activations
+    float* dahat;     // [B][H]        dL/d(normalised activation)
     float* whi;       // [nad][H][D]   tf32-exact part of W1 (tensor-core GEMM-1 operand)
     float* wlo;       // [nad][H][D]   W1 - whi
     float* part;      // [16][H][D]    batch-chunk partial tiles of dW1 (tensor-core path)
-    size_t accum_bytes;  // bytes of the zeroed region at the start (colsum, dgb, gram, S)
+    float* g1part;    // [ksplit][nad][B][H] D-slice partial tiles of GEMM-1
+    float* lr;        // [DBMM_LR_TABLE] per-step learning rates of the running epoch
+    size_t accum_bytes;  // bytes of the zeroed region at the start (colsum, dgb, S, gram)
     size_t total;
 };
 
@@ -111,22 +124,22 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_colsum = take(sizeof(double) * nad * 2 * H);
     size_t o_dgb = take(sizeof(double) * 2 * H);
-    size_t o_gram = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));     // split-K targets: zeroed with the sums
-    size_t o_S = take(sizeof(float) * (size_t)(H + 1 + C) * (H + 1));
+    size_t o_S = take(sizeof(float) * (size_t)(H + 1 + C) * s_stride(H));
+    size_t o_gram = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));     // split-K target: zeroed with the sums
     w.accum_bytes = off;
     size_t o_A = take(sizeof(float) * (size_t)nad * B * H);
-    size_t o_h = take(sizeof(float) * (size_t)B * H);
     size_t o_da = take(sizeof(float) * (size_t)B * H);
-    size_t o_c = take(sizeof(float) * (size_t)B);
-    size_t o_ds = take(sizeof(float) * (size_t)B * C);
     size_t o_whi = take(sizeof(float) * (size_t)nad * H * D);
     size_t o_wlo = take(sizeof(float) * (size_t)nad * H * D);
     size_t o_part = take(sizeof(float) * (size_t)16 * H * D);
+    size_t o_g1 = take(sizeof(float) * (size_t)(DBMM_G1_PART_ROWS + 2 * 128) * H);
+    size_t o_lr = take(sizeof(float) * DBMM_LR_TABLE);
     w.total = off;
     w.colsum = (double*)(p + o_colsum); w.dgb = (double*)(p + o_dgb);
-    w.A = (float*)(p + o_A); w.hbuf = (float*)(p + o_h); w.dahat = (float*)(p + o_da);
-    w.cvec = (float*)(p + o_c); w.ds = (float*)(p + o_ds); w.gram = (float*)(p + o_gram); w.S = (float*)(p + o_S);
+    w.A = (float*)(p + o_A); w.dahat = (float*)(p + o_da);
+    w.gram = (float*)(p + o_gram); w.S = (float*)(p + o_S);
     w.whi = (float*)(p + o_whi); w.wlo = (float*)(p + o_wlo); w.part = (float*)(p + o_part);
+    w.g1part = (float*)(p + o_g1); w.lr = (float*)(p + o_lr);
     return w;
 }
 

@@ -8,6 +8,10 @@
 #include "kernels_simt.cuh"
 #include "rows_train.cuh"
 #include "wgrad_tc.cuh"
+#include "update.cuh"
+
+#include <mutex>
+#include <vector>
 
 namespace dbmm {
 
@@ -51,7 +55,7 @@ static int launch_rows(const RowsArgs& ra, int nad, int H, int C, cudaStream_t s
 #define DBMM_ROWS_LAUNCH(NAD_, CT_, RB_, NW_)                                                             \
     do {                                                                                                  \
         auto kern = k_rows<TRAIN, NAD_, CT_, RB_, NW_>;                                                   \
-        DBMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        DBMM_CUDA(set_smem(kern, smem));    \
         kern<<<grid, NW_ * 32, smem, st>>>(ra);                                                           \
     } while (0)
 #define DBMM_ROWS_CASE(NAD_, CT_)                                                                         \
@@ -103,10 +107,22 @@ static bool use_tc_wgrad(int D, int H) {
     return (D % WG_TILE == 0) && (H % 4 == 0) && H <= WG_TILE;
 }
 
+// D-slices of the tensor-core GEMM-1 for a training batch: enough CTAs to pull the batch through ~128 SMs at once.
+static int gemm1_ksplit(int B, int nad, int D) {
+    const int kb_all = D / G1_BK;
+    int ks = 128 / (ceil_div(B, G1_BM) * nad);
+    if (ks > 16) ks = 16;
+    if (ks > kb_all / 2) ks = kb_all / 2;
+    if (ks < 1) ks = 1;
+    const int kb_per = (kb_all + ks - 1) / ks;
+    return (kb_all + kb_per - 1) / kb_per;           // no empty slice
+}
+
 // a = x W1^T + b1 for one or two adapters (+ fp64 column sums).  whi/wlo: scratch [nad][H][D] each.
+// ksplit > 1 (training): D-sliced partial tiles into `g1part`, finished by k_reduce_stats.
 static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t pos0, int B, int D, int H,
                         const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, double* colsum,
-                        float* whi, float* wlo, bool split_weights, cudaStream_t st) {
+                        float* whi, float* wlo, bool split_weights, int ksplit, float* g1part, cudaStream_t st) {
     const int nad = old_ad ? 2 : 1;
     if (!use_tc_gemm1(D, H)) {
         Gemm1Args g;
@@ -127,10 +143,19 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
         }
     }
     if (nad == 1) { t.Whi[1] = t.Whi[0]; t.Wlo[1] = t.Wlo[0]; t.b1[1] = t.b1[0]; }
-    t.A = A; t.colsum = colsum;
+    t.A = A; t.colsum = colsum; t.ksplit = ksplit; t.part = g1part;
     int bn = 128;
-    if (B <= 4096) bn = (H % 32 == 0) ? 32 : H;      // few row tiles: narrow hidden slices -> more CTAs pulling operands
-    return launch_gemm1_tc(t, bn, st);
+    if (ksplit == 1 && B <= 4096) bn = (H % 32 == 0) ? 32 : H;      // few row tiles: narrow hidden slices -> more CTAs
+    if (int rc = launch_gemm1_tc(t, bn, st)) return rc;
+    if (ksplit > 1) {
+        ReduceStatsArgs r;
+        r.part = g1part; r.ksplit = ksplit; r.nad = nad; r.B = B; r.H = H; r.b1[0] = t.b1[0]; r.b1[1] = t.b1[1];
+        r.A = A; r.colsum = colsum;
+        DBMM_CUDA(set_smem(k_reduce_stats, 0));
+        k_reduce_stats<<<dim3(ceil_div(B, RS_ROWS), nad), RS_THREADS, 0, st>>>(r);
+        DBMM_LAUNCH_CHECK();
+    }
+    return DBMM_OK;
 }
 
 }  // namespace dbmm
@@ -204,7 +229,7 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
     if (int rc = launch_gram(old_ad, ad, That, gram, D, H, C, st)) return rc;
     for (int64_t pos0 = 0; pos0 < N; pos0 += EVAL_CHUNK) {
         const int B = (int)((N - pos0) < EVAL_CHUNK ? (N - pos0) : EVAL_CHUNK);
-        if (int rc = launch_gemm1(X, ldx, idx, pos0, B, D, H, old_ad, ad, A, nullptr, whi, wlo, pos0 == 0, st)) return rc;
+        if (int rc = launch_gemm1(X, ldx, idx, pos0, B, D, H, old_ad, ad, A, nullptr, whi, wlo, pos0 == 0, 1, nullptr, st)) return rc;
         RowsArgs ra;
         memset(&ra, 0, sizeof(ra));
         ra.N = B; ra.pos0 = pos0; ra.idx = idx; ra.y = y; ra.grp = grp; ra.H = H; ra.C = C; ra.G = G;
@@ -218,35 +243,31 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
     return DBMM_OK;
 }
 
-int dbmm_train_step(int phases,
-                    const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
-                    int B_local, int64_t B_global, int D, int H, int C, int G,
-                    const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
-                    const float* That, float inv_tau,
-                    float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
-                    dbmm_batch_stats stats, int64_t slot,
-                    void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = check_dims(D, H, C, G)) return rc;
-    if (int rc = check_adapter(ad, "trainable")) return rc;
-    if (old_ad) if (int rc = check_adapter(old_ad, "old")) return rc;
-    DBMM_CHECK_ARG(X && y && That && ws && grads, "NULL X / y / That / workspace / grads");
-    DBMM_CHECK_ARG(B_local >= 1 && B_global >= B_local && ldx >= D, "bad B_local=%d B_global=%lld ldx=%lld",
-                   B_local, (long long)B_global, (long long)ldx);
-    // torch.nn.BatchNorm1d in train mode: "Expected more than 1 value per channel when training"
-    DBMM_CHECK_ARG(B_global > 1, "BatchNorm needs more than 1 row per batch in training (got %lld)", (long long)B_global);
+// One training step.  fresh: first step of an API call -- the accumulators are zeroed, the Gram matrices and the tf32
+// weight splits are computed from scratch; otherwise the previous step's k_finalize_grads / k_update left them ready.
+// lr_dev != nullptr: the learning rate is read from device memory by the update kernel (CUDA-graph replay).
+static int train_step_impl(int phases, bool fresh,
+                           const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                           int B, int64_t B_global, int D, int H, int C, int G,
+                           const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                           const float* That, float inv_tau,
+                           float* grads, float* momentum_buf, float lr, const float* lr_dev, float momentum, float weight_decay,
+                           dbmm_batch_stats stats, int64_t slot, const TrainWs& w, cudaStream_t st) {
     const int nad = old_ad ? 2 : 1;
-    const int B = B_local;
-    TrainWs w = carve_train_ws(ws, B, D, H, C, nad);
-    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
-    const size_t np = dbmm_param_count(D, H);
     const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
-    const int ksplit = B >= 512 ? (B / 256 > 16 ? 16 : B / 256) : 1;   // split the batch reduction over more CTAs
+    const size_t gram_floats = (size_t)(H + 1) * (H + 1 + C);
+    float* gram_t = w.gram + (size_t)(nad - 1) * gram_floats;
+    const bool tc1 = use_tc_gemm1(D, H);
+    static const int skip = getenv("DBMM_SKIP") ? atoi(getenv("DBMM_SKIP")) : 0;   // timing experiments only: drop kernels by bit mask
+    if (skip) phases &= ~skip;
 
     if (phases & DBMM_PHASE_GEMM1) {
-        DBMM_CUDA(cudaMemsetAsync(ws, 0, w.accum_bytes, st));
-        if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
-        if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, true, st)) return rc;
+        if (fresh) {
+            DBMM_CUDA(cudaMemsetAsync(w.colsum, 0, w.accum_bytes, st));
+            if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
+        }
+        const int ks = tc1 ? gemm1_ksplit(B, nad, D) : 1;
+        if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, fresh, ks, w.g1part, st)) return rc;
     }
     if (phases & DBMM_PHASE_ROWS) {
         RowsTrainArgs ra;
@@ -264,13 +285,14 @@ int dbmm_train_step(int phases,
         int nchunk = 0;
         const float* A_t = w.A + (size_t)(nad - 1) * B * H;
         const double* colsum_t = w.colsum + (size_t)(nad - 1) * 2 * H;
-        if (tc) {
+        if (tc && !(skip & 32)) {
             WgradTcArgs t;
             t.X = X; t.ldx = ldx; t.idx = idx; t.B = B; t.Bg = B_global; t.D = D; t.H = H;
             t.A = A_t; t.dahat = w.dahat; t.colsum = colsum_t; t.dgb = w.dgb; t.gamma = ad->gamma; t.part = w.part;
             nchunk = wgrad_tc_chunks(B, &t.rows_per_chunk);
             if (int rc = launch_wgrad_tc(t, nchunk, st)) return rc;
         } else {
+            const int ksplit = B >= 512 ? (B / 256 > 16 ? 16 : B / 256) : 1;
             WgradArgs wa;
             wa.X = X; wa.ldx = ldx; wa.idx = idx; wa.B = B; wa.Bg = B_global; wa.D = D; wa.H = H;
             wa.A = A_t; wa.dahat = w.dahat; wa.colsum = colsum_t; wa.dgb = w.dgb; wa.gamma = ad->gamma;
@@ -285,23 +307,86 @@ int dbmm_train_step(int phases,
         fa.W2 = ad->W2; fa.b2 = ad->b2; fa.That = That; fa.S = w.S; fa.dgb = w.dgb;
         fa.gW1 = grads + oW1; fa.gb1 = grads + ob1; fa.ggamma = grads + og; fa.gbeta = grads + obeta;
         fa.gW2 = grads + oW2; fa.gb2 = grads + ob2; fa.D = D; fa.H = H; fa.C = C; fa.n_w1_ctas = 0;
-        if (int rc = launch_finalize(fa, st)) return rc;
+        fa.gb_scale = (float)((double)B / (double)B_global);
+        fa.gram_zero = gram_t; fa.gram_floats = (int)gram_floats;
+        if (!(skip & 16)) if (int rc = launch_finalize(fa, st)) return rc;
     }
     if (phases & DBMM_PHASE_UPDATE) {
-        DBMM_CHECK_ARG(momentum_buf != nullptr, "NULL momentum buffer");
-        SgdArgs sa;
-        sa.p[0] = ad->W1; sa.p[1] = ad->b1; sa.p[2] = ad->gamma; sa.p[3] = ad->beta; sa.p[4] = ad->W2; sa.p[5] = ad->b2;
-        sa.off[0] = oW1; sa.off[1] = ob1; sa.off[2] = og; sa.off[3] = obeta; sa.off[4] = oW2; sa.off[5] = ob2; sa.off[6] = np;
-        sa.g = grads; sa.v = momentum_buf; sa.lr = lr; sa.momentum = momentum; sa.wd = weight_decay; sa.first = first_step; sa.vec4 = (H % 4 == 0 && D % 4 == 0) ? 1 : 0;
-        sa.nad = nad; sa.H = H; sa.Bg = B_global; sa.colsum = w.colsum;
+        UpdateArgs ua;
+        memset(&ua, 0, sizeof(ua));
+        ua.W1 = ad->W1; ua.b1 = ad->b1; ua.gamma = ad->gamma; ua.beta = ad->beta; ua.W2 = ad->W2; ua.b2 = ad->b2;
+        ua.g = grads; ua.v = momentum_buf; ua.lr_dev = lr_dev; ua.lr = lr; ua.momentum = momentum; ua.wd = weight_decay;
+        ua.whi = tc1 ? w.whi + (size_t)(nad - 1) * H * D : nullptr; ua.wlo = tc1 ? w.wlo + (size_t)(nad - 1) * H * D : nullptr;
+        ua.That = That; ua.gram = gram_t;
+        ua.D = D; ua.H = H; ua.C = C; ua.nad = nad; ua.Bg = B_global;
+        ua.colsum = w.colsum; ua.dgb = w.dgb; ua.S = w.S; ua.zero_accum = 1;
         const dbmm_adapter* a0 = old_ad ? old_ad : ad;
-        sa.rm[0] = a0->running_mean; sa.rv[0] = a0->running_var; sa.nbt[0] = (long long*)a0->num_batches_tracked;
-        sa.rm[1] = ad->running_mean; sa.rv[1] = ad->running_var; sa.nbt[1] = (long long*)ad->num_batches_tracked;
-        k_sgd<<<ceil_div((int64_t)np, 4 * 256) < 1 ? 1 : ceil_div((int64_t)np, 4 * 256), 256, 0, st>>>(sa);
-        DBMM_LAUNCH_CHECK();
+        ua.rm[0] = a0->running_mean; ua.rv[0] = a0->running_var; ua.nbt[0] = (long long*)a0->num_batches_tracked;
+        ua.rm[1] = ad->running_mean; ua.rv[1] = ad->running_var; ua.nbt[1] = (long long*)ad->num_batches_tracked;
+        if (int rc = launch_update(ua, st)) return rc;
     }
     return DBMM_OK;
 }
+
+static int check_train_args(const float* X, int64_t ldx, const int32_t* y, int B_local, int64_t B_global, int D, int H, int C,
+                            int G, const dbmm_adapter* old_ad, const dbmm_adapter* ad, const float* That, void* ws,
+                            float* grads) {
+    if (int rc = check_dims(D, H, C, G)) return rc;
+    DBMM_CHECK_SHAPE(H % 4 == 0, "H=%d must be a multiple of 4", H);
+    if (int rc = check_adapter(ad, "trainable")) return rc;
+    if (old_ad) if (int rc = check_adapter(old_ad, "old")) return rc;
+    DBMM_CHECK_ARG(X && y && That && ws && grads, "NULL X / y / That / workspace / grads");
+    DBMM_CHECK_ARG(B_local >= 1 && B_global >= B_local && ldx >= D, "bad B_local=%d B_global=%lld ldx=%lld",
+                   B_local, (long long)B_global, (long long)ldx);
+    // torch.nn.BatchNorm1d in train mode: "Expected more than 1 value per channel when training"
+    DBMM_CHECK_ARG(B_global > 1, "BatchNorm needs more than 1 row per batch in training (got %lld)", (long long)B_global);
+    return DBMM_OK;
+}
+
+int dbmm_train_step(int phases,
+                    const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                    int B_local, int64_t B_global, int D, int H, int C, int G,
+                    const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                    const float* That, float inv_tau,
+                    float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
+                    dbmm_batch_stats stats, int64_t slot,
+                    void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_train_args(X, ldx, y, B_local, B_global, D, H, C, G, old_ad, ad, That, ws, grads)) return rc;
+    const int nad = old_ad ? 2 : 1;
+    TrainWs w = carve_train_ws(ws, B_local, D, H, C, nad);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    if (phases & DBMM_PHASE_UPDATE) {
+        DBMM_CHECK_ARG(momentum_buf != nullptr, "NULL momentum buffer");
+        // torch SGD: the momentum buffer starts as a copy of the first gradient == the recurrence from v = 0
+        if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * dbmm_param_count(D, H), st));
+    }
+    return train_step_impl(phases, true, X, ldx, idx, y, grp, B_local, B_global, D, H, C, G, old_ad, ad, ebd_weight, That,
+                           inv_tau, grads, momentum_buf, lr, nullptr, momentum, weight_decay, stats, slot, w, st);
+}
+
+namespace dbmm {
+
+// ---- epoch graphs: the ~6 kernels x steps of one epoch are captured once per distinct argument set and replayed; a
+// dependent kernel boundary inside a graph costs ~0.5 us on B200 against ~3.5 us as a stream launch (profiles/r1_ubench.txt)
+struct EpochKey {
+    const void* X; int64_t ldx; const void* order; int64_t n_rows; int batch_size; const void* y; const void* grp;
+    int D, H, C, G; dbmm_adapter old_ad; dbmm_adapter ad; int has_old; float ebd_weight; const void* That; float inv_tau;
+    const void* grads; const void* mom; float momentum, wd; const void* loss_sum; const void* counts; const void* ws; int device;
+};
+struct EpochGraph { EpochKey key; cudaGraphExec_t exec; uint64_t stamp; };
+static std::mutex g_graph_mu;
+static std::vector<EpochGraph> g_graphs;
+static uint64_t g_graph_clock = 0;
+static cudaStream_t g_capture_stream[64] = {};
+constexpr size_t MAX_EPOCH_GRAPHS = 24;
+
+static bool graphs_enabled() {
+    const char* e = getenv("DBMM_GRAPH");          // debugging switch: DBMM_GRAPH=0 replays the epoch as stream launches
+    return !(e && strcmp(e, "0") == 0);
+}
+
+}  // namespace dbmm
 
 int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
                      const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
@@ -310,17 +395,70 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
                      float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
                      int first_step, dbmm_batch_stats stats,
                      void* ws, size_t ws_bytes, void* stream) {
-    DBMM_CHECK_ARG(order && lr_host, "NULL order / lr table");
+    cudaStream_t st = (cudaStream_t)stream;
+    DBMM_CHECK_ARG(order && lr_host && momentum_buf, "NULL order / lr table / momentum buffer");
     DBMM_CHECK_ARG(n_rows >= 1 && batch_size >= 1, "bad n_rows=%lld batch_size=%d", (long long)n_rows, batch_size);
     const int64_t steps = (n_rows + batch_size - 1) / batch_size;
-    for (int64_t s = 0; s < steps; ++s) {
-        const int64_t p0 = s * batch_size;
-        const int B = (int)((n_rows - p0) < batch_size ? (n_rows - p0) : batch_size);
-        int rc = dbmm_train_step(DBMM_PHASE_ALL, X, ldx, order + p0, y, grp, B, B, D, H, C, G, old_ad, ad, ebd_weight,
-                                 That, inv_tau, grads, momentum_buf, lr_host[s], momentum, weight_decay,
-                                 (first_step && s == 0) ? 1 : 0, stats, s, ws, ws_bytes, stream);
-        if (rc) return rc;
+    const int B0 = (int)(n_rows < batch_size ? n_rows : batch_size);
+    const int64_t last_B = n_rows - (steps - 1) * batch_size;
+    if (int rc = check_train_args(X, ldx, y, B0, B0, D, H, C, G, old_ad, ad, That, ws, grads)) return rc;
+    DBMM_CHECK_ARG(last_B > 1, "BatchNorm needs more than 1 row per batch in training (trailing batch of %lld)", (long long)last_B);
+    DBMM_CHECK_ARG(steps <= DBMM_LR_TABLE, "an epoch of %lld steps exceeds the %d-entry learning-rate table", (long long)steps, DBMM_LR_TABLE);
+    const int nad = old_ad ? 2 : 1;
+    TrainWs w = carve_train_ws(ws, B0, D, H, C, nad);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+
+    if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * dbmm_param_count(D, H), st));
+    DBMM_CUDA(cudaMemcpyAsync(w.lr, lr_host, sizeof(float) * (size_t)steps, cudaMemcpyHostToDevice, st));
+
+    auto enqueue = [&](cudaStream_t s_) -> int {
+        for (int64_t s = 0; s < steps; ++s) {
+            const int64_t p0 = s * batch_size;
+            const int B = (int)((n_rows - p0) < batch_size ? (n_rows - p0) : batch_size);
+            int rc = train_step_impl(DBMM_PHASE_ALL, s == 0, X, ldx, order + p0, y, grp, B, B, D, H, C, G, old_ad, ad, ebd_weight,
+                                     That, inv_tau, grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, s_);
+            if (rc) return rc;
+        }
+        return DBMM_OK;
+    };
+    if (!graphs_enabled() || steps < 4) return enqueue(st);
+
+    int device = 0;
+    DBMM_CUDA(cudaGetDevice(&device));
+    EpochKey key;
+    memset(&key, 0, sizeof(key));
+    key.X = X; key.ldx = ldx; key.order = order; key.n_rows = n_rows; key.batch_size = batch_size; key.y = y; key.grp = grp;
+    key.D = D; key.H = H; key.C = C; key.G = G; key.ad = *ad; key.has_old = old_ad ? 1 : 0; if (old_ad) key.old_ad = *old_ad;
+    key.ebd_weight = ebd_weight; key.That = That; key.inv_tau = inv_tau; key.grads = grads; key.mom = momentum_buf;
+    key.momentum = momentum; key.wd = weight_decay; key.loss_sum = stats.loss_sum; key.counts = stats.counts; key.ws = ws;
+    key.device = device;
+
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : g_graphs)
+        if (memcmp(&g.key, &key, sizeof(key)) == 0) { exec = g.exec; g.stamp = ++g_graph_clock; break; }
+    if (!exec) {
+        DBMM_CHECK_ARG(device >= 0 && device < 64, "device index %d out of range", device);
+        if (!g_capture_stream[device]) DBMM_CUDA(cudaStreamCreateWithFlags(&g_capture_stream[device], cudaStreamNonBlocking));
+        cudaStream_t cs = g_capture_stream[device];
+        DBMM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue(cs);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) { set_error("stream capture of the epoch failed: %s", cudaGetErrorString(ce)); return DBMM_ERR_CUDA; }
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); return DBMM_ERR_CUDA; }
+        if (g_graphs.size() >= MAX_EPOCH_GRAPHS) {
+            size_t victim = 0;
+            for (size_t i = 1; i < g_graphs.size(); ++i) if (g_graphs[i].stamp < g_graphs[victim].stamp) victim = i;
+            cudaGraphExecDestroy(g_graphs[victim].exec);
+            g_graphs.erase(g_graphs.begin() + victim);
+        }
+        g_graphs.push_back(EpochGraph{key, exec, ++g_graph_clock});
     }
+    DBMM_CUDA(cudaGraphLaunch(exec, st));
     return DBMM_OK;
 }
 

@@ -23,6 +23,8 @@ struct Gemm1TcArgs {
     const float* Whi[2]; const float* Wlo[2]; const float* b1[2];   // per adapter, [H][D] / [H]
     float* A;          // [nad][B][H]
     double* colsum;    // [nad][2][H] or nullptr
+    int ksplit;        // > 1: blockIdx.z owns a slice of D and stores its raw partial tile (no bias, no sums) to
+    float* part;       //      part[kpart][nad][B][H]; k_reduce_stats finishes the job
 };
 
 __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ w, float* __restrict__ hi,
@@ -63,7 +65,10 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
     const int slices = a.H / BN;                        // hidden slices per adapter
     const int ad = blockIdx.y / slices;
     const int n0 = (blockIdx.y - ad * slices) * BN;     // first hidden unit of this CTA
-    const int KB = a.D / G1_BK;
+    const int KB_all = a.D / G1_BK;
+    const int kb_per = (KB_all + a.ksplit - 1) / a.ksplit;
+    const int kb_lo = blockIdx.z * kb_per;
+    const int KB = max(0, min(KB_all, kb_lo + kb_per) - kb_lo);      // k-blocks of this CTA (host guarantees >= 1)
 
     if (tid < G1_BM) {
         int m = m0 + tid;
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
             ptx::mbar_wait(&empty[s], ((kb / S) & 1) ^ 1);
             uint8_t* stage = smem + (size_t)s * Cfg::STAGE_BYTES;
             const uint32_t sA = ptx::smem_u32(stage);
-            const int k0 = kb * G1_BK;
+            const int k0 = (kb_lo + kb) * G1_BK;
 #pragma unroll
             for (int id = tid; id < G1_BM * 8; id += G1_PRODUCERS) {
                 const int row = id >> 3, c = id & 7;
@@ -135,6 +140,16 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
             ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + ch * 32, r);
             ptx::tmem_ld_wait();
             float v[32];
+            if (a.ksplit > 1) {
+                if (row_ok) {
+                    float* prow = a.part + (((size_t)blockIdx.z * a.nad + ad) * a.B + m) * a.H + n0 + ch * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(prow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(bias + ch * 32 + j);
             if (row_ok) {
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
         }
         ptx::tc_fence_before_sync();
         asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
-        if (a.colsum && tid < BN) {
+        if (a.ksplit == 1 && a.colsum && tid < BN) {
             atomicAdd(&a.colsum[((size_t)ad * 2 + 0) * a.H + n0 + tid], sCol[0][tid]);
             atomicAdd(&a.colsum[((size_t)ad * 2 + 1) * a.H + n0 + tid], sCol[1][tid]);
         }
@@ -191,8 +206,8 @@ template <int BN, int TERMS>
 static int launch_gemm1_tc_impl(const Gemm1TcArgs& a, cudaStream_t st) {
     using Cfg = G1Cfg<BN, TERMS>;
     auto kern = k_gemm1_tc<BN, TERMS>;
-    DBMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    dim3 grid(ceil_div(a.B, G1_BM), a.nad * (a.H / BN));
+    DBMM_CUDA(set_smem(kern, Cfg::SMEM));
+    dim3 grid(ceil_div(a.B, G1_BM), a.nad * (a.H / BN), a.ksplit);
     kern<<<grid, G1_THREADS, Cfg::SMEM, st>>>(a);
     DBMM_LAUNCH_CHECK();
     return DBMM_OK;
@@ -201,12 +216,72 @@ static int launch_gemm1_tc_impl(const Gemm1TcArgs& a, cudaStream_t st) {
 // BN: hidden units per CTA.  Small batches use narrow slices so that more SMs pull operands concurrently.
 static int launch_gemm1_tc(const Gemm1TcArgs& a, int bn, cudaStream_t st) {
     DBMM_CHECK_SHAPE(a.D % G1_BK == 0, "tensor-core GEMM-1 needs D %% 32 == 0 (D=%d)", a.D);
+    DBMM_CHECK_ARG(a.ksplit >= 1 && (a.ksplit - 1) * ((a.D / G1_BK + a.ksplit - 1) / a.ksplit) < a.D / G1_BK,
+                   "GEMM-1 split of D into %d parts leaves an empty part", a.ksplit);
     DBMM_CHECK_SHAPE(a.H % bn == 0, "H=%d not divisible by the hidden slice %d", a.H, bn);
     switch (bn) {
         case 128: return launch_gemm1_tc_impl<128, 2>(a, st);
         case 64: return launch_gemm1_tc_impl<64, 2>(a, st);
         case 32: return launch_gemm1_tc_impl<32, 2>(a, st);
         default: set_error("unsupported hidden slice %d", bn); return DBMM_ERR_UNSUPPORTED_SHAPE;
+    }
+}
+
+}  // namespace dbmm
+
+namespace dbmm {
+
+// A[ad][b][:] = b1 + sum over the D-slices' partial tiles, plus the fp64 BatchNorm column sums (train only).
+struct ReduceStatsArgs {
+    const float* part; int ksplit, nad, B, H;
+    const float* b1[2];
+    float* A;          // [nad][B][H]
+    double* colsum;    // [nad][2][H] or nullptr
+};
+constexpr int RS_ROWS = 16, RS_MAXK = 16, RS_THREADS = 256;
+
+// 256 threads = 8 row lanes x 32 column quads (H <= 128), two rows per thread; the D-slice partials of one element are
+// fetched together (RS_MAXK independent 16-byte loads in flight) before they are summed.  Few, fat CTAs on purpose:
+// the fp64 column-sum atomics of all CTAs hit the same 2H addresses and the L2 serialises them (~40 cycles each).
+__global__ void __launch_bounds__(RS_THREADS) k_reduce_stats(ReduceStatsArgs a) {
+    __shared__ float sS[2][8][DBMM_MAX_H];
+    const int H = a.H, H4 = H >> 2;
+    const int ad = blockIdx.y;
+    const int tid = threadIdx.x, q = tid >> 5, c = tid & 31;
+    const size_t plane = (size_t)a.nad * a.B * H;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < H4) {
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(a.b1[ad]) + c);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = blockIdx.x * RS_ROWS + q + 8 * half;
+            if (r >= a.B) continue;
+            const size_t off = ((size_t)ad * a.B + r) * H + c * 4;
+            float4 v[RS_MAXK];
+#pragma unroll
+            for (int kp = 0; kp < RS_MAXK; ++kp)
+                v[kp] = kp < a.ksplit ? __ldcg(reinterpret_cast<const float4*>(a.part + kp * plane + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 acc = bias;
+#pragma unroll
+            for (int kp = 0; kp < RS_MAXK; ++kp) { acc.x += v[kp].x; acc.y += v[kp].y; acc.z += v[kp].z; acc.w += v[kp].w; }
+            *reinterpret_cast<float4*>(a.A + off) = acc;
+            s1[0] += acc.x; s1[1] += acc.y; s1[2] += acc.z; s1[3] += acc.w;
+            s2[0] = fmaf(acc.x, acc.x, s2[0]); s2[1] = fmaf(acc.y, acc.y, s2[1]);
+            s2[2] = fmaf(acc.z, acc.z, s2[2]); s2[3] = fmaf(acc.w, acc.w, s2[3]);
+        }
+    }
+    if (!a.colsum) return;
+    if (c < H4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sS[0][q][c * 4 + e] = s1[e]; sS[1][q][c * 4 + e] = s2[e]; }
+    }
+    __syncthreads();
+    for (int e = tid; e < 2 * H; e += RS_THREADS) {
+        const int which = e / H, j = e - which * H;
+        double v = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) v += (double)sS[which][rr][j];
+        atomicAdd(&a.colsum[((size_t)ad * 2 + which) * H + j], v);
     }
 }
 

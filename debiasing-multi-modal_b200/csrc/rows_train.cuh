@@ -1,16 +1,16 @@
 // Training row kernel (H-space, see kernels_simt.cuh header):  BatchNorm -> ReLU -> t = [h,1] G -> logits -> CE ->
 // row backward (dL/d ahat) -> per-batch reductions (dgamma, dbeta, S = [c*h | c | ds]^T [h | 1]) in ONE launch.
 //
-// A CTA owns RT_ROWS = 8 batch rows and 8 warps.  The (H+1)-long contraction t = [h,1] G is split over the WARPS
-// (17 Gram rows each, all 8 batch rows at once, 40 accumulators per lane) and combined through shared memory, so the
-// dependent-FMA chain per warp is 17 long instead of 129.  Afterwards warp w finishes row w (softmax-CE, argmax,
-// group counters, dh, BatchNorm-backward inputs), and the CTA adds its 8-row share of S with coalesced fp32 reds.
+// A CTA owns RT_ROWS = 8 batch rows and 16 warps.  The (H+1)-long contraction t = [h,1] G is split over the WARPS
+// (9 Gram rows each, all 8 batch rows at once, 40 accumulators per lane) and combined through shared memory, so the
+// dependent-FMA chain per warp is 9 long instead of 129.  Afterwards warp w < 8 finishes row w (softmax-CE, argmax,
+// group counters, dh, BatchNorm-backward inputs), and all warps add the CTA's 8-row share of S with coalesced reds.
 #pragma once
 #include "kernels_simt.cuh"
 
 namespace dbmm {
 
-constexpr int RT_ROWS = 8, RT_WARPS = 8, RT_THREADS = RT_WARPS * 32;
+constexpr int RT_ROWS = 8;      // batch rows per CTA; NW warps per CTA (16 for one adapter, 8 when two Gram matrices fill the smem)
 
 struct RowsTrainArgs {
     int B; int64_t Bg;
@@ -25,7 +25,7 @@ struct RowsTrainArgs {
     float* dahat; double* dgb; float* S;  // outputs: [B][H], [2][H] (+=), [H+1+C][H+1] (+=)
 };
 
-static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT) {
+static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT, int RT_WARPS) {
     const size_t ldg = H + 1 + C;
     size_t fl = rows_gram_floats(H, C, nad) + (size_t)nad * 4 * H + (size_t)RT_ROWS * (H + 1)      // sG, sBN, sH
               + (size_t)RT_WARPS * RT_ROWS * RK_NSLOT * 32                                          // sT
@@ -33,8 +33,9 @@ static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT) {
     return fl * 4 + 16;
 }
 
-template <int NAD, int CT>
-__global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
+template <int NAD, int CT, int NW>
+__global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
+    constexpr int RT_WARPS = NW, RT_THREADS = NW * 32;
     extern __shared__ __align__(16) float dyn_smem[];
     const int H = a.H, C = a.C, ldg = H + 1 + C, HP = H + 1;
     const int HS = (H + 31) >> 5, NS = (ldg + 31) >> 5;
@@ -61,6 +62,16 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
         asm volatile("cp.async.commit_group;" ::: "memory");
         for (int e = (n4 << 2) + tid; e < n; e += RT_THREADS) sG[e] = a.gram[e];
     }
+    // first row group's activations (adapter 0): in flight while the Gram matrix and the statistics arrive
+    float av_pre[RK_HSLOT];
+    {
+        const int r = blockIdx.x * RT_ROWS + warp;
+#pragma unroll
+        for (int s = 0; s < RK_HSLOT; ++s) {
+            const int j = lane + 32 * s;
+            av_pre[s] = (warp < RT_ROWS && s < HS && j < H && r < a.B) ? __ldcg(a.A + (size_t)r * H + j) : 0.f;
+        }
+    }
     for (int e = tid; e < NAD * H; e += RT_THREADS) {
         const int ad = e / H, j = e - ad * H;
         const double s1 = a.colsum[((size_t)ad * 2 + 0) * H + j], s2 = a.colsum[((size_t)ad * 2 + 1) * H + j];
@@ -83,8 +94,15 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
     const int MR = (ldg + RT_WARPS - 1) / RT_WARPS;            // S rows per warp
 
     for (int base = blockIdx.x * RT_ROWS; base < a.B; base += gridDim.x * RT_ROWS) {
-        const int r = base + warp;                             // this warp's batch row
-        const bool valid = r < a.B;
+        const int r = base + warp;                             // this warp's batch row (warps >= RT_ROWS own none)
+        const bool owner = warp < RT_ROWS;
+        const bool valid = owner && r < a.B;
+        int yv = -1, gval = -1;                                // labels of this row: requested before the long phases
+        if (valid) {
+            const int64_t dsrow = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
+            yv = a.y[dsrow];
+            gval = a.grp ? a.grp[dsrow] : 0;
+        }
         float t[RK_NSLOT], hv[RK_HSLOT], ahat[RK_HSLOT];
         unsigned prepos = 0u;
         float n2 = 1.f, sc[CT];
@@ -101,15 +119,16 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
                 const int j = lane + 32 * s;
                 float h = 0.f, ah = 0.f;
                 if (s < HS && j < H && valid) {
-                    const float av = __ldcg(a.A + (size_t)ad * a.strideA + (size_t)r * H + j);
+                    const float av = (ad == 0 && base == (int)blockIdx.x * RT_ROWS)
+                                         ? av_pre[s] : __ldcg(a.A + (size_t)ad * a.strideA + (size_t)r * H + j);
                     ah = (av - bn[j]) * bn[H + j];
                     const float pre = fmaf(ah, bn[2 * H + j], bn[3 * H + j]);
                     if (pre > 0.f) { h = pre; prepos |= (1u << s); }
                 }
                 hv[s] = h; ahat[s] = ah;
-                if (s < HS && j < H) hrow[j] = h;
+                if (owner && s < HS && j < H) hrow[j] = h;
             }
-            if (lane == 0) hrow[H] = valid ? 1.0f : 0.f;
+            if (owner && lane == 0) hrow[H] = valid ? 1.0f : 0.f;
             __syncthreads();
             // ---- phase 2: partial t over this warp's Gram rows, all RT_ROWS batch rows
             {
@@ -143,8 +162,10 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
 #pragma unroll
             for (int s = 0; s < RK_NSLOT; ++s) {
                 float v = 0.f;
+                if (owner) {
 #pragma unroll
-                for (int w2 = 0; w2 < RT_WARPS; ++w2) v += sT[((size_t)w2 * RT_ROWS + warp) * TSTR + lane + 32 * s];
+                    for (int w2 = 0; w2 < RT_WARPS; ++w2) v += sT[((size_t)w2 * RT_ROWS + warp) * TSTR + lane + 32 * s];
+                }
                 t[s] = v;
             }
             // ---- n^2 and the C prompt scores of this adapter (row `warp`)
@@ -171,7 +192,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
                 }
                 if (NAD == 2 && ad == 0) {
                     const float inv_n = 1.0f / sqrtf(n2);
-                    if (lane < CT) {
+                    if (owner && lane < CT) {
                         float v = 0.f;
 #pragma unroll
                         for (int c = 0; c < CT; ++c) if (c == lane) v = sc[c];
@@ -183,14 +204,11 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
         }
 
         // ---- phase 3: row epilogue (trainable adapter)
-        float nll = 0.f; int gval = -1, corr = 0;
+        float nll = 0.f; int corr = 0;
         float cc = 0.f, dsv[CT];
 #pragma unroll
         for (int c = 0; c < CT; ++c) dsv[c] = 0.f;
         if (valid) {
-            const int64_t dsrow = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
-            const int yv = a.y[dsrow];
-            gval = a.grp ? a.grp[dsrow] : 0;
             const float inv_n = 1.0f / sqrtf(n2);
             float lnew[CT], l[CT];
             float mx = -INFINITY; int am = 0;
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
             }
         }
         // L row = [c*h | c | ds] for the S reduction (zeros for rows past the batch end)
-        {
+        if (owner) {
             float* lrow = sL + (size_t)warp * ldg;
 #pragma unroll
             for (int s = 0; s < RK_HSLOT; ++s) {
@@ -255,7 +273,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
                 lrow[H + 1 + lane] = v;
             }
         }
-        if (lane == 0) { sRowNll[warp] = nll; sRowG[warp] = gval; sRowCorr[warp] = corr; }
+        if (owner && lane == 0) { sRowNll[warp] = nll; sRowG[warp] = gval; sRowCorr[warp] = corr; }
         __syncthreads();
 
         // ---- loss / group counters of these 8 rows: one atomic per group (update_dict, final_main.py:383-391)
@@ -286,7 +304,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
                     const int n = lane + 32 * s;
                     Rr[rr][s] = (n < HP) ? sH[(size_t)rr * HP + n] : 0.f;
                 }
-            const int m0 = warp * MR, m1 = min(ldg, m0 + MR);
+            const int m0 = warp * MR, m1 = min(ldg, m0 + MR), SP = s_stride(H);
             for (int m = m0; m < m1; ++m) {
                 float v[RK_NSLOT];
 #pragma unroll
@@ -300,7 +318,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
 #pragma unroll
                 for (int s = 0; s < RK_NSLOT; ++s) {
                     const int n = lane + 32 * s;
-                    if (n < HP) atomicAdd(&a.S[(size_t)m * HP + n], v[s]);
+                    if (n < HP) atomicAdd(&a.S[(size_t)m * SP + n], v[s]);
                 }
             }
         }
@@ -318,20 +336,21 @@ __global__ void __launch_bounds__(RT_THREADS) k_rows_train(RowsTrainArgs a) {
 
 static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) {
     const int CT = ra.C <= 4 ? 4 : 16;
-    const size_t smem = rows_train_smem_bytes(ra.H, ra.C, nad, CT);
+    const int nw = nad == 1 ? 16 : 8;
+    const size_t smem = rows_train_smem_bytes(ra.H, ra.C, nad, CT, nw);
     DBMM_CHECK_SHAPE(smem <= 227 * 1024, "train row kernel needs %zu bytes of shared memory", smem);
     int grid = ceil_div(ra.B, RT_ROWS);
     if (grid > 148 * 2) grid = 148 * 2;
-#define DBMM_RT_CASE(NAD_, CT_)                                                                           \
+#define DBMM_RT_CASE(NAD_, CT_, NW_)                                                                      \
     do {                                                                                                  \
-        auto kern = k_rows_train<NAD_, CT_>;                                                              \
-        DBMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        kern<<<grid, RT_THREADS, smem, st>>>(ra);                                                         \
+        auto kern = k_rows_train<NAD_, CT_, NW_>;                                                         \
+        DBMM_CUDA(set_smem(kern, smem));    \
+        kern<<<grid, NW_ * 32, smem, st>>>(ra);                                                           \
     } while (0)
-    if (nad == 1 && CT == 4) DBMM_RT_CASE(1, 4);
-    else if (nad == 1) DBMM_RT_CASE(1, 16);
-    else if (CT == 4) DBMM_RT_CASE(2, 4);
-    else DBMM_RT_CASE(2, 16);
+    if (nad == 1 && CT == 4) DBMM_RT_CASE(1, 4, 16);
+    else if (nad == 1) DBMM_RT_CASE(1, 16, 16);
+    else if (CT == 4) DBMM_RT_CASE(2, 4, 8);
+    else DBMM_RT_CASE(2, 16, 8);
 #undef DBMM_RT_CASE
     DBMM_LAUNCH_CHECK();
     return DBMM_OK;

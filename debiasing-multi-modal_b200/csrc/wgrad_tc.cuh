@@ -72,6 +72,69 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     const int n_sub = (b_end - b_begin + WG_BK - 1) / WG_BK;     // >= 1: the host never launches empty chunks
     const int H = a.H;
 
+    // ---- producer helpers (warps 0-3).  A thread owns 16 chunk ids per 64-row stage: id = tid + 128 * i,
+    // row = id / 32 (batch row inside the stage), c16 = id % 32 (16-byte chunk along the 128-float tile edge).
+    auto issue_x = [&](int sub) {            // X tile: gathered through the batch's index list, straight into shared memory
+        const uint32_t sX = ptx::smem_u32(smem + (size_t)(sub % WG_STAGES) * WG_STAGE_BYTES) + 2 * WG_OP_BYTES;
+        const int b0 = b_begin + sub * WG_BK;
+        int64_t roff[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int b = b0 + ((tid + 128 * i) >> 5);
+            if (b >= b_end) b = b_end - 1;                        // tail rows: any finite values (da is 0 there)
+            roff[i] = (a.idx ? (int64_t)__ldg(a.idx + b) : (int64_t)b) * a.ldx;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int id = tid + 128 * i, row = id >> 5, c16 = id & 31;
+            ptx::cp_async16(sX + wg_tile_offset(row, c16), a.X + roff[i] + d0 + c16 * 4);
+        }
+        ptx::cp_async_commit();
+    };
+    auto load_da = [&](int sub, int half, float4 (&av)[8], float4 (&dv)[8]) {
+        const int b0 = b_begin + sub * WG_BK;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int id = tid + 128 * (half * 8 + i), b = b0 + (id >> 5), j = (id & 31) * 4;
+            av[i] = make_float4(0.f, 0.f, 0.f, 0.f); dv[i] = av[i];
+            if (b < b_end && j < H) {
+                av[i] = __ldcg(reinterpret_cast<const float4*>(a.A + (size_t)b * H + j));
+                dv[i] = __ldcg(reinterpret_cast<const float4*>(a.dahat + (size_t)b * H + j));
+            }
+        }
+    };
+    auto store_da = [&](int sub, int half, const float4 (&av)[8], const float4 (&dv)[8]) {
+        uint8_t* stage = smem + (size_t)(sub % WG_STAGES) * WG_STAGE_BYTES;
+        const int b0 = b_begin + sub * WG_BK;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int id = tid + 128 * (half * 8 + i), row = id >> 5, c16 = id & 31;
+            const int b = b0 + row, j = c16 * 4;
+            float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+            if (b < b_end && j < H) {
+                const float ax[4] = {av[i].x, av[i].y, av[i].z, av[i].w}, dx[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+                float h4[4], l4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float rstd = sCst[1][j + q];
+                    const float ah = (ax[q] - sCst[0][j + q]) * rstd;
+                    const float da = (dx[q] - sCst[2][j + q] - ah * sCst[3][j + q]) * rstd;
+                    h4[q] = __uint_as_float(__float_as_uint(da) & 0xffffe000u);
+                    l4[q] = da - h4[q];
+                }
+                hi = make_float4(h4[0], h4[1], h4[2], h4[3]);
+                lo = make_float4(l4[0], l4[1], l4[2], l4[3]);
+            }
+            const uint32_t off = wg_tile_offset(row, c16);
+            *reinterpret_cast<float4*>(stage + off) = hi;
+            *reinterpret_cast<float4*>(stage + WG_OP_BYTES + off) = lo;
+        }
+    };
+
+    // everything that does not depend on the set-up barrier is requested first: stage 0's X tile and half of its
+    // A / dahat values are in flight while the statistics are turned into BatchNorm constants
+    float4 av[8], dv[8];
+    if (warp < 4) { issue_x(0); load_da(0, 0, av, dv); }
     if (tid < WG_TILE) {
         float mu = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
         if (tid < H) {
@@ -100,46 +163,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
         // ===================== producers =====================
         for (int sub = 0; sub < n_sub; ++sub) {
             const int s = sub % WG_STAGES;
-            ptx::mbar_wait(&empty[s], ((sub / WG_STAGES) & 1) ^ 1);
-            uint8_t* stage = smem + (size_t)s * WG_STAGE_BYTES;
-            const uint32_t sX = ptx::smem_u32(stage) + 2 * WG_OP_BYTES;
-            const int b0 = b_begin + sub * WG_BK;
-            // X tile: 64 rows x 512 bytes, gathered through the batch's index list
-#pragma unroll 4
-            for (int id = tid; id < WG_BK * 32; id += 128) {
-                const int row = id >> 5, c16 = id & 31;
-                int b = b0 + row;
-                if (b >= b_end) b = b_end - 1;                    // tail rows: any finite values (da is 0 there)
-                const int64_t r = a.idx ? (int64_t)__ldg(a.idx + b) : (int64_t)b;
-                ptx::cp_async16(sX + wg_tile_offset(row, c16), a.X + r * a.ldx + d0 + c16 * 4);
+            if (sub > 0) {
+                ptx::mbar_wait(&empty[s], ((sub / WG_STAGES) & 1) ^ 1);
+                issue_x(sub);
+                load_da(sub, 0, av, dv);
             }
-            ptx::cp_async_commit();
-            // da tile (hi / lo), computed while the X copies are in flight
-#pragma unroll 2
-            for (int id = tid; id < WG_BK * 32; id += 128) {
-                const int row = id >> 5, c16 = id & 31;
-                const int b = b0 + row, j = c16 * 4;
-                float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
-                if (b < b_end && j < H) {
-                    const float4 av = __ldg(reinterpret_cast<const float4*>(a.A + (size_t)b * H + j));
-                    const float4 dv = __ldg(reinterpret_cast<const float4*>(a.dahat + (size_t)b * H + j));
-                    const float ax[4] = {av.x, av.y, av.z, av.w}, dx[4] = {dv.x, dv.y, dv.z, dv.w};
-                    float h4[4], l4[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float rstd = sCst[1][j + q];
-                        const float ah = (ax[q] - sCst[0][j + q]) * rstd;
-                        const float da = (dx[q] - sCst[2][j + q] - ah * sCst[3][j + q]) * rstd;
-                        h4[q] = __uint_as_float(__float_as_uint(da) & 0xffffe000u);
-                        l4[q] = da - h4[q];
-                    }
-                    hi = make_float4(h4[0], h4[1], h4[2], h4[3]);
-                    lo = make_float4(l4[0], l4[1], l4[2], l4[3]);
-                }
-                const uint32_t off = wg_tile_offset(row, c16);
-                *reinterpret_cast<float4*>(stage + off) = hi;
-                *reinterpret_cast<float4*>(stage + WG_OP_BYTES + off) = lo;
-            }
+            store_da(sub, 0, av, dv);
+            load_da(sub, 1, av, dv);
+            store_da(sub, 1, av, dv);
             ptx::cp_async_wait<0>();
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(&full[s]);
@@ -201,7 +232,7 @@ static inline int wgrad_tc_chunks(int B, int* rows_per_chunk) {
 
 static int launch_wgrad_tc(const WgradTcArgs& a, int nchunk, cudaStream_t st) {
     DBMM_CHECK_SHAPE(a.D % WG_TILE == 0 && a.H <= WG_TILE && a.H % 4 == 0, "tensor-core dW1 needs D %% 128 == 0 and H <= 128 (D=%d H=%d)", a.D, a.H);
-    DBMM_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
+    DBMM_CUDA(set_smem(k_wgrad_tc, WG_SMEM));
     dim3 grid(a.D / WG_TILE, nchunk);
     k_wgrad_tc<<<grid, WG_THREADS, WG_SMEM, st>>>(a);
     DBMM_LAUNCH_CHECK();
@@ -213,41 +244,49 @@ static int launch_wgrad_tc(const WgradTcArgs& a, int nchunk, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 struct FinalizeArgs {
     const float* part; int nchunk;        // [nchunk][H][D], or nullptr when gW1 was produced directly
-    const float* W2; const float* b2; const float* That; const float* S;   // S: [H+1+C][H+1]
+    const float* W2; const float* b2; const float* That; const float* S;   // S: [H+1+C][s_stride(H)]
     const double* dgb;
     float* gW1; float* gb1; float* ggamma; float* gbeta; float* gW2; float* gb2;
     int D, H, C;
     int n_w1_ctas;
+    float gb_scale;        // B_local / B_global: dgb holds GLOBAL sums under data parallelism, the flat gradient is summed over ranks
+    float* gram_zero; int gram_floats;     // Gram matrix of the trainable adapter: consumed by the row kernel, re-accumulated by k_update
 };
 
 constexpr int FIN_ROWS = 16;       // embedding rows of dW2a per CTA
 constexpr int FIN_THREADS = 256;
 
 static inline size_t finalize_smem_bytes(int H, int C) {
-    return sizeof(float) * ((size_t)(H + 1 + C) * (H + 1) + (size_t)FIN_ROWS * (H + 1 + C)) + 16;
+    const size_t KP = (H + 1 + C + 3) & ~3, NP = (H + 1 + 3) & ~3;
+    return sizeof(float) * (KP * NP + (size_t)FIN_ROWS * KP) + 16;
 }
 
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) {
     extern __shared__ __align__(16) float fin_smem[];
     const int H = a.H, C = a.C, D = a.D, K = H + 1 + C, N = H + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     if ((int)blockIdx.x < a.n_w1_ctas) {
         // ---- dW1 = sum of the batch-chunk partial tiles (16-byte accesses; H * D is a multiple of 4)
         if (a.part) {
             const int64_t n4 = (int64_t)H * D / 4;
+            const size_t plane4 = (size_t)H * D / 4;
             for (int64_t i = (int64_t)blockIdx.x * FIN_THREADS + tid; i < n4; i += (int64_t)a.n_w1_ctas * FIN_THREADS) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int c = 0; c < a.nchunk; ++c) {
-                    const float4 v = __ldcg(reinterpret_cast<const float4*>(a.part + (size_t)c * H * D) + i);
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                }
+                float4 v[16];                                   // all chunk partials of this quad in flight together
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    v[c] = c < a.nchunk ? __ldcg(reinterpret_cast<const float4*>(a.part) + c * plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 acc = v[0];
+#pragma unroll
+                for (int c = 1; c < 16; ++c) { acc.x += v[c].x; acc.y += v[c].y; acc.z += v[c].z; acc.w += v[c].w; }
                 reinterpret_cast<float4*>(a.gW1)[i] = acc;
             }
         }
+        if (a.gram_zero)
+            for (int e = blockIdx.x * FIN_THREADS + tid; e < a.gram_floats; e += a.n_w1_ctas * FIN_THREADS) a.gram_zero[e] = 0.f;
         if (blockIdx.x == 0) {
             for (int j = tid; j < H; j += FIN_THREADS) {
-                a.ggamma[j] = (float)a.dgb[j];
-                a.gbeta[j] = (float)a.dgb[H + j];
+                a.ggamma[j] = (float)(a.dgb[j] * (double)a.gb_scale);
+                a.gbeta[j] = (float)(a.dgb[H + j] * (double)a.gb_scale);
                 // db1 = sum_B da vanishes identically (BatchNorm removes the bias); the reference's value is autograd
                 // rounding noise (|db1| ~ 1e-9, tests/test_oracle_golden.py), so b1 moves by weight decay only.
                 a.gb1[j] = 0.f;
@@ -256,55 +295,69 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) 
         return;
     }
     // ---- dW2a rows [d0, d0 + FIN_ROWS):  out[d][n] = sum_k L[d][k] S[k][n],  L = [W2 | b2 | That]
-    float* sS = fin_smem;                       // [K][N]
-    float* sL = sS + (size_t)K * N;             // [FIN_ROWS][K]
+    // 4 x 4 register tiles, operands read as 16-byte vectors (k padded to KP, n padded to NP with zeros)
+    const int KP = (K + 3) & ~3, NP = (N + 3) & ~3;
+    float* sS = fin_smem;                       // [KP][NP]
+    float* sL = sS + (size_t)KP * NP;           // [FIN_ROWS][KP]
     const int d0 = ((int)blockIdx.x - a.n_w1_ctas) * FIN_ROWS;
-    for (int e = tid; e < K * N; e += FIN_THREADS) sS[e] = __ldcg(a.S + e);
-    for (int e = tid; e < FIN_ROWS * K; e += FIN_THREADS) {
-        const int r = e / K, k = e - r * K, d = d0 + r;
+    {   // S is stored with row stride NP: whole 16-byte chunks, everything in flight at once
+        const int n4 = K * NP / 4;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sS);
+        for (int e = tid; e < n4; e += FIN_THREADS) ptx::cp_async16(dst + e * 16, a.S + e * 4);
+        ptx::cp_async_commit();
+        for (int e = K * NP + tid; e < KP * NP; e += FIN_THREADS) sS[e] = 0.f;
+    }
+    for (int e = tid; e < FIN_ROWS * KP; e += FIN_THREADS) {
+        const int r = e / KP, k = e - r * KP, d = d0 + r;
         float v = 0.f;
-        if (d < D) v = k < H ? a.W2[(size_t)d * H + k] : (k == H ? a.b2[d] : a.That[(size_t)d * C + (k - H - 1)]);
+        if (d < D && k < K) v = k < H ? a.W2[(size_t)d * H + k] : (k == H ? a.b2[d] : a.That[(size_t)d * C + (k - H - 1)]);
         sL[e] = v;
     }
+    ptx::cp_async_wait<0>();
     __syncthreads();
-    constexpr int RPW = FIN_ROWS / (FIN_THREADS / 32);      // rows per warp (2)
-    constexpr int NS = 5;                                   // 32-wide output column slots (N <= 129 + padding)
-    float acc[RPW][NS];
+    const int ncq = NP >> 2;                                // column quads
+    if (tid >= (FIN_ROWS / 4) * ncq) return;
+    const int rq = tid / ncq, cq = tid - rq * ncq;
+    float acc[4][4];
 #pragma unroll
-    for (int r = 0; r < RPW; ++r)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int s = 0; s < NS; ++s) acc[r][s] = 0.f;
-    const float* Lr = sL + (size_t)(warp * RPW) * K;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        float sv[NS];
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k = 0; k < KP; k += 4) {
+        float4 sv[4], lv[4];
 #pragma unroll
-        for (int s = 0; s < NS; ++s) { const int n = lane + 32 * s; sv[s] = n < N ? sS[(size_t)k * N + n] : 0.f; }
+        for (int kk = 0; kk < 4; ++kk) sv[kk] = *reinterpret_cast<const float4*>(sS + (size_t)(k + kk) * NP + cq * 4);
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            const float l = Lr[(size_t)r * K + k];
+        for (int i = 0; i < 4; ++i) lv[i] = *reinterpret_cast<const float4*>(sL + (size_t)(rq * 4 + i) * KP + k);
 #pragma unroll
-            for (int s = 0; s < NS; ++s) acc[r][s] = fmaf(l, sv[s], acc[r][s]);
+        for (int i = 0; i < 4; ++i) {
+            const float l[4] = {lv[i].x, lv[i].y, lv[i].z, lv[i].w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                acc[i][0] = fmaf(l[kk], sv[kk].x, acc[i][0]); acc[i][1] = fmaf(l[kk], sv[kk].y, acc[i][1]);
+                acc[i][2] = fmaf(l[kk], sv[kk].z, acc[i][2]); acc[i][3] = fmaf(l[kk], sv[kk].w, acc[i][3]);
+            }
         }
     }
 #pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-        const int d = d0 + warp * RPW + r;
+    for (int i = 0; i < 4; ++i) {
+        const int d = d0 + rq * 4 + i;
         if (d >= D) continue;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const int n = lane + 32 * s;
-            if (n < H) a.gW2[(size_t)d * H + n] = acc[r][s];
-            else if (n == H) a.gb2[d] = acc[r][s];
+        for (int j = 0; j < 4; ++j) {
+            const int n = cq * 4 + j;
+            if (n < H) a.gW2[(size_t)d * H + n] = acc[i][j];
+            else if (n == H) a.gb2[d] = acc[i][j];
         }
     }
 }
 
 static int launch_finalize(FinalizeArgs a, cudaStream_t st) {
     const size_t smem = finalize_smem_bytes(a.H, a.C);
-    DBMM_CHECK_SHAPE(smem <= 227 * 1024 && a.H + 1 <= 160, "finalize kernel: H=%d C=%d too large", a.H, a.C);
-    DBMM_CUDA(cudaFuncSetAttribute(k_finalize_grads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DBMM_CHECK_SHAPE(smem <= 227 * 1024 && (FIN_ROWS / 4) * ((a.H + 4) / 4) <= FIN_THREADS, "finalize kernel: H=%d C=%d too large", a.H, a.C);
+    DBMM_CUDA(set_smem(k_finalize_grads, smem));
     a.n_w1_ctas = a.part ? 64 : 1;
+    DBMM_CHECK_ARG(a.nchunk <= 16, "at most 16 batch chunks (got %d)", a.nchunk);
     const int n_w2 = ceil_div(a.D, FIN_ROWS);
     k_finalize_grads<<<a.n_w1_ctas + n_w2, FIN_THREADS, smem, st>>>(a);
     DBMM_LAUNCH_CHECK();

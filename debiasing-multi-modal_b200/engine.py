@@ -40,8 +40,29 @@ def _check_criterion(criterion):
         raise NotImplementedError("the fused step implements nn.CrossEntropyLoss() (mean), the reference's criterion")
 
 
+_persistent: dict = {}
+
+
 def _order_to_device(base, rows):
-    return torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int32)).to(base.device)
+    """Batch order on the device, in a per-(device, length) buffer that keeps its address from epoch to epoch: the
+    epoch's CUDA graph inside libdbmm is cached by argument addresses."""
+    n = len(rows)
+    key = ("order", str(base.device), n)
+    buf = _persistent.get(key)
+    if buf is None:
+        buf = _persistent[key] = torch.empty(n, dtype=torch.int32, device=base.device)
+    buf.copy_(torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int32)))
+    return buf
+
+
+def _stats_buffers(n_slots, n_groups, device, tag):
+    key = ("stats", tag, str(device), n_slots, n_groups)
+    st = _persistent.get(key)
+    if st is None:
+        st = _persistent[key] = ops.BatchStatsBuffers(n_slots, n_groups, device=device)
+    else:
+        st.zero_()
+    return st
 
 
 def _batch_sizes(n, bs):
@@ -83,7 +104,7 @@ def _run_train_epoch(opt, loader, classifier, optimizer, target, use_group, warm
     old, ad, w = classifier.kernel_adapters()
     That = classifier.prompt_matrix(use_group=use_group)
     labels = base.labels["group"] if use_group else base.labels[target]
-    stats = ops.BatchStatsBuffers(len(sizes), base.n_groups, device=base.device)
+    stats = _stats_buffers(len(sizes), base.n_groups, base.device, "train")
     t0 = time.time()
     ops.train_epoch(base.x, _order_to_device(base, rows), bs, labels, base.labels["group"], ad, That,
                     1.0 / classifier.temperature, optimizer.buffers, lrs, stats, old_ad=old, ebd_weight=w,
@@ -150,7 +171,7 @@ def _run_eval(loader, classifier, target, spurious_prompts=False):
     sizes = _batch_sizes(n, bs)
     old, ad, w = classifier.kernel_adapters()
     That = classifier.prompt_matrix(spurious=spurious_prompts)
-    stats = ops.BatchStatsBuffers(len(sizes), base.n_groups, device=base.device)
+    stats = _stats_buffers(len(sizes), base.n_groups, base.device, "eval")
     contiguous = len(rows) == len(base) and np.array_equal(rows, np.arange(len(base)))
     idx = None if contiguous else _order_to_device(base, rows)
     ops.eval_fwd(base.x, base.labels[target], base.labels["group"], ad, That, 1.0 / classifier.temperature, stats, bs,
