@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "../../include/dbmm.h"
 
@@ -69,6 +71,25 @@ static inline cudaError_t set_smem(K kern, size_t dyn_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes);
+}
+
+// Kernel launch with the programmatic-dependent-launch attribute (see ptx::pdl_wait).  Measured on B200 it does not
+// shorten the step (the kernels' own dependency chains dominate, not the boundaries: 58.6 vs 57.2 us/step), so it is
+// opt-in: DBMM_PDL=1.
+static inline bool pdl_enabled() {
+    static const bool on = getenv("DBMM_PDL") && strcmp(getenv("DBMM_PDL"), "1") == 0;
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 __host__ __device__ static inline int s_stride(int H) { return (H + 1 + 3) & ~3; }     // row stride of the S matrix

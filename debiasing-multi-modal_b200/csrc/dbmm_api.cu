@@ -152,8 +152,7 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
         r.part = g1part; r.ksplit = ksplit; r.nad = nad; r.B = B; r.H = H; r.b1[0] = t.b1[0]; r.b1[1] = t.b1[1];
         r.A = A; r.colsum = colsum;
         DBMM_CUDA(set_smem(k_reduce_stats, 0));
-        k_reduce_stats<<<dim3(ceil_div(B, RS_ROWS), nad), RS_THREADS, 0, st>>>(r);
-        DBMM_LAUNCH_CHECK();
+        DBMM_CUDA(launch_pdl(k_reduce_stats, dim3(ceil_div(B, RS_ROWS), nad), dim3(RS_THREADS), 0, st, r));
     }
     return DBMM_OK;
 }

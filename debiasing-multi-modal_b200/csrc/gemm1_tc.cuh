@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
+    ptx::pdl_wait();                // W1 hi / lo come from the previous step's update kernel
+    ptx::pdl_launch();
 
     if (warp < 4) {
         // ===================== producers: gather X rows + W1 hi/lo slices into swizzled K-major tiles =====================
@@ -208,8 +210,7 @@ static int launch_gemm1_tc_impl(const Gemm1TcArgs& a, cudaStream_t st) {
     auto kern = k_gemm1_tc<BN, TERMS>;
     DBMM_CUDA(set_smem(kern, Cfg::SMEM));
     dim3 grid(ceil_div(a.B, G1_BM), a.nad * (a.H / BN), a.ksplit);
-    kern<<<grid, G1_THREADS, Cfg::SMEM, st>>>(a);
-    DBMM_LAUNCH_CHECK();
+    DBMM_CUDA(launch_pdl(kern, grid, dim3(G1_THREADS), Cfg::SMEM, st, a));
     return DBMM_OK;
 }
 
@@ -250,6 +251,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_reduce_stats(ReduceStatsArgs a) 
     const int tid = threadIdx.x, q = tid >> 5, c = tid & 31;
     const size_t plane = (size_t)a.nad * a.B * H;
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    ptx::pdl_wait();
+    ptx::pdl_launch();
     if (c < H4) {
         const float4 bias = __ldg(reinterpret_cast<const float4*>(a.b1[ad]) + c);
 #pragma unroll

@@ -39,6 +39,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
+// ---- programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while its
+// predecessor drains; pdl_wait() blocks until the predecessor grid has completed and its writes are visible, and
+// pdl_launch() lets the successor's CTAs be scheduled.  Protocol used by every kernel of the training step:
+//     [set-up + loads of data written at least two kernels upstream]  pdl_wait();  pdl_launch();  [everything else]
+// (triggering only after the own wait guarantees that a successor's pre-wait region never overlaps the grand-parent).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- proxies / fences ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

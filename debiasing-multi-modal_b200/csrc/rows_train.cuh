@@ -7,6 +7,7 @@
 // group counters, dh, BatchNorm-backward inputs), and all warps add the CTA's 8-row share of S with coalesced reds.
 #pragma once
 #include "kernels_simt.cuh"
+#include "ptx_sm100.cuh"
 
 namespace dbmm {
 
@@ -62,6 +63,16 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
         asm volatile("cp.async.commit_group;" ::: "memory");
         for (int e = (n4 << 2) + tid; e < n; e += RT_THREADS) sG[e] = a.gram[e];
     }
+    // labels of the first row group (constants) are requested before the dependency wait as well
+    int y_pre = -1, g_pre = -1;
+    if (warp < RT_ROWS && blockIdx.x * RT_ROWS + warp < a.B) {
+        const int r = blockIdx.x * RT_ROWS + warp;
+        const int64_t dsrow = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
+        y_pre = a.y[dsrow];
+        g_pre = a.grp ? a.grp[dsrow] : 0;
+    }
+    ptx::pdl_wait();                // A / column sums come from k_reduce_stats; the Gram matrix is two kernels upstream
+    ptx::pdl_launch();
     // first row group's activations (adapter 0): in flight while the Gram matrix and the statistics arrive
     float av_pre[RK_HSLOT];
     {
@@ -99,9 +110,12 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
         const bool valid = owner && r < a.B;
         int yv = -1, gval = -1;                                // labels of this row: requested before the long phases
         if (valid) {
-            const int64_t dsrow = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
-            yv = a.y[dsrow];
-            gval = a.grp ? a.grp[dsrow] : 0;
+            if (base == (int)blockIdx.x * RT_ROWS) { yv = y_pre; gval = g_pre; }
+            else {
+                const int64_t dsrow = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
+                yv = a.y[dsrow];
+                gval = a.grp ? a.grp[dsrow] : 0;
+            }
         }
         float t[RK_NSLOT], hv[RK_HSLOT], ahat[RK_HSLOT];
         unsigned prepos = 0u;
@@ -345,7 +359,7 @@ static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) 
     do {                                                                                                  \
         auto kern = k_rows_train<NAD_, CT_, NW_>;                                                         \
         DBMM_CUDA(set_smem(kern, smem));    \
-        kern<<<grid, NW_ * 32, smem, st>>>(ra);                                                           \
+        DBMM_CUDA(launch_pdl(kern, dim3(grid), dim3(NW_ * 32), smem, st, ra));                            \
     } while (0)
     if (nad == 1 && CT == 4) DBMM_RT_CASE(1, 4, 16);
     else if (nad == 1) DBMM_RT_CASE(1, 16, 16);

@@ -8,6 +8,7 @@
 //     (the frozen one drifts too, final_main.py:122,574) and re-zeroes the per-step accumulators.
 #pragma once
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace dbmm {
 
@@ -36,6 +37,8 @@ __global__ void __launch_bounds__(UP_THREADS) k_update(UpdateArgs a) {
     const float lr = a.lr_dev ? __ldg(a.lr_dev) : a.lr;
     const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
     const int bid = blockIdx.x;
+    ptx::pdl_wait();                // the flat gradient comes from k_finalize_grads
+    ptx::pdl_launch();
 
     if (bid < a.n_w1_ctas) {
         // ---- W1: 16-byte SGD + tf32 split
@@ -194,8 +197,7 @@ static int launch_update(UpdateArgs a, cudaStream_t st) {
     DBMM_CUDA(set_smem(k_update, smem));
     a.n_w1_ctas = 64;
     a.n_w2_ctas = ceil_div(a.D, UP_ROWS);
-    k_update<<<a.n_w1_ctas + a.n_w2_ctas + 1, UP_THREADS, smem, st>>>(a);
-    DBMM_LAUNCH_CHECK();
+    DBMM_CUDA(launch_pdl(k_update, dim3(a.n_w1_ctas + a.n_w2_ctas + 1), dim3(UP_THREADS), smem, st, a));
     return DBMM_OK;
 }
 

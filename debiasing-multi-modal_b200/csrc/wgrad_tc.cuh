@@ -134,7 +134,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     // everything that does not depend on the set-up barrier is requested first: stage 0's X tile and half of its
     // A / dahat values are in flight while the statistics are turned into BatchNorm constants
     float4 av[8], dv[8];
-    if (warp < 4) { issue_x(0); load_da(0, 0, av, dv); }
+    if (warp < 4) issue_x(0);
+    if (tid == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { ptx::mbar_init(&full[s], 128); ptx::mbar_init(&empty[s], 1); }
+        ptx::mbar_init(tmem_full, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 4) ptx::tmem_alloc<WG_TILE>(tmem_ptr);
+    ptx::pdl_wait();                // dahat / dgamma / dbeta come from the row kernel (X, idx are constants)
+    ptx::pdl_launch();
+    if (warp < 4) load_da(0, 0, av, dv);
     if (tid < WG_TILE) {
         float mu = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
         if (tid < H) {
@@ -148,12 +157,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
         }
         sCst[0][tid] = mu; sCst[1][tid] = rstd; sCst[2][tid] = m1; sCst[3][tid] = m2;
     }
-    if (tid == 0) {
-        for (int s = 0; s < WG_STAGES; ++s) { ptx::mbar_init(&full[s], 128); ptx::mbar_init(&empty[s], 1); }
-        ptx::mbar_init(tmem_full, 1);
-        ptx::fence_mbar_init();
-    }
-    if (warp == 4) ptx::tmem_alloc<WG_TILE>(tmem_ptr);
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
@@ -234,8 +237,7 @@ static int launch_wgrad_tc(const WgradTcArgs& a, int nchunk, cudaStream_t st) {
     DBMM_CHECK_SHAPE(a.D % WG_TILE == 0 && a.H <= WG_TILE && a.H % 4 == 0, "tensor-core dW1 needs D %% 128 == 0 and H <= 128 (D=%d H=%d)", a.D, a.H);
     DBMM_CUDA(set_smem(k_wgrad_tc, WG_SMEM));
     dim3 grid(a.D / WG_TILE, nchunk);
-    k_wgrad_tc<<<grid, WG_THREADS, WG_SMEM, st>>>(a);
-    DBMM_LAUNCH_CHECK();
+    DBMM_CUDA(launch_pdl(k_wgrad_tc, grid, dim3(WG_THREADS), WG_SMEM, st, a));
     return DBMM_OK;
 }
 
@@ -266,6 +268,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) 
     const int H = a.H, C = a.C, D = a.D, K = H + 1 + C, N = H + 1;
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < a.n_w1_ctas) {
+        ptx::pdl_wait();            // the chunk partials come from k_wgrad_tc
+        ptx::pdl_launch();
         // ---- dW1 = sum of the batch-chunk partial tiles (16-byte accesses; H * D is a multiple of 4)
         if (a.part) {
             const int64_t n4 = (int64_t)H * D / 4;
@@ -314,6 +318,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) 
         sL[e] = v;
     }
     ptx::cp_async_wait<0>();
+    ptx::pdl_wait();                // S, W2, b2, That are all at least two kernels upstream: nothing waited for so far
+    ptx::pdl_launch();
     __syncthreads();
     const int ncq = NP >> 2;                                // column quads
     if (tid >= (FIN_ROWS / 4) * ncq) return;
@@ -359,8 +365,7 @@ static int launch_finalize(FinalizeArgs a, cudaStream_t st) {
     a.n_w1_ctas = a.part ? 64 : 1;
     DBMM_CHECK_ARG(a.nchunk <= 16, "at most 16 batch chunks (got %d)", a.nchunk);
     const int n_w2 = ceil_div(a.D, FIN_ROWS);
-    k_finalize_grads<<<a.n_w1_ctas + n_w2, FIN_THREADS, smem, st>>>(a);
-    DBMM_LAUNCH_CHECK();
+    DBMM_CUDA(launch_pdl(k_finalize_grads, dim3(a.n_w1_ctas + n_w2), dim3(FIN_THREADS), smem, st, a));
     return DBMM_OK;
 }
 
