@@ -9,6 +9,7 @@
 #include "rows_train.cuh"
 #include "wgrad_tc.cuh"
 #include "update.cuh"
+#include "head_supcon.cuh"
 
 #include <mutex>
 #include <vector>
@@ -459,6 +460,140 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
     }
     DBMM_CUDA(cudaGraphLaunch(exec, st));
     return DBMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// zero-shot head (config 4) and contrastive regulariser (config 3): tensor-core NT GEMM + row kernels
+// ---------------------------------------------------------------------------------------------------------------
+namespace dbmm {
+struct HeadWs { float* thi; float* tlo; float* inv_norm; SoftmaxPart* part; float* gather; int64_t chunk; int ntile; size_t total; };
+static HeadWs carve_head_ws(void* base, int64_t N, int D, int C, bool gathered) {
+    HeadWs w; char* p = (char*)base; size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    w.ntile = ceil_div(C, TG_BN);
+    int64_t chunk = gathered ? 32768 : 262144;
+    if (chunk > N) chunk = N;
+    w.chunk = chunk;
+    const size_t o_thi = take(sizeof(float) * (size_t)C * D), o_tlo = take(sizeof(float) * (size_t)C * D);
+    const size_t o_in = take(sizeof(float) * (size_t)chunk), o_part = take(sizeof(SoftmaxPart) * (size_t)chunk * w.ntile);
+    const size_t o_g = take(gathered ? sizeof(float) * (size_t)chunk * D : 0);
+    w.total = off;
+    w.thi = (float*)(p + o_thi); w.tlo = (float*)(p + o_tlo); w.inv_norm = (float*)(p + o_in);
+    w.part = (SoftmaxPart*)(p + o_part); w.gather = (float*)(p + o_g);
+    return w;
+}
+struct SupconWs { float *zhi, *zlo, *zthi, *ztlo, *G, *ghi, *glo, *gthi, *gtlo, *scale; int Bgp, Blp; size_t total; };
+static SupconWs carve_supcon_ws(void* base, int Bl, int Bg, int d) {
+    SupconWs w; char* p = (char*)base; size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    w.Bgp = (Bg + 3) & ~3; w.Blp = (Bl + 3) & ~3;
+    const size_t zb = sizeof(float) * (size_t)Bg * d, ztb = sizeof(float) * (size_t)d * w.Bgp;
+    const size_t gb = sizeof(float) * (size_t)Bl * w.Bgp, gtb = sizeof(float) * (size_t)Bg * w.Blp;
+    const size_t o1 = take(zb), o2 = take(zb), o3 = take(ztb), o4 = take(ztb), o5 = take(gb), o6 = take(gb), o7 = take(gb),
+                 o8 = take(gtb), o9 = take(gtb), o10 = take(256);
+    w.total = off;
+    w.zhi = (float*)(p + o1); w.zlo = (float*)(p + o2); w.zthi = (float*)(p + o3); w.ztlo = (float*)(p + o4);
+    w.G = (float*)(p + o5); w.ghi = (float*)(p + o6); w.glo = (float*)(p + o7); w.gthi = (float*)(p + o8); w.gtlo = (float*)(p + o9);
+    w.scale = (float*)(p + o10);
+    return w;
+}
+}  // namespace dbmm
+
+size_t dbmm_head_workspace_bytes(int64_t N, int D, int C, int gathered) {
+    if (N < 1 || D < 1 || C < 1) return 0;
+    return carve_head_ws(nullptr, N, D, C, gathered != 0).total;
+}
+size_t dbmm_supcon_workspace_bytes(int Bl, int Bg, int d) {
+    if (Bl < 1 || Bg < Bl || d < 1) return 0;
+    return carve_supcon_ws(nullptr, Bl, Bg, d).total;
+}
+
+int dbmm_logits_ce(const float* U, int64_t ldu, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                   int64_t N, int D, int C, int G, const float* That, float inv_tau, int normalize_rows, int64_t batch_size,
+                   dbmm_batch_stats stats, int32_t* pred_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DBMM_CHECK_ARG(U && That && ws, "NULL U / That / workspace");
+    DBMM_CHECK_SHAPE(D >= 4 && D % 4 == 0 && C >= 1 && G >= 1 && G <= DBMM_MAX_G, "bad D=%d C=%d G=%d", D, C, G);
+    DBMM_CHECK_ARG(N >= 0 && ldu >= D && ldu % 4 == 0 && batch_size >= 1, "bad N=%lld ldu=%lld batch_size=%lld", (long long)N,
+                   (long long)ldu, (long long)batch_size);
+    DBMM_CHECK_ARG(y || (!stats.loss_sum && !stats.counts), "labels are required when batch statistics are requested");
+    if (N == 0) return DBMM_OK;
+    HeadWs w = carve_head_ws(ws, N, D, C, idx != nullptr);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    // prompts: [D, C] -> K-major [C, D], split hi + lo (once per call; 2 * C * D floats)
+    k_transpose_split<<<dim3(ceil_div(C, 32), ceil_div(D, 32)), 256, 0, st>>>(That, C, w.thi, w.tlo, D, C, D);
+    DBMM_LAUNCH_CHECK();
+    for (int64_t pos0 = 0; pos0 < N; pos0 += w.chunk) {
+        const int64_t n = (N - pos0) < w.chunk ? (N - pos0) : w.chunk;
+        const float* A = U + pos0 * ldu; int64_t lda = ldu;
+        if (idx) {
+            k_gather_rows<<<148 * 4, 256, 0, st>>>(U, ldu, idx, pos0, n, D, w.gather);
+            DBMM_LAUNCH_CHECK();
+            A = w.gather; lda = D;
+        }
+        if (normalize_rows) {
+            k_row_inv_norm<<<148 * 4, 256, 0, st>>>(A, lda, nullptr, 0, n, D, w.inv_norm);
+            DBMM_LAUNCH_CHECK();
+        }
+        TcGemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.M = (int)n; g.N = C; g.K = D; g.scale = inv_tau; g.rowscale = normalize_rows ? w.inv_norm : nullptr;
+        g.y = y; g.idx = idx; g.pos0 = pos0; g.part = w.part;
+        if (int rc = launch_tc_gemm_nt<false, EPI_SOFTMAX_PART>(A, nullptr, lda, w.thi, w.tlo, D, g, st)) return rc;
+        k_head_finish<<<ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8, 256, 0, st>>>(
+            w.part, w.ntile, n, pos0, idx, grp, G, batch_size, stats.loss_sum, stats.counts, pred_out, y);
+        DBMM_LAUNCH_CHECK();
+    }
+    return DBMM_OK;
+}
+
+static int supcon_check(const float* Z_all, int Bg, int d, int64_t row0, int Bl, const int32_t* labels, void* ws) {
+    DBMM_CHECK_ARG(Z_all && ws, "NULL Z / workspace");
+    DBMM_CHECK_SHAPE(d >= 4 && d % 4 == 0, "embedding width d=%d must be a positive multiple of 4", d);
+    DBMM_CHECK_ARG(Bl >= 1 && Bg >= Bl && row0 >= 0 && row0 + Bl <= Bg && row0 % 4 == 0, "bad anchor slice row0=%lld Bl=%d Bg=%d",
+                   (long long)row0, Bl, Bg);
+    (void)labels;
+    return DBMM_OK;
+}
+
+int dbmm_supcon_fwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, const int32_t* labels, float inv_tau_cl,
+                    double* loss_sum, int32_t* n_valid, float* row_loss, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = supcon_check(Z_all, Bg, d, row0, Bl, labels, ws)) return rc;
+    DBMM_CHECK_ARG(labels && loss_sum && n_valid, "NULL labels / loss_sum / n_valid");
+    SupconWs w = carve_supcon_ws(ws, Bl, Bg, d);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    k_split_hi_lo<<<148 * 2, 256, 0, st>>>(Z_all, d, w.zhi, w.zlo, Bg, d, d);
+    DBMM_LAUNCH_CHECK();
+    TcGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = Bl; g.N = Bg; g.K = d; g.scale = inv_tau_cl; g.C = w.G; g.ldc = w.Bgp;
+    if (int rc = launch_tc_gemm_nt<true, EPI_STORE>(w.zhi + (size_t)row0 * d, w.zlo + (size_t)row0 * d, d, w.zhi, w.zlo, d, g, st)) return rc;
+    k_supcon_rows<<<Bl, 256, 0, st>>>(w.G, w.Bgp, Bl, Bg, row0, labels, loss_sum, n_valid, row_loss);
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+int dbmm_supcon_bwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, float inv_tau_cl, const int32_t* n_valid_global,
+                    float* dZ_local, float* dZ_all, int accumulate_all, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = supcon_check(Z_all, Bg, d, row0, Bl, nullptr, ws)) return rc;
+    DBMM_CHECK_ARG(n_valid_global && dZ_local && dZ_all, "NULL n_valid / dZ outputs");
+    SupconWs w = carve_supcon_ws(ws, Bl, Bg, d);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    k_supcon_scale<<<1, 1, 0, st>>>(n_valid_global, 1.0f, w.scale);
+    k_split_hi_lo<<<148 * 4, 256, 0, st>>>(w.G, w.Bgp, w.ghi, w.glo, Bl, Bg, w.Bgp);
+    k_transpose_split<<<dim3(ceil_div(Bg, 32), ceil_div(Bl, 32)), 256, 0, st>>>(w.G, w.Bgp, w.gthi, w.gtlo, Bl, Bg, w.Blp);
+    k_transpose_split<<<dim3(ceil_div(d, 32), ceil_div(Bg, 32)), 256, 0, st>>>(Z_all, d, w.zthi, w.ztlo, Bg, d, w.Bgp);
+    DBMM_LAUNCH_CHECK();
+    TcGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    // anchor role: dZ_local[i] = (1 / (tau n)) sum_j G_ij z_j
+    g.M = Bl; g.N = d; g.K = Bg; g.scale = inv_tau_cl; g.scale_dev = w.scale; g.C = dZ_local; g.ldc = d;
+    if (int rc = launch_tc_gemm_nt<true, EPI_STORE>(w.ghi, w.glo, w.Bgp, w.zthi, w.ztlo, w.Bgp, g, st)) return rc;
+    // contrast role: dZ_all[j] (+)= (1 / (tau n)) sum_i G_ij z_i   over this rank's anchors i
+    g.M = Bg; g.N = d; g.K = Bl; g.C = dZ_all; g.ldc = d; g.accumulate = accumulate_all;
+    return launch_tc_gemm_nt<true, EPI_STORE>(w.gthi, w.gtlo, w.Blp, w.zthi + row0, w.ztlo + row0, w.Bgp, g, st);
 }
 
 int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float momentum, float weight_decay,

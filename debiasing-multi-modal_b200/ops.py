@@ -256,3 +256,74 @@ def group_counts(logits: torch.Tensor, y, grp, stats: BatchStatsBuffers, batch_s
     _lib.check(lib.dbmm_group_counts(logits.data_ptr(), y.data_ptr(), _ptr(grp), N, Cn, G, batch_size, stats.c(),
                                      _ptr(pred), _stream_ptr()))
     return pred
+
+
+def logits_ce(U: torch.Tensor, y, grp, That: torch.Tensor, inv_tau: float, stats: BatchStatsBuffers | None, batch_size: int, *,
+              idx=None, n_rows=None, G: int = 4, normalize_rows=True, want_pred=False):
+    """Zero-shot head on raw embeddings (validate_zs, final_main.py:757-768; BASELINE config 4): cosine logits against
+    the prompt columns, CE, argmax and per-group counters without materialising the [N, C] logits."""
+    lib = _lib.load()
+    _check(U, torch.float32, "U", contiguous=False)
+    if U.stride(1) != 1:
+        raise DbmmError("U rows must be contiguous")
+    _check(That, torch.float32, "That")
+    D, Cn = U.shape[1], That.shape[1]
+    if That.shape[0] != D:
+        raise DbmmError("dimension mismatch between U and the text prompts")
+    G = _label_args(y, grp, G)
+    if idx is not None:
+        _check(idx, torch.int32, "idx")
+    N = int(n_rows if n_rows is not None else (idx.numel() if idx is not None else U.shape[0]))
+    ws = workspace(lib.dbmm_head_workspace_bytes(max(N, 1), D, Cn, 1 if idx is not None else 0), U.device)
+    pred = torch.empty((N,), dtype=torch.int32, device=U.device) if want_pred else None
+    st = stats.c() if stats is not None else BatchStats(None, None)
+    _lib.check(lib.dbmm_logits_ce(U.data_ptr(), U.stride(0), _ptr(idx), _ptr(y), _ptr(grp), N, D, Cn, G, That.data_ptr(), inv_tau,
+                                  1 if normalize_rows else 0, batch_size, st, _ptr(pred), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return pred
+
+
+class SupconState:
+    """Device scalars of one contrastive step: sum of per-anchor losses and number of valid anchors."""
+
+    def __init__(self, device="cuda"):
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
+        self.n_valid = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def zero_(self):
+        self.loss_sum.zero_()
+        self.n_valid.zero_()
+
+    def loss(self) -> float:
+        return float(self.loss_sum.item() / max(int(self.n_valid.item()), 1))
+
+
+def supcon_fwd(Z_all: torch.Tensor, labels: torch.Tensor, state: SupconState, *, row0=0, n_local=None, tau_cl=0.1, want_row_loss=False):
+    """All-anchor supervised contrastive loss (demo/visualizer_supcon.py:1532-1571 per anchor) of this rank's anchors
+    [row0, row0 + n_local) against the global batch Z_all.  Adds into `state`; keeps the similarity gradient in the workspace."""
+    lib = _lib.load()
+    _check(Z_all, torch.float32, "Z_all")
+    _check(labels, torch.int32, "labels")
+    Bg, d = Z_all.shape
+    Bl = int(n_local if n_local is not None else Bg - row0)
+    ws = workspace(lib.dbmm_supcon_workspace_bytes(Bl, Bg, d), Z_all.device)
+    row_loss = torch.empty(Bl, dtype=torch.float32, device=Z_all.device) if want_row_loss else None
+    _lib.check(lib.dbmm_supcon_fwd(Z_all.data_ptr(), Bg, d, row0, Bl, labels.data_ptr(), 1.0 / tau_cl, state.loss_sum.data_ptr(),
+                                   state.n_valid.data_ptr(), _ptr(row_loss), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return row_loss
+
+
+def supcon_bwd(Z_all: torch.Tensor, state: SupconState, *, row0=0, n_local=None, tau_cl=0.1, dZ_all=None, accumulate_all=False):
+    """Gradient of the mean contrastive loss w.r.t. the normalised embeddings.  Returns (dZ_local [Bl, d], dZ_all [Bg, d]):
+    anchor-role and contrast-role parts (on one GPU the gradient is their sum; under data parallelism dZ_all is
+    reduce-scattered).  `state.n_valid` must already hold the GLOBAL number of valid anchors."""
+    lib = _lib.load()
+    Bg, d = Z_all.shape
+    Bl = int(n_local if n_local is not None else Bg - row0)
+    ws = workspace(lib.dbmm_supcon_workspace_bytes(Bl, Bg, d), Z_all.device)
+    dZ_local = torch.empty((Bl, d), dtype=torch.float32, device=Z_all.device)
+    if dZ_all is None:
+        dZ_all = torch.empty((Bg, d), dtype=torch.float32, device=Z_all.device)
+        accumulate_all = False
+    _lib.check(lib.dbmm_supcon_bwd(Z_all.data_ptr(), Bg, d, row0, Bl, 1.0 / tau_cl, state.n_valid.data_ptr(), dZ_local.data_ptr(),
+                                   dZ_all.data_ptr(), 1 if accumulate_all else 0, ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return dZ_local, dZ_all

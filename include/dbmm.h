@@ -14,7 +14,7 @@
  *   dbmm_sgd_step         demo/util.py:118-136      SGD on a flat buffer (data-parallel path)
  *   dbmm_group_counts     final_main.py:383-391     update_dict on given logits
  *   dbmm_logits_ce        final_main.py:757-759,768 raw-embedding cosine logits + CE (zero-shot head)
- *   dbmm_supcon_fwd_bwd   demo/visualizer_supcon.py:1532-1571  contrastive loss, all anchors at once
+ *   dbmm_supcon_fwd/bwd   demo/visualizer_supcon.py:1532-1571  contrastive loss, all anchors at once
  *
  * Conventions: all pointers are DEVICE pointers unless the name ends in _host; fp32 storage,
  * int32 labels/indices, int64 counters.  No allocation, no exceptions: every function returns 0 on
@@ -160,6 +160,37 @@ int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float
 /* update_dict (final_main.py:383-391) on given logits [N, C]: adds into stats slot row/batch_size. */
 int dbmm_group_counts(const float* logits, const int32_t* y, const int32_t* grp, int64_t N, int C, int G,
                       int64_t batch_size, dbmm_batch_stats stats, int32_t* pred_out, void* stream);
+
+/*
+ * Zero-shot head on raw embeddings (validate_zs with --tl_method linear_probing / feature-quality check,
+ * final_main.py:757-768, and BASELINE config 4: N rows x C up to 1,000+ prompt columns):
+ *   logits = (u / ||u||) . That * inv_tau  (normalize_rows != 0), CE against y, argmax, per-group counters.
+ * The logits are never materialised: a tcgen05 GEMM reduces each 128-column tile to online-softmax partials.
+ *   U[N_total, D] row stride ldu (multiple of 4), idx == NULL -> rows 0..N-1; That: [D, C] column-normalised prompts.
+ */
+size_t dbmm_head_workspace_bytes(int64_t N, int D, int C, int gathered);
+int dbmm_logits_ce(const float* U, int64_t ldu, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                   int64_t N, int D, int C, int G, const float* That, float inv_tau, int normalize_rows, int64_t batch_size,
+                   dbmm_batch_stats stats, int32_t* pred_out, void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Contrastive regulariser, all anchors of the batch at once (formula: SupervisedContrastiveLoss.forward,
+ * demo/visualizer_supcon.py:1532-1571, which the reference evaluates for ONE anchor per call in a Python loop,
+ * demo/visualizer_supcon.py:458-485).  Z_all: [Bg, d] L2-normalised rows of the GLOBAL batch (all-gathered under data
+ * parallelism); this rank's anchors are rows [row0, row0 + Bl).  For anchor i with positives P_i (same label, not
+ * itself) and negatives N_i:  loss_i = log sum_{j != i} exp(z_i.z_j / tau) - mean_{p in P_i} z_i.z_p / tau ; anchors
+ * without a positive or without a negative are skipped; the loss is the mean over the valid anchors.
+ *   fwd:  *loss_sum += sum of loss_i, *n_valid += #valid anchors (device scalars: all-reduce them across ranks);
+ *         row_loss[Bl] optional.  The similarity gradient stays in the workspace for bwd.
+ *   bwd:  dZ_local[Bl, d]  = anchor-role gradient of this rank's rows,
+ *         dZ_all[Bg, d] (+)= contrast-role gradient of every row of the global batch from this rank's anchors
+ *         (reduce-scatter it across ranks; on one GPU the gradient is dZ_local + dZ_all), both scaled by 1 / *n_valid_global.
+ */
+size_t dbmm_supcon_workspace_bytes(int Bl, int Bg, int d);
+int dbmm_supcon_fwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, const int32_t* labels, float inv_tau_cl,
+                    double* loss_sum, int32_t* n_valid, float* row_loss, void* ws, size_t ws_bytes, void* stream);
+int dbmm_supcon_bwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, float inv_tau_cl, const int32_t* n_valid_global,
+                    float* dZ_local, float* dZ_all, int accumulate_all, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

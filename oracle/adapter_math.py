@@ -363,3 +363,39 @@ def supcon_all_anchors(Z, labels, tau_cl=0.1, dtype=np.float64):
         feats = np.concatenate([Z[i:i + 1], Z[pos], Z[neg]], 0)
         losses.append(supcon_single_anchor(feats, len(pos), len(neg), tau_cl, dtype))
     return float(np.mean(losses)) if losses else 0.0
+
+
+def supcon_all_anchors_grad(Z, labels, tau_cl=0.1, dtype=np.float64):
+    """Vectorised all-anchor loss and its gradient w.r.t. the (already normalised) rows, s_ij = z_i . z_j / tau:
+    loss_i = logsumexp_{j != i} s_ij - mean_{p in P_i} s_ip; G_ij = softmax_{j != i}(s_i)_j - [j in P_i] / |P_i|;
+    dZ = (G + G^T) Z / (tau * n_valid).  Checked against autograd of the loop form in tests/test_oracle_golden.py."""
+    Z = Z.astype(dtype)
+    labels = np.asarray(labels)
+    B = len(Z)
+    S = (Z @ Z.T) / tau_cl
+    eye = np.eye(B, dtype=bool)
+    same = (labels[:, None] == labels[None, :]) & ~eye
+    npos = same.sum(1)
+    nneg = (labels[:, None] != labels[None, :]).sum(1)
+    valid = (npos > 0) & (nneg > 0)
+    Sm = np.where(eye, -np.inf, S)
+    mx = Sm.max(1, keepdims=True)
+    E = np.exp(Sm - mx)
+    se = E.sum(1, keepdims=True)
+    lse = (np.log(se) + mx)[:, 0]
+    pos_mean = np.where(npos > 0, (np.where(same, S, 0.0).sum(1)) / np.maximum(npos, 1), 0.0)
+    row_loss = np.where(valid, lse - pos_mean, 0.0)
+    n_valid = int(valid.sum())
+    G = E / se - same / np.maximum(npos, 1)[:, None]
+    G[~valid] = 0.0
+    dZ = (G + G.T) @ Z / (tau_cl * max(n_valid, 1))
+    loss = float(row_loss.sum() / max(n_valid, 1))
+    return dict(loss=loss, row_loss=row_loss, n_valid=n_valid, G=G, dZ=dZ)
+
+
+def head_logits(U, That, tau, normalize_rows=True, dtype=np.float64):
+    """validate_zs on raw embeddings (final_main.py:757-768): row-normalise, cosine logits / temperature."""
+    U = U.astype(dtype)
+    if normalize_rows:
+        U = U / np.sqrt((U * U).sum(1, keepdims=True))
+    return (U @ That.astype(dtype)) / tau

@@ -157,3 +157,29 @@ def test_supcon_all_anchors_reduces_to_single_anchor():
     single = am.supcon_single_anchor(np.concatenate([Z[i:i + 1], Z[pos], Z[neg]]), len(pos), len(neg))
     assert np.isfinite(single)
     assert np.isfinite(am.supcon_all_anchors(Z, labels))
+
+
+def test_supcon_vectorised_matches_loop_and_autograd():
+    """The B x B form used as the GPU kernels' oracle == the loop over the reference-pinned single-anchor formula, and its
+    analytic gradient == torch autograd of that loop (unit rows, one label with a single member -> invalid anchor)."""
+    import torch
+    rng = np.random.default_rng(5)
+    Z = rng.standard_normal((14, 16)); Z /= np.linalg.norm(Z, axis=1, keepdims=True)
+    labels = np.array([0] * 5 + [1] * 6 + [2] * 2 + [3])
+    r = am.supcon_all_anchors_grad(Z, labels, 0.1)
+    assert r["n_valid"] == 13
+    assert r["loss"] == pytest.approx(am.supcon_all_anchors(Z, labels, 0.1), rel=1e-10)
+    Zt = torch.tensor(Z, dtype=torch.float64, requires_grad=True)
+    losses = []
+    for i in range(14):
+        pos = [j for j in range(14) if j != i and labels[j] == labels[i]]
+        neg = [j for j in range(14) if labels[j] != labels[i]]
+        if not pos or not neg:
+            continue
+        sp = (Zt[pos] @ Zt[i]) / 0.1
+        sn = (Zt[neg] @ Zt[i]) / 0.1
+        m = sp.max().detach()                                   # demo/visualizer_supcon.py:1546 (detached max of the positives)
+        lp = torch.log(torch.exp(sp - m)) - torch.log(torch.exp(sn - m).sum() + torch.exp(sp - m).sum())
+        losses.append((-lp).mean())
+    torch.stack(losses).mean().backward()
+    np.testing.assert_allclose(r["dZ"], Zt.grad.numpy(), rtol=1e-9, atol=1e-12)
