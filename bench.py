@@ -43,6 +43,14 @@ def peaks():
     return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
 
 
+def traffic_from_profiles(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(kernel)
+    return None
+
+
 def synth_rows(n, seed, dim=D):
     """CelebA-shaped rows: x = base + k*mu_group + eps, rounded through fp16."""
     rng = np.random.default_rng(seed)
@@ -92,6 +100,52 @@ class ClockSampler:
                     samples=len(sm))
 
 
+def extra_legs(torch, ops, dev, P, e0, e1):
+    """Zero-shot head (config 4 shape per GPU slice) and contrastive regulariser (config 3 shape), device-resident."""
+    res = {}
+    rng = np.random.default_rng(5)
+    # head: 262,144 rows x 1024-d against 1,000 prompt columns; 2 * D * C flop per row, single pass over X
+    n, c = 262144, 1000
+    U = torch.randn(n, D, device=dev).half().float()
+    yh = torch.randint(0, c, (n,), device=dev, dtype=torch.int32)
+    gh = torch.randint(0, G, (n,), device=dev, dtype=torch.int32)
+    Th = ops.normalize_text(torch.randn(D, c, device=dev))
+    st = ops.BatchStatsBuffers((n + 1023) // 1024, G, device=dev)
+    for _ in range(2):
+        ops.logits_ce(U, yh, gh, Th, 100.0, st, 1024, G=G)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        ops.logits_ce(U, yh, gh, Th, 100.0, st, 1024, G=G)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 3 * 1e-3
+    fl = 2.0 * D * c * n
+    res["head_c1000"] = {"rows": n, "emb_per_s": n / t, "ms": t * 1e3, "algorithmic_tflops": fl / t / 1e12,
+                         "frac_of_bf16_sustained_peak": fl / t / 1e12 / P["tc_sustained"],
+                         "note": "kind::tf32 x 2 terms (X * That_hi + X * That_lo): 4x the bf16 cost per algorithmic flop"}
+    del U
+    # contrastive: B = 8192, d = 768, forward + backward; 6 * B * d flop per row
+    B, d = 8192, 768
+    Z = torch.nn.functional.normalize(torch.randn(B, d, device=dev), dim=1).contiguous()
+    lab = torch.randint(0, 4, (B,), device=dev, dtype=torch.int32)
+    sc = ops.SupconState(device=dev)
+    for _ in range(2):
+        sc.zero_(); ops.supcon_fwd(Z, lab, sc); ops.supcon_bwd(Z, sc)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        sc.zero_(); ops.supcon_fwd(Z, lab, sc); ops.supcon_bwd(Z, sc)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 3 * 1e-3
+    fl = 6.0 * B * d * B
+    res["supcon_b8192_d768"] = {"rows": B, "emb_per_s": B / t, "ms": t * 1e3, "algorithmic_tflops": fl / t / 1e12,
+                                "frac_of_bf16_sustained_peak": fl / t / 1e12 / P["tc_sustained"], "loss": sc.loss(),
+                                "note": "3xTF32 (6x the bf16 cost per algorithmic flop); similarity gradient staged in HBM"}
+    return res
+
+
 def cpu_reference_step(rows_x, rows_y, rows_g, T, n_sgd_steps):
     """The reference's step body (oracle port, torch CPU, all host threads) on a bounded sample."""
     from oracle import ref_port
@@ -104,8 +158,8 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sgd = 12                                  # bounded sample per step: 12 SGD steps of 1024 rows
-    x, y, g, T = synth_rows(n_sgd * BATCH, seed=1234)
+    n_sgd = 400                                 # bounded sample per bench step: 400 SGD steps of 1024 rows (~2 s)
+    x, y, g, T = synth_rows(48 * BATCH, seed=1234)
     cpu_reference_step(x, y, g, T, 2)           # page-in / thread pool warm-up
     for _ in range(args.warmup):
         cpu_reference_step(x, y, g, T, n_sgd)
@@ -253,44 +307,35 @@ def main():
                "us_per_sgd_step": 1e3 * ms_per_step / steps_per_epoch, "final_epoch_mean_loss": final_loss,
                "gpu_launches": args.steps * (steps_per_epoch * 6 + 3)}
 
-    # ---- per-phase timing of the same epoch (CUDA events on the launch stream) -> roofline of the dominant kernel
-    phase_ms = np.zeros(4)
-    n_prof = min(steps_per_epoch, 64)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n_prof)]
-    order = orders[0]
-    torch.cuda.synchronize()
-    for s in range(n_prof):
-        idx = order[s * BATCH:(s + 1) * BATCH]
-        kw = dict(idx=idx, B_global=idx.numel(), G=G)
-        for ph in range(4):
-            evs[s][ph].record()
-            ops.train_step(X, y, g, ad, That, 100.0, buf, 0.0, stats, s, phases=1 << ph, **kw)
-        evs[s][4].record()
-    torch.cuda.synchronize()
-    for s in range(n_prof):
-        for ph in range(4):
-            phase_ms[ph] += evs[s][ph].elapsed_time(evs[s][ph + 1])
-    phase_ms /= n_prof
-    names = ["gemm1(+gram,memset)", "rows", "wgrad(dW1,S,dW2)", "sgd"]
-    dom = int(np.argmax(phase_ms))
-    if rank == 0:
-        # GEMM-1 and dW1 each stream the batch's X once (4096 B/emb) and do 2*D*H flop/emb
-        dom_flop = {0: 2.0 * D * H * BATCH, 2: 2.0 * D * H * BATCH + 2.0 * H * H * BATCH, 1: 4.0 * H * (H + C) * BATCH,
-                    3: 4.0 * (2 * D * H)}[dom]
-        dom_bytes = {0: ALG_BYTES_PER_EMB * BATCH, 2: ALG_BYTES_PER_EMB * BATCH, 1: 2 * 4 * H * BATCH,
-                     3: 5 * 4 * (2 * D * H + 3 * H + D)}[dom]
-        t_dom = phase_ms[dom] * 1e-3
+    # ---- per-kernel timing inside the running step (CUDA events between the kernels, stream launches) -> roofline of the
+    #      dominant kernel.  Algorithmic bytes / flops per launch: GEMM-1 and dW1 each stream the
+    #      batch's X once (B * 4096 B) and do 2*D*H flop per row; the row kernel moves A + dahat (2 * B * H * 4 B).
+    if world == 1:
+        order_buf.copy_(orders[0])
+        kus = ops.train_epoch_profile(X, order_buf, BATCH, y, g, ad, That, 100.0, buf, lrs, stats, G=G)
+    else:
+        kus = None
+    if rank == 0 and kus is not None:
+        np_ = 2 * D * H + 3 * H + D
+        alg = {"gemm1_tc": (ALG_BYTES_PER_EMB * BATCH, 2.0 * D * H * BATCH), "wgrad_tc": (ALG_BYTES_PER_EMB * BATCH, 2.0 * D * H * BATCH),
+               "reduce_stats": (2 * 4 * H * BATCH, 2.0 * H * BATCH), "rows_train": (2 * 4 * H * BATCH, 4.0 * H * (H + C) * BATCH),
+               "finalize_grads": (4 * np_, 2.0 * D * (H + 1) * (H + 1 + C)), "update": (5 * 4 * np_, 4.0 * np_)}
+        dom = max(kus, key=kus.get)
+        dom_bytes, dom_flop = alg[dom]
+        t_dom = kus[dom] * 1e-6
         t_hbm, t_tc = dom_bytes / (P["hbm"] * 1e9), dom_flop / (P["tc_sustained"] * 1e12)
         if t_tc >= t_hbm:
             roof = {"bound": "tensor", "achieved": dom_flop / t_dom / 1e12, "peak": P["tc_sustained"], "unit": "TFLOP/s"}
         else:
             roof = {"bound": "hbm", "achieved": dom_bytes / t_dom / 1e9, "peak": P["hbm"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["traffic"] = None
-        roof["kernel"] = names[dom]
+        roof["kernel"] = "k_" + dom
+        roof["traffic"] = traffic_from_profiles("k_" + dom)
         roof["peak_source"] = P["src"] + (" (sustained bf16 figure: kernel timed inside a long step)" if roof["bound"] == "tensor" else "")
-        roof["phase_us"] = {n: float(1e3 * t) for n, t in zip(names, phase_ms)}
-        # whole training step against its binding roof (tensor roof binds the train step)
+        roof["kernel_us"] = kus
+        roof["algorithmic_bytes_per_launch"] = dom_bytes
+        # whole training step against its binding roof (the tensor roof binds the reference
+        # formulation of the step); the dependent-phase latency floor is discussed in DESIGN.md section 5
         t_step = ms_per_step * 1e-3 / steps_per_epoch
         roof["step"] = {"bound": "tensor", "achieved_tflops": ALG_FLOP_TRAIN * BATCH / t_step / 1e12,
                         "frac": ALG_FLOP_TRAIN * BATCH / t_step / 1e12 / P["tc_sustained"],
@@ -316,47 +361,69 @@ def main():
                        "roofline": {"bound": "hbm", "achieved": ev * ALG_BYTES_PER_EMB / 1e9, "peak": P["hbm"], "unit": "GB/s",
                                     "frac": ev * ALG_BYTES_PER_EMB / 1e9 / P["hbm"], "traffic": None}}
 
-    # ---- e2e leg: host buffers in, statistics out, copies inside the timed region
+    # ---- kernels of BASELINE configs 3 / 4 (tcgen05 + TMA GEMMs), short legs, N = 1 only
+    if rank == 0 and world == 1:
+        out["extra"] = extra_legs(torch, ops, dev, P, e0, e1)
+
+    # ---- e2e leg: host buffers in, statistics out, copies inside the timed region.  Two device buffer sets: the
+    #      pinned-host -> device copy of epoch i+1's inputs runs on a copy stream while epoch i trains.
     xh = torch.from_numpy(x_np).pin_memory()
     yh, gh = torch.from_numpy(y_np).pin_memory(), torch.from_numpy(g_np).pin_memory()
     oh = [o.cpu().pin_memory() for o in orders]
-    Xd, yd, gd, od = torch.empty_like(X), torch.empty_like(y), torch.empty_like(g), torch.empty_like(orders[0])
+    sets = [dict(X=torch.empty_like(X), y=torch.empty_like(y), g=torch.empty_like(g), o=torch.empty_like(orders[0]),
+                 st=ops.BatchStatsBuffers(steps_per_epoch, G, device=dev), ready=torch.cuda.Event(), free=torch.cuda.Event())
+            for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
     loss_h = torch.empty(steps_per_epoch, dtype=torch.float64).pin_memory()
     cnt_h = torch.empty(steps_per_epoch, 2, G, dtype=torch.int64).pin_memory()
+    main_stream = torch.cuda.current_stream()
 
-    def e2e_epoch(i):
-        Xd.copy_(xh, non_blocking=True); yd.copy_(yh, non_blocking=True); gd.copy_(gh, non_blocking=True)
-        od.copy_(oh[i % 4], non_blocking=True)
-        stats.zero_()
-        if world == 1:
-            ops.train_epoch(Xd, od, BATCH, yd, gd, ad, That, 100.0, buf, lrs, stats, G=G)
-        else:
-            for s in range(steps_per_epoch):
-                dp_step_on(Xd, yd, gd, od[s * BATCH:(s + 1) * BATCH], float(lrs[s]), s)
-        loss_h.copy_(stats.loss_sum, non_blocking=True); cnt_h.copy_(stats.counts, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_h.sum())
+    def prefetch(i):
+        b = sets[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(b["free"])                 # the epoch that last used this buffer set has finished
+            b["X"].copy_(xh, non_blocking=True); b["y"].copy_(yh, non_blocking=True); b["g"].copy_(gh, non_blocking=True)
+            b["o"].copy_(oh[i % 4], non_blocking=True)
+            b["ready"].record(copy_stream)
 
-    def dp_step_on(Xs, ys, gs, idx, lr, slot):
+    def dp_step_on(Xs, ys, gs, idx, lr, slot, st):
         kw = dict(idx=idx, B_global=idx.numel() * world, G=G)
-        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, stats, slot, phases=1, **kw)
+        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, st, slot, phases=1, **kw)
         colsum, dgb = parallel.accum_views(ops.workspace(0, dev), H, 1)
         dist.all_reduce(colsum)
-        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, stats, slot, phases=2, **kw)
+        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, st, slot, phases=2, **kw)
         dist.all_reduce(dgb)
-        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, stats, slot, phases=4, **kw)
+        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, st, slot, phases=4, **kw)
         dist.all_reduce(buf.grads)
-        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, stats, slot, phases=8, **kw)
+        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, st, slot, phases=8, **kw)
+
+    def e2e_epoch(i):
+        b = sets[i % 2]
+        main_stream.wait_event(b["ready"])
+        prefetch(i + 1)                                       # overlaps with this epoch's kernels
+        b["st"].zero_()
+        if world == 1:
+            ops.train_epoch(b["X"], b["o"], BATCH, b["y"], b["g"], ad, That, 100.0, buf, lrs, b["st"], G=G)
+        else:
+            for s in range(steps_per_epoch):
+                dp_step_on(b["X"], b["y"], b["g"], b["o"][s * BATCH:(s + 1) * BATCH], float(lrs[s]), s, b["st"])
+        loss_h.copy_(b["st"].loss_sum, non_blocking=True); cnt_h.copy_(b["st"].counts, non_blocking=True)
+        b["free"].record(main_stream)
+        main_stream.synchronize()                             # the step's result (loss / counters) is read on the host
+        return float(loss_h.sum())
 
     n_e2e = max(3, min(args.steps, 5))
-    e2e_epoch(0)
+    for b in sets:
+        b["free"].record(main_stream)
+    prefetch(0)
+    e2e_epoch(0); e2e_epoch(1)                                # warm-up: both buffer sets' graphs exist
     barrier()
-    t0 = time.perf_counter()
     e0.record()
-    for i in range(n_e2e):
+    for i in range(2, 2 + n_e2e):
         e2e_epoch(i)
     e1.record()
     barrier()
+    copy_stream.synchronize()
     ms2 = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms2], device=dev)
@@ -367,16 +434,19 @@ def main():
         d2h = loss_h.numel() * 8 + cnt_h.numel() * 8
         out["e2e"] = {"value": world * N_TRAIN * n_e2e / (ms2 * 1e-3), "unit": "embeddings/s",
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms2 / n_e2e,
-                      "api": "dbmm_train_epoch (C ABI) on pinned host buffers copied per step"}
+                      "api": "dbmm_train_epoch (C ABI): pinned host buffers copied in every step on a copy stream "
+                             "(double-buffered against the previous step's kernels), per-batch statistics read back"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port of the reference step on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_sgd = 24
-        r = cpu_reference_step(x_np[:n_sgd * BATCH], y_np[:n_sgd * BATCH], g_np[:n_sgd * BATCH], T_np, 2)
-        r = cpu_reference_step(x_np[:n_sgd * BATCH], y_np[:n_sgd * BATCH], g_np[:n_sgd * BATCH], T_np, n_sgd)
+        n_rows_s = 48 * BATCH
+        r = cpu_reference_step(x_np[:n_rows_s], y_np[:n_rows_s], g_np[:n_rows_s], T_np, 24)       # warm-up + rate estimate
+        n_sgd = int(min(max(12.0 * r["emb_per_s"] / BATCH, 48), 6000))                             # ~12 s of CPU work
+        r = cpu_reference_step(x_np[:n_rows_s], y_np[:n_rows_s], g_np[:n_rows_s], T_np, n_sgd)
         out["cpu_baseline"] = {"value": r["emb_per_s"], "unit": "embeddings/s", "cores": r["threads"], "kind": "port",
-                               "sample": f"{n_sgd} SGD steps of {BATCH} rows of the same workload ({r['seconds']:.1f} s), "
-                                         "reference step body restated in torch-CPU (oracle/ref_port.py), tensors pre-loaded"}
+                               "sample": f"{n_sgd} SGD steps of {BATCH} rows cycling over the first {n_rows_s} rows of the same "
+                                         f"workload ({r['seconds']:.1f} s), reference step body restated in torch-CPU "
+                                         "(oracle/ref_port.py), tensors pre-loaded"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -123,8 +123,10 @@ static int gemm1_ksplit(int B, int nad, int D) {
 // ksplit > 1 (training): D-sliced partial tiles into `g1part`, finished by k_reduce_stats.
 static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t pos0, int B, int D, int H,
                         const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, double* colsum,
-                        float* whi, float* wlo, bool split_weights, int ksplit, float* g1part, cudaStream_t st) {
+                        float* whi, float* wlo, bool split_weights, int ksplit, float* g1part, cudaStream_t st,
+                        cudaEvent_t* ev = nullptr) {
     const int nad = old_ad ? 2 : 1;
+    if (ev && !split_weights) cudaEventRecord(ev[0], st);
     if (!use_tc_gemm1(D, H)) {
         Gemm1Args g;
         fill_gemm1(g, X, ldx, idx, pos0, B, D, H, old_ad, ad, A, colsum);
@@ -144,10 +146,12 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
         }
     }
     if (nad == 1) { t.Whi[1] = t.Whi[0]; t.Wlo[1] = t.Wlo[0]; t.b1[1] = t.b1[0]; }
+    if (ev && split_weights) cudaEventRecord(ev[0], st);
     t.A = A; t.colsum = colsum; t.ksplit = ksplit; t.part = g1part;
     int bn = 128;
     if (ksplit == 1 && B <= 4096) bn = (H % 32 == 0) ? 32 : H;      // few row tiles: narrow hidden slices -> more CTAs
     if (int rc = launch_gemm1_tc(t, bn, st)) return rc;
+    if (ev) cudaEventRecord(ev[1], st);
     if (ksplit > 1) {
         ReduceStatsArgs r;
         r.part = g1part; r.ksplit = ksplit; r.nad = nad; r.B = B; r.H = H; r.b1[0] = t.b1[0]; r.b1[1] = t.b1[1];
@@ -252,8 +256,10 @@ static int train_step_impl(int phases, bool fresh,
                            const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
                            const float* That, float inv_tau,
                            float* grads, float* momentum_buf, float lr, const float* lr_dev, float momentum, float weight_decay,
-                           dbmm_batch_stats stats, int64_t slot, const TrainWs& w, cudaStream_t st) {
+                           dbmm_batch_stats stats, int64_t slot, const TrainWs& w, cudaStream_t st,
+                           cudaEvent_t* ev = nullptr /* 7 events: before each of the 6 step kernels + after the last */) {
     const int nad = old_ad ? 2 : 1;
+    auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
     const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
     const size_t gram_floats = (size_t)(H + 1) * (H + 1 + C);
     float* gram_t = w.gram + (size_t)(nad - 1) * gram_floats;
@@ -267,9 +273,10 @@ static int train_step_impl(int phases, bool fresh,
             if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
         }
         const int ks = tc1 ? gemm1_ksplit(B, nad, D) : 1;
-        if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, fresh, ks, w.g1part, st)) return rc;
+        if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, fresh, ks, w.g1part, st, ev)) return rc;
     }
     if (phases & DBMM_PHASE_ROWS) {
+        mark(2);
         RowsTrainArgs ra;
         memset(&ra, 0, sizeof(ra));
         ra.B = B; ra.Bg = B_global; ra.idx = idx; ra.y = y; ra.grp = grp; ra.H = H; ra.C = C; ra.G = G;
@@ -282,6 +289,7 @@ static int train_step_impl(int phases, bool fresh,
     }
     if (phases & DBMM_PHASE_WGRAD) {
         const bool tc = use_tc_wgrad(D, H);
+        mark(3);
         int nchunk = 0;
         const float* A_t = w.A + (size_t)(nad - 1) * B * H;
         const double* colsum_t = w.colsum + (size_t)(nad - 1) * 2 * H;
@@ -302,6 +310,7 @@ static int train_step_impl(int phases, bool fresh,
             k_wgrad<<<grid, GT_THREADS, 0, st>>>(wa);
             DBMM_LAUNCH_CHECK();
         }
+        mark(4);
         FinalizeArgs fa;
         fa.part = tc ? w.part : nullptr; fa.nchunk = nchunk;
         fa.W2 = ad->W2; fa.b2 = ad->b2; fa.That = That; fa.S = w.S; fa.dgb = w.dgb;
@@ -312,6 +321,7 @@ static int train_step_impl(int phases, bool fresh,
         if (!(skip & 16)) if (int rc = launch_finalize(fa, st)) return rc;
     }
     if (phases & DBMM_PHASE_UPDATE) {
+        mark(5);
         UpdateArgs ua;
         memset(&ua, 0, sizeof(ua));
         ua.W1 = ad->W1; ua.b1 = ad->b1; ua.gamma = ad->gamma; ua.beta = ad->beta; ua.W2 = ad->W2; ua.b2 = ad->b2;
@@ -324,6 +334,7 @@ static int train_step_impl(int phases, bool fresh,
         ua.rm[0] = a0->running_mean; ua.rv[0] = a0->running_var; ua.nbt[0] = (long long*)a0->num_batches_tracked;
         ua.rm[1] = ad->running_mean; ua.rv[1] = ad->running_var; ua.nbt[1] = (long long*)ad->num_batches_tracked;
         if (int rc = launch_update(ua, st)) return rc;
+        mark(6);
     }
     return DBMM_OK;
 }
@@ -594,6 +605,62 @@ int dbmm_supcon_bwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, flo
     // contrast role: dZ_all[j] (+)= (1 / (tau n)) sum_i G_ij z_i   over this rank's anchors i
     g.M = Bg; g.N = d; g.K = Bl; g.C = dZ_all; g.ldc = d; g.accumulate = accumulate_all;
     return launch_tc_gemm_nt<true, EPI_STORE>(w.gthi, w.gtlo, w.Blp, w.zthi + row0, w.ztlo + row0, w.Bgp, g, st);
+}
+
+namespace dbmm {
+// Keeps the stream busy while the host queues up a window of launches, so that the timed kernels run back to back
+// (no host-launch gaps between them) exactly as they do inside the epoch graph.
+__global__ void k_hold_stream(long long cycles) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) { }
+}
+}  // namespace dbmm
+
+// Measurement aid (bench.py `roofline`): one epoch as plain stream launches with CUDA events between the kernels of
+// every step; kernel_us_host[k] = mean device time of step kernel k (GEMM-1, reduce/stats, rows, dW1, finalize, update)
+// as it runs inside the step, i.e. with warm L2 and its real predecessors.  Synchronises the stream.
+int dbmm_train_epoch_profile(const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                             const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
+                             const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                             const float* That, float inv_tau, float* grads, float* momentum_buf, const float* lr_host,
+                             float momentum, float weight_decay, dbmm_batch_stats stats,
+                             void* ws, size_t ws_bytes, void* stream, float* kernel_us_host) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DBMM_CHECK_ARG(order && lr_host && momentum_buf && kernel_us_host, "NULL order / lr table / momentum buffer / output");
+    const int64_t steps = (n_rows + batch_size - 1) / batch_size;
+    const int B0 = (int)(n_rows < batch_size ? n_rows : batch_size);
+    if (int rc = check_train_args(X, ldx, y, B0, B0, D, H, C, G, old_ad, ad, That, ws, grads)) return rc;
+    DBMM_CHECK_ARG(steps >= 2 && steps <= 4096 && n_rows - (steps - 1) * batch_size > 1, "profile needs 2..4096 steps");
+    const int nad = old_ad ? 2 : 1;
+    TrainWs w = carve_train_ws(ws, B0, D, H, C, nad);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    DBMM_CUDA(cudaMemcpyAsync(w.lr, lr_host, sizeof(float) * (size_t)steps, cudaMemcpyHostToDevice, st));
+    std::vector<cudaEvent_t> ev((size_t)steps * 7);
+    for (auto& e : ev) DBMM_CUDA(cudaEventCreate(&e));
+    int rc = DBMM_OK;
+    for (int64_t s = 0; s < steps && !rc; ++s) {
+        const int64_t p0 = s * batch_size;
+        const int B = (int)((n_rows - p0) < batch_size ? (n_rows - p0) : batch_size);
+        if (s % 48 == 1) {                                       // a window of 48 steps (~620 queue entries) behind each hold
+            k_hold_stream<<<1, 1, 0, st>>>(8000000LL);           // ~4 ms at 1.9 GHz
+            DBMM_LAUNCH_CHECK();
+        }
+        rc = train_step_impl(DBMM_PHASE_ALL, s == 0, X, ldx, order + p0, y, grp, B, B, D, H, C, G, old_ad, ad, ebd_weight, That,
+                             inv_tau, grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, st, &ev[(size_t)s * 7]);
+    }
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("stream synchronize failed"); rc = DBMM_ERR_CUDA; }
+    if (!rc) {
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int64_t s = 1; s < steps; ++s)                      // step 0 also computes the Gram matrix / weight split
+            for (int k = 0; k < 6; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[(size_t)s * 7 + k], ev[(size_t)s * 7 + k + 1]);
+                acc[k] += ms;
+            }
+        for (int k = 0; k < 6; ++k) kernel_us_host[k] = (float)(1e3 * acc[k] / (double)(steps - 1));
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
 }
 
 int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float momentum, float weight_decay,

@@ -237,6 +237,31 @@ def train_epoch(X, order: torch.Tensor, batch_size: int, y, grp, ad: AdapterTens
     return steps
 
 
+STEP_KERNELS = ("gemm1_tc", "reduce_stats", "rows_train", "wgrad_tc", "finalize_grads", "update")
+
+
+def train_epoch_profile(X, order: torch.Tensor, batch_size: int, y, grp, ad: AdapterTensors, That, inv_tau, buf: TrainBuffers,
+                        lrs, stats: BatchStatsBuffers, *, old_ad=None, ebd_weight=0.5, G=4, momentum=0.9, weight_decay=5e-5):
+    """Measurement aid: one epoch with CUDA events between the kernels of every step -> {kernel: mean microseconds}."""
+    lib = _lib.load()
+    D, H, Cn = X.shape[1], ad.H, That.shape[1]
+    G = _label_args(y, grp, G)
+    n = order.numel()
+    steps = (n + batch_size - 1) // batch_size
+    lrs = np.ascontiguousarray(lrs, dtype=np.float32)
+    nad = 2 if old_ad is not None else 1
+    ws = workspace(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, min(batch_size, n), D, H, Cn, nad), X.device)
+    old_p = old_ad.ptrs() if old_ad is not None else None
+    out = (C.c_float * 6)()
+    _lib.check(lib.dbmm_train_epoch_profile(X.data_ptr(), X.stride(0), order.data_ptr(), n, batch_size, y.data_ptr(), _ptr(grp),
+                                            D, H, Cn, G, C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()),
+                                            ebd_weight, That.data_ptr(), inv_tau, buf.grads.data_ptr(), buf.momentum.data_ptr(),
+                                            lrs[:steps].ctypes.data_as(C.POINTER(C.c_float)), momentum, weight_decay, stats.c(),
+                                            ws.data_ptr(), ws.numel(), _stream_ptr(), out))
+    buf.first_step = False
+    return dict(zip(STEP_KERNELS, [float(v) for v in out]))
+
+
 def sgd_step(p: torch.Tensor, g: torch.Tensor, v: torch.Tensor, lr, momentum=0.9, weight_decay=5e-5, first_step=False):
     """torch.optim.SGD on flat fp32 buffers (demo/util.py:118-136)."""
     lib = _lib.load()

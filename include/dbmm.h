@@ -153,6 +153,16 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
                      int first_step, dbmm_batch_stats stats,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* Measurement aid: the same epoch as stream launches with CUDA events between the kernels of every step;
+ * kernel_us_host[6] = mean device microseconds of GEMM-1, reduce/statistics, row kernel, dW1, gradient finalisation,
+ * update, each timed inside the running step.  Synchronises the stream. */
+int dbmm_train_epoch_profile(const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                             const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
+                             const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                             const float* That, float inv_tau, float* grads, float* momentum_buf, const float* lr_host,
+                             float momentum, float weight_decay, dbmm_batch_stats stats,
+                             void* ws, size_t ws_bytes, void* stream, float* kernel_us_host);
+
 /* torch.optim.SGD on a flat buffer: g += wd*p; v = g (first_step) or momentum*v + g; p -= lr*v */
 int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float momentum, float weight_decay,
                   int first_step, void* stream);

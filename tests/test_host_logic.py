@@ -160,3 +160,29 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_sweep_csv_protocol_matches_reference_quirks(tmp_path):
+    """Sweep aggregation (run_multiple/final_main_iteration_wb.py:1129-1196): block order, index labels, 4-decimal rounding,
+    and the std row computed AFTER the mean row was appended (CelebA seeds 0.9000 / 0.8889 print 0.0055)."""
+    import dbmm
+    from dbmm import sweep
+    keys = ["weighted_mean_acc", "worst_acc", "acc_0_0", "acc_0_1", "acc_1_0", "acc_1_1", "mean_acc"]
+
+    def res(v):
+        d = {k: v for k in keys}
+        return dict(train={k: v for k in keys[1:]}, val=d, test=d, zs_target=d, zs_spurious=d)
+    df = sweep.aggregate({1: res(0.9000), 2: res(0.8889)})
+    assert list(df.index) == [1, 2, "test_mean", "test_std", 1, 2, "zs_spu_mean", "zs_spu_std", 1, 2, "tr_mean", "tr_std",
+                              1, 2, "val_mean", "val_std", 1, 2, "zs_tg_mean", "zs_tg_std"]
+    assert df.loc["test_mean", "worst_acc"] == 0.8944 or abs(df.loc["test_mean", "worst_acc"] - 0.8944) < 6e-5
+    assert df.loc["test_std", "worst_acc"] == 0.0055            # not 0.0078 (std of the two seeds alone)
+    opt = sweep.parse_option(["--dataset", "celeba", "--tl_method", "adapter_reg_seq_alter", "--add_adapter", "--balance_val",
+                              "--epochs_feature_learning", "2", "--lr_list", "0.1,1.0", "--bs_list", "1024", "--bsr_list", "4,8",
+                              "--lr_multiple", "10", "--num_iter", "2", "--random_seeds", "42,32"])
+    pts = sweep.grid_points(opt)
+    assert pts == [(0.1, 1024, 4), (0.1, 1024, 8), (1.0, 1024, 4), (1.0, 1024, 8)]
+    assert [m[1:] for m in sweep.members(opt)][:3] == [(1, 42), (2, 32), (1, 42)]
+    o = sweep.member_options(opt, pts[1], 32)
+    assert (o.learning_rate, o.learning_rate_reg, o.batch_size, o.batch_size_reg, o.random_seed) == (0.1, 1.0, 1024, 8, 32)
+    assert sweep.csv_name(o) == "ds_celeba_tl_adapter_reg_seq_alter_bs_1024_lr_0.1_lrr1.0_bsr8_balval_MA+rn.csv"
