@@ -215,6 +215,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # the version banner goes to stdout, where ONE JSON line is expected
         dist.init_process_group("nccl", device_id=dev)
     P = peaks()
 
@@ -241,7 +243,7 @@ def main():
     gen = torch.Generator().manual_seed(7)
     orders = [torch.randperm(N_TRAIN, generator=gen).to(torch.int32).to(dev) for _ in range(4)]
     order_buf = torch.empty_like(orders[0])      # fixed address: the epoch's CUDA graph is cached by argument addresses
-    dp = parallel.DataParallelTrainer() if world > 1 else None
+    dp = parallel.DataParallelTrainer(local_batches=True) if world > 1 else None
 
     def train_epoch(i):
         stats.zero_()
@@ -249,24 +251,10 @@ def main():
             order_buf.copy_(orders[i % 4])
             ops.train_epoch(X, order_buf, BATCH, y, g, ad, That, 100.0, buf, lrs, stats, G=G)
         else:
-            # global batch = concatenation of every rank's 1024 local rows; this rank processes its own rows and the
-            # kernels are told B_global = world * B_local (BatchNorm / CE mean over the global batch)
-            order = orders[i % 4]
-            for s in range(steps_per_epoch):
-                idx = order[s * BATCH:(s + 1) * BATCH]
-                dp_step(idx, float(lrs[s]), s)
-
-    def dp_step(idx, lr, slot):
-        Bg = idx.numel() * world       # every rank's batch has the same size at every step (same N_TRAIN, same BATCH)
-        kw = dict(idx=idx, B_global=Bg, G=G)
-        ops.train_step(X, y, g, ad, That, 100.0, buf, lr, stats, slot, phases=1, **kw)
-        colsum, dgb = parallel.accum_views(ops.workspace(0, dev), H, 1)
-        dist.all_reduce(colsum)
-        ops.train_step(X, y, g, ad, That, 100.0, buf, lr, stats, slot, phases=2, **kw)
-        dist.all_reduce(dgb)
-        ops.train_step(X, y, g, ad, That, 100.0, buf, lr, stats, slot, phases=4, **kw)
-        dist.all_reduce(buf.grads)
-        ops.train_step(X, y, g, ad, That, 100.0, buf, lr, stats, slot, phases=8, **kw)
+            # weak scaling: every rank holds its own 162,770-row shard and contributes its own 1024 rows to each global
+            # batch of world x 1024; BatchNorm statistics / CE mean / gradients are those of the global batch
+            order_buf.copy_(orders[i % 4])
+            dp.train_epoch(X, order_buf, BATCH, y, g, ad, That, 100.0, buf, lrs, stats, G=G)
 
     def barrier():
         if world > 1:
@@ -386,17 +374,6 @@ def main():
             b["o"].copy_(oh[i % 4], non_blocking=True)
             b["ready"].record(copy_stream)
 
-    def dp_step_on(Xs, ys, gs, idx, lr, slot, st):
-        kw = dict(idx=idx, B_global=idx.numel() * world, G=G)
-        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, st, slot, phases=1, **kw)
-        colsum, dgb = parallel.accum_views(ops.workspace(0, dev), H, 1)
-        dist.all_reduce(colsum)
-        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, st, slot, phases=2, **kw)
-        dist.all_reduce(dgb)
-        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, st, slot, phases=4, **kw)
-        dist.all_reduce(buf.grads)
-        ops.train_step(Xs, ys, gs, ad, That, 100.0, buf, lr, st, slot, phases=8, **kw)
-
     def e2e_epoch(i):
         b = sets[i % 2]
         main_stream.wait_event(b["ready"])
@@ -405,8 +382,7 @@ def main():
         if world == 1:
             ops.train_epoch(b["X"], b["o"], BATCH, b["y"], b["g"], ad, That, 100.0, buf, lrs, b["st"], G=G)
         else:
-            for s in range(steps_per_epoch):
-                dp_step_on(b["X"], b["y"], b["g"], b["o"][s * BATCH:(s + 1) * BATCH], float(lrs[s]), s, b["st"])
+            dp.train_epoch(b["X"], b["o"], BATCH, b["y"], b["g"], ad, That, 100.0, buf, lrs, b["st"], G=G)
         loss_h.copy_(b["st"].loss_sum, non_blocking=True); cnt_h.copy_(b["st"].counts, non_blocking=True)
         b["free"].record(main_stream)
         main_stream.synchronize()                             # the step's result (loss / counters) is read on the host

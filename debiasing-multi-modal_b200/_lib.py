@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--expt-relaxed-constexpr", "--extended-lambda", "-shared", "-Xcompiler", "-fPIC"]
+              "--expt-relaxed-constexpr", "--extended-lambda", "-shared", "-Xcompiler", "-fPIC", "-ldl"]
 SOURCES = ["dbmm_api.cu"]
 
 MAX_H, MAX_C, MAX_G = 128, 16, 16
@@ -77,9 +77,17 @@ SIGNATURES = {
                                 _i64, BatchStats, _vp, _vp, _vp, _sz, _vp]),
     "dbmm_train_step": (C.c_int, [_i32, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32,
                                   _vp, _f32, _vp, _vp, _f32, _f32, _f32, _i32, BatchStats, _i64, _vp, _sz, _vp]),
+    "dbmm_train_step_ex": (C.c_int, [_i32, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32,
+                                     _vp, _f32, _vp, _vp, _f32, _vp, _f32, _f32, _i32, BatchStats, _i64, _vp, _sz, _vp]),
     "dbmm_train_epoch": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _AP, _AP, _f32,
                                    _vp, _f32, _vp, _vp, C.POINTER(C.c_float), _f32, _f32, _i32, BatchStats,
                                    _vp, _sz, _vp]),
+    "dbmm_comm_unique_id": (C.c_int, [_vp]),
+    "dbmm_comm_init": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
+    "dbmm_comm_destroy": (C.c_int, [_vp]),
+    "dbmm_train_epoch_dp": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _AP, _AP,
+                                      _f32, _vp, _f32, _vp, _vp, C.POINTER(C.c_float), _f32, _f32, _i32, BatchStats, _i32,
+                                      _vp, _sz, _vp]),
     "dbmm_train_epoch_profile": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _AP, _AP, _f32,
                                            _vp, _f32, _vp, _vp, C.POINTER(C.c_float), _f32, _f32, BatchStats,
                                            _vp, _sz, _vp, C.POINTER(C.c_float)]),

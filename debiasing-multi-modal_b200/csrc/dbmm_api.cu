@@ -10,6 +10,7 @@
 #include "wgrad_tc.cuh"
 #include "update.cuh"
 #include "head_supcon.cuh"
+#include "nccl_dyn.cuh"
 
 #include <mutex>
 #include <vector>
@@ -354,14 +355,14 @@ static int check_train_args(const float* X, int64_t ldx, const int32_t* y, int B
     return DBMM_OK;
 }
 
-int dbmm_train_step(int phases,
-                    const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
-                    int B_local, int64_t B_global, int D, int H, int C, int G,
-                    const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
-                    const float* That, float inv_tau,
-                    float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
-                    dbmm_batch_stats stats, int64_t slot,
-                    void* ws, size_t ws_bytes, void* stream) {
+int dbmm_train_step_ex(int phases, int fresh,
+                       const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                       int B_local, int64_t B_global, int D, int H, int C, int G,
+                       const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                       const float* That, float inv_tau,
+                       float* grads, float* momentum_buf, float lr, const float* lr_dev, float momentum, float weight_decay,
+                       int first_step, dbmm_batch_stats stats, int64_t slot,
+                       void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = check_train_args(X, ldx, y, B_local, B_global, D, H, C, G, old_ad, ad, That, ws, grads)) return rc;
     const int nad = old_ad ? 2 : 1;
@@ -372,8 +373,20 @@ int dbmm_train_step(int phases,
         // torch SGD: the momentum buffer starts as a copy of the first gradient == the recurrence from v = 0
         if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * dbmm_param_count(D, H), st));
     }
-    return train_step_impl(phases, true, X, ldx, idx, y, grp, B_local, B_global, D, H, C, G, old_ad, ad, ebd_weight, That,
-                           inv_tau, grads, momentum_buf, lr, nullptr, momentum, weight_decay, stats, slot, w, st);
+    return train_step_impl(phases, fresh != 0, X, ldx, idx, y, grp, B_local, B_global, D, H, C, G, old_ad, ad, ebd_weight, That,
+                           inv_tau, grads, momentum_buf, lr, lr_dev, momentum, weight_decay, stats, slot, w, st);
+}
+
+int dbmm_train_step(int phases,
+                    const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                    int B_local, int64_t B_global, int D, int H, int C, int G,
+                    const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                    const float* That, float inv_tau,
+                    float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
+                    dbmm_batch_stats stats, int64_t slot,
+                    void* ws, size_t ws_bytes, void* stream) {
+    return dbmm_train_step_ex(phases, 1, X, ldx, idx, y, grp, B_local, B_global, D, H, C, G, old_ad, ad, ebd_weight, That, inv_tau,
+                              grads, momentum_buf, lr, nullptr, momentum, weight_decay, first_step, stats, slot, ws, ws_bytes, stream);
 }
 
 namespace dbmm {
@@ -384,6 +397,7 @@ struct EpochKey {
     const void* X; int64_t ldx; const void* order; int64_t n_rows; int batch_size; const void* y; const void* grp;
     int D, H, C, G; dbmm_adapter old_ad; dbmm_adapter ad; int has_old; float ebd_weight; const void* That; float inv_tau;
     const void* grads; const void* mom; float momentum, wd; const void* loss_sum; const void* counts; const void* ws; int device;
+    const void* comm; int world, rank, local_batches;
 };
 struct EpochGraph { EpochKey key; cudaGraphExec_t exec; uint64_t stamp; };
 static std::mutex g_graph_mu;
@@ -399,36 +413,68 @@ static bool graphs_enabled() {
 
 }  // namespace dbmm
 
-int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
-                     const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
-                     const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
-                     const float* That, float inv_tau,
-                     float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
-                     int first_step, dbmm_batch_stats stats,
-                     void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+// One epoch, single GPU (comm == nullptr) or data parallel over an NCCL communicator created by dbmm_comm_init:
+// the kernels of every step and -- between its phases -- the all-reduces of the BatchNorm column sums, the (dgamma,
+// dbeta) sums and the flat gradient are enqueued on ONE stream, captured into a CUDA graph (NCCL supports capture) and
+// replayed.  local_batches: every rank's `order` lists its OWN rows (weak scaling, global batch = world x batch_size);
+// otherwise `order` is the global order and each rank takes its contiguous shard of every batch.
+static int train_epoch_impl(ncclComm_t comm, int world, int rank, int local_batches,
+                            const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                            const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
+                            const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                            const float* That, float inv_tau,
+                            float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
+                            int first_step, dbmm_batch_stats stats, int reduce_stats,
+                            void* ws, size_t ws_bytes, cudaStream_t st) {
     DBMM_CHECK_ARG(order && lr_host && momentum_buf, "NULL order / lr table / momentum buffer");
     DBMM_CHECK_ARG(n_rows >= 1 && batch_size >= 1, "bad n_rows=%lld batch_size=%d", (long long)n_rows, batch_size);
     const int64_t steps = (n_rows + batch_size - 1) / batch_size;
     const int B0 = (int)(n_rows < batch_size ? n_rows : batch_size);
     const int64_t last_B = n_rows - (steps - 1) * batch_size;
-    if (int rc = check_train_args(X, ldx, y, B0, B0, D, H, C, G, old_ad, ad, That, ws, grads)) return rc;
-    DBMM_CHECK_ARG(last_B > 1, "BatchNorm needs more than 1 row per batch in training (trailing batch of %lld)", (long long)last_B);
+    const bool dp = comm != nullptr && world > 1;
+    if (int rc = check_train_args(X, ldx, y, B0, (int64_t)B0 * (dp && local_batches ? world : 1), D, H, C, G, old_ad, ad, That, ws, grads)) return rc;
+    DBMM_CHECK_ARG(last_B * (dp && local_batches ? world : 1) > 1, "BatchNorm needs more than 1 row per batch in training (trailing batch of %lld)", (long long)last_B);
     DBMM_CHECK_ARG(steps <= DBMM_LR_TABLE, "an epoch of %lld steps exceeds the %d-entry learning-rate table", (long long)steps, DBMM_LR_TABLE);
+    DBMM_CHECK_ARG(!dp || local_batches || last_B >= world, "trailing batch of %lld rows cannot be sharded over %d ranks", (long long)last_B, world);
     const int nad = old_ad ? 2 : 1;
     TrainWs w = carve_train_ws(ws, B0, D, H, C, nad);
     DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    NcclApi* nc = dp ? nccl_api() : nullptr;
+    DBMM_CHECK_ARG(!dp || nc->ok, "NCCL is not available in this process");
+    const size_t np = dbmm_param_count(D, H);
 
-    if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * dbmm_param_count(D, H), st));
+    if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * np, st));
     DBMM_CUDA(cudaMemcpyAsync(w.lr, lr_host, sizeof(float) * (size_t)steps, cudaMemcpyHostToDevice, st));
 
     auto enqueue = [&](cudaStream_t s_) -> int {
         for (int64_t s = 0; s < steps; ++s) {
             const int64_t p0 = s * batch_size;
-            const int B = (int)((n_rows - p0) < batch_size ? (n_rows - p0) : batch_size);
-            int rc = train_step_impl(DBMM_PHASE_ALL, s == 0, X, ldx, order + p0, y, grp, B, B, D, H, C, G, old_ad, ad, ebd_weight,
-                                     That, inv_tau, grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, s_);
-            if (rc) return rc;
+            const int Bb = (int)((n_rows - p0) < batch_size ? (n_rows - p0) : batch_size);
+            const int32_t* idx = order + p0;
+            int B = Bb; int64_t Bg = Bb;
+            if (dp && local_batches) Bg = (int64_t)Bb * world;
+            else if (dp) {                                       // contiguous shard; the first Bb % world ranks get one extra row
+                const int base = Bb / world, extra = Bb % world;
+                const int lo = rank * base + (rank < extra ? rank : extra);
+                B = base + (rank < extra ? 1 : 0);
+                idx += lo;
+            }
+            auto phase = [&](int ph) {
+                return train_step_impl(ph, s == 0, X, ldx, idx, y, grp, B, Bg, D, H, C, G, old_ad, ad, ebd_weight, That, inv_tau,
+                                       grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, s_);
+            };
+            if (!dp) { if (int rc = phase(DBMM_PHASE_ALL)) return rc; continue; }
+            if (int rc = phase(DBMM_PHASE_GEMM1)) return rc;
+            DBMM_NCCL(nc->AllReduce(w.colsum, w.colsum, (size_t)nad * 2 * H, ncclFloat64, ncclSum, comm, s_));
+            if (int rc = phase(DBMM_PHASE_ROWS)) return rc;
+            DBMM_NCCL(nc->AllReduce(w.dgb, w.dgb, (size_t)2 * H, ncclFloat64, ncclSum, comm, s_));
+            if (int rc = phase(DBMM_PHASE_WGRAD)) return rc;
+            DBMM_NCCL(nc->AllReduce(grads, grads, np, ncclFloat32, ncclSum, comm, s_));
+            if (int rc = phase(DBMM_PHASE_UPDATE)) return rc;
+        }
+        if (dp && reduce_stats) {
+            if (stats.loss_sum) DBMM_NCCL(nc->AllReduce(stats.loss_sum, stats.loss_sum, (size_t)steps, ncclFloat64, ncclSum, comm, s_));
+            if (stats.counts) DBMM_NCCL(nc->AllReduce(stats.counts, stats.counts, (size_t)steps * 2 * G, ncclInt64, ncclSum, comm, s_));
         }
         return DBMM_OK;
     };
@@ -442,7 +488,8 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
     key.D = D; key.H = H; key.C = C; key.G = G; key.ad = *ad; key.has_old = old_ad ? 1 : 0; if (old_ad) key.old_ad = *old_ad;
     key.ebd_weight = ebd_weight; key.That = That; key.inv_tau = inv_tau; key.grads = grads; key.mom = momentum_buf;
     key.momentum = momentum; key.wd = weight_decay; key.loss_sum = stats.loss_sum; key.counts = stats.counts; key.ws = ws;
-    key.device = device;
+    key.device = device; key.comm = comm; key.world = dp ? world : 1; key.rank = dp ? rank : 0;
+    key.local_batches = (dp ? local_batches : 0) | (reduce_stats ? 2 : 0);
 
     std::lock_guard<std::mutex> lock(g_graph_mu);
     cudaGraphExec_t exec = nullptr;
@@ -471,6 +518,65 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
     }
     DBMM_CUDA(cudaGraphLaunch(exec, st));
     return DBMM_OK;
+}
+
+int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                     const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
+                     const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                     const float* That, float inv_tau,
+                     float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
+                     int first_step, dbmm_batch_stats stats,
+                     void* ws, size_t ws_bytes, void* stream) {
+    return train_epoch_impl(nullptr, 1, 0, 0, X, ldx, order, n_rows, batch_size, y, grp, D, H, C, G, old_ad, ad, ebd_weight, That,
+                            inv_tau, grads, momentum_buf, lr_host, momentum, weight_decay, first_step, stats, 0, ws, ws_bytes,
+                            (cudaStream_t)stream);
+}
+
+// ---- data parallel over one NVSwitch box: own NCCL communicator (rank 0 creates the id, the host broadcasts its 128 bytes)
+int dbmm_comm_unique_id(void* id_out_128_bytes) {
+    DBMM_CHECK_ARG(id_out_128_bytes != nullptr, "NULL id buffer");
+    NcclApi* nc = nccl_api();
+    DBMM_CHECK_ARG(nc->ok, "NCCL (libnccl.so.2) could not be loaded");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    DBMM_NCCL(nc->GetUniqueId((ncclUniqueId*)id_out_128_bytes));
+    return DBMM_OK;
+}
+
+int dbmm_comm_init(const void* id_128_bytes, int world, int rank, void** comm_out) {
+    DBMM_CHECK_ARG(id_128_bytes && comm_out && world >= 1 && rank >= 0 && rank < world, "bad communicator arguments");
+    NcclApi* nc = nccl_api();
+    DBMM_CHECK_ARG(nc->ok, "NCCL (libnccl.so.2) could not be loaded");
+    ncclUniqueId id;
+    memcpy(&id, id_128_bytes, sizeof(id));
+    ncclComm_t comm = nullptr;
+    DBMM_NCCL(nc->CommInitRank(&comm, world, id, rank));
+    *comm_out = comm;
+    return DBMM_OK;
+}
+
+int dbmm_comm_destroy(void* comm) {
+    if (!comm) return DBMM_OK;
+    {   // graphs that captured this communicator's collectives must not outlive it
+        std::lock_guard<std::mutex> lock(g_graph_mu);
+        for (size_t i = 0; i < g_graphs.size();)
+            if (g_graphs[i].key.comm == comm) { cudaGraphExecDestroy(g_graphs[i].exec); g_graphs.erase(g_graphs.begin() + i); } else ++i;
+    }
+    DBMM_NCCL(nccl_api()->CommDestroy((ncclComm_t)comm));
+    return DBMM_OK;
+}
+
+int dbmm_train_epoch_dp(void* comm, int world, int rank, int local_batches,
+                        const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                        const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
+                        const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                        const float* That, float inv_tau,
+                        float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
+                        int first_step, dbmm_batch_stats stats, int reduce_stats,
+                        void* ws, size_t ws_bytes, void* stream) {
+    DBMM_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && (world == 1 || comm != nullptr), "bad world=%d rank=%d / NULL communicator", world, rank);
+    return train_epoch_impl((ncclComm_t)comm, world, rank, local_batches, X, ldx, order, n_rows, batch_size, y, grp, D, H, C, G,
+                            old_ad, ad, ebd_weight, That, inv_tau, grads, momentum_buf, lr_host, momentum, weight_decay, first_step,
+                            stats, reduce_stats, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -188,8 +188,9 @@ class TrainBuffers:
 
 def train_step(X, y, grp, ad: AdapterTensors, That, inv_tau, buf: TrainBuffers, lr: float, stats: BatchStatsBuffers,
                slot: int = 0, *, idx=None, n_rows=None, B_global=None, old_ad=None, ebd_weight=0.5, G=4,
-               momentum=0.9, weight_decay=5e-5, phases=_lib.PHASE_ALL):
-    """One iteration of the train loops' body (final_main.py:455-466 / 610-623)."""
+               momentum=0.9, weight_decay=5e-5, phases=_lib.PHASE_ALL, fresh=True, lr_dev=None, first_step=None):
+    """One iteration of the train loops' body (final_main.py:455-466 / 610-623).  `fresh` / `lr_dev`: see
+    dbmm_train_step_ex (steps chained by the caller, learning rate read from device memory)."""
     lib = _lib.load()
     _check(X, torch.float32, "X", contiguous=False)
     _check(That, torch.float32, "That")
@@ -202,12 +203,13 @@ def train_step(X, y, grp, ad: AdapterTensors, That, inv_tau, buf: TrainBuffers, 
     nad = 2 if old_ad is not None else 1
     ws = workspace(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, B, D, H, Cn, nad), X.device)
     old_p = old_ad.ptrs() if old_ad is not None else None
-    _lib.check(lib.dbmm_train_step(phases, X.data_ptr(), X.stride(0), _ptr(idx), y.data_ptr(), _ptr(grp), B, Bg,
-                                   D, H, Cn, G, C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()),
-                                   ebd_weight, That.data_ptr(), inv_tau, buf.grads.data_ptr(), buf.momentum.data_ptr(),
-                                   lr, momentum, weight_decay, 1 if buf.first_step else 0, stats.c(), slot,
-                                   ws.data_ptr(), ws.numel(), _stream_ptr()))
-    if phases & _lib.PHASE_UPDATE:
+    first = buf.first_step if first_step is None else first_step
+    _lib.check(lib.dbmm_train_step_ex(phases, 1 if fresh else 0, X.data_ptr(), X.stride(0), _ptr(idx), y.data_ptr(), _ptr(grp),
+                                      B, Bg, D, H, Cn, G, C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()),
+                                      ebd_weight, That.data_ptr(), inv_tau, buf.grads.data_ptr(), buf.momentum.data_ptr(),
+                                      lr, _ptr(lr_dev), momentum, weight_decay, 1 if first else 0, stats.c(), slot,
+                                      ws.data_ptr(), ws.numel(), _stream_ptr()))
+    if phases & _lib.PHASE_UPDATE and first_step is None:
         buf.first_step = False
 
 

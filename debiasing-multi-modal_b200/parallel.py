@@ -37,22 +37,58 @@ def accum_views(ws: torch.Tensor, H: int, nad: int):
 
 
 class DataParallelTrainer:
-    """Runs the phases of dbmm_train_step with the all-reduces in between.  `step_fn` and `all_reduce` are
-    injectable so the sharding / reduction logic is testable on CPU with gloo (tests/test_parallel_cpu.py)."""
+    """Data-parallel training.  On CUDA the whole epoch runs inside libdbmm (`dbmm_train_epoch_dp`): the library owns an
+    NCCL communicator (created here: rank 0's unique id is broadcast with torch.distributed), and the kernels of every
+    step plus the three all-reduces between their phases are captured into one CUDA graph and replayed -- no host work
+    per step.  `step_fn` / `all_reduce` are injectable so that the sharding / reduction protocol is testable on CPU with
+    gloo, the oracle standing in for the kernels (tests/test_parallel_cpu.py); that path runs the phases of
+    dbmm_train_step eagerly with the all-reduces in between, and is also what DBMM_DP=eager selects on CUDA."""
 
-    def __init__(self, group=None, step_fn=None, all_reduce=None):
+    def __init__(self, group=None, step_fn=None, all_reduce=None, local_batches=False):
+        """local_batches=False: every rank passes the same GLOBAL index list and trains on its contiguous shard of it
+        (same global batch as a single-GPU run).  local_batches=True: every rank passes the indices of its OWN rows (its
+        own data shard, equal counts on all ranks) and the global batch is their union (weak scaling)."""
+        self.local_batches = local_batches
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._custom_step = step_fn is not None
         self._step = step_fn or ops.train_step
         self._all_reduce = all_reduce or (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group))
+        self._comm = None
 
+    # ---- native communicator --------------------------------------------------------------------------------------
+    def _native_comm(self, device):
+        if self._comm is None:
+            lib = _lib.load()
+            ident = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                buf = (C.c_ubyte * 128)()
+                _lib.check(lib.dbmm_comm_unique_id(buf))
+                ident = torch.tensor(list(buf), dtype=torch.uint8)
+            ident = ident.to(device)
+            dist.broadcast(ident, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+            raw = bytes(ident.cpu().tolist())
+            comm = C.c_void_p()
+            _lib.check(lib.dbmm_comm_init(raw, self.world, self.rank, C.byref(comm)))
+            self._comm = comm
+        return self._comm
+
+    def close(self):
+        if self._comm is not None:
+            _lib.check(_lib.load().dbmm_comm_destroy(self._comm))
+            self._comm = None
+
+    # ---- eager protocol (CPU tests, debugging) --------------------------------------------------------------------
     def train_step(self, X, y, grp, ad, That, inv_tau, buf, lr, stats, slot, global_idx: torch.Tensor, *, old_ad=None,
                    ebd_weight=0.5, G=4, momentum=0.9, weight_decay=5e-5):
         """global_idx: the GLOBAL batch's row indices (identical on every rank); this rank takes its shard."""
-        Bg = int(global_idx.numel())
-        lo, hi = shard_bounds(Bg, self.world, self.rank)
-        idx = global_idx[lo:hi].contiguous()
+        if self.local_batches:
+            idx, Bg = global_idx, int(global_idx.numel()) * self.world
+        else:
+            Bg = int(global_idx.numel())
+            lo, hi = shard_bounds(Bg, self.world, self.rank)
+            idx = global_idx[lo:hi].contiguous()
         kw = dict(idx=idx, B_global=Bg, old_ad=old_ad, ebd_weight=ebd_weight, G=G, momentum=momentum,
                   weight_decay=weight_decay)
         nad = 2 if old_ad is not None else 1
@@ -69,12 +105,47 @@ class DataParallelTrainer:
             self._all_reduce(buf.grads)
         self._step(X, y, grp, ad, That, inv_tau, buf, lr, stats, slot, phases=_lib.PHASE_UPDATE, **kw)
 
-    def train_epoch(self, X, order: torch.Tensor, batch_size_global: int, y, grp, ad, That, inv_tau, buf, lrs, stats, **kw):
+    def _eager_epoch(self, X, order, batch_size_global, y, grp, ad, That, inv_tau, buf, lrs, stats, **kw):
         n = order.numel()
         steps = (n + batch_size_global - 1) // batch_size_global
         for s in range(steps):
             self.train_step(X, y, grp, ad, That, inv_tau, buf, float(np.float32(lrs[s])), stats, s,
                             order[s * batch_size_global:(s + 1) * batch_size_global], **kw)
+        return steps
+
+    # ---- epoch ----------------------------------------------------------------------------------------------------
+    def train_epoch(self, X, order: torch.Tensor, batch_size_global: int, y, grp, ad, That, inv_tau, buf, lrs, stats, *,
+                    old_ad=None, ebd_weight=0.5, G=4, momentum=0.9, weight_decay=5e-5, reduce_stats=False):
+        """batch_size_global: rows of `order` consumed per step (the global batch when local_batches is False, this
+        rank's share of it otherwise)."""
+        import os
+        native = (not self._custom_step and getattr(X, "is_cuda", False) and os.environ.get("DBMM_DP", "native") != "eager")
+        if not native:
+            steps = self._eager_epoch(X, order, batch_size_global, y, grp, ad, That, inv_tau, buf, lrs, stats, old_ad=old_ad,
+                                      ebd_weight=ebd_weight, G=G, momentum=momentum, weight_decay=weight_decay)
+            if reduce_stats:
+                self.reduce_stats(stats)
+            return steps
+        lib = _lib.load()
+        D, H, Cn = X.shape[1], ad.H, That.shape[1]
+        n = order.numel()
+        steps = (n + batch_size_global - 1) // batch_size_global
+        lrs = np.ascontiguousarray(lrs, dtype=np.float32)
+        if len(lrs) < steps or stats.n_slots < steps:
+            raise _lib.DbmmError(f"need {steps} learning rates / stat slots")
+        nad = 2 if old_ad is not None else 1
+        ws = ops.workspace(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, min(batch_size_global, n), D, H, Cn, nad), X.device)
+        comm = self._native_comm(X.device) if self.world > 1 else None
+        old_p = old_ad.ptrs() if old_ad is not None else None
+        _lib.check(lib.dbmm_train_epoch_dp(comm, self.world, self.rank, 1 if self.local_batches else 0, X.data_ptr(), X.stride(0),
+                                           order.data_ptr(), n, batch_size_global, y.data_ptr(),
+                                           None if grp is None else grp.data_ptr(), D, H, Cn, G if grp is not None else 1,
+                                           C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()), ebd_weight,
+                                           That.data_ptr(), inv_tau, buf.grads.data_ptr(), buf.momentum.data_ptr(),
+                                           lrs.ctypes.data_as(C.POINTER(C.c_float)), momentum, weight_decay,
+                                           1 if buf.first_step else 0, stats.c(), 1 if reduce_stats else 0,
+                                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+        buf.first_step = False
         return steps
 
     def reduce_stats(self, stats: ops.BatchStatsBuffers):

@@ -139,6 +139,21 @@ int dbmm_train_step(int phases,
                     dbmm_batch_stats stats, int64_t slot,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* As dbmm_train_step, for callers that chain the steps of an epoch themselves (the data-parallel epoch graph):
+ *   fresh != 0   first step of a chain: accumulators are zeroed, Gram matrices and tf32 weight splits computed from
+ *                scratch; fresh == 0 relies on the previous step's WGRAD / UPDATE phases having prepared them (same
+ *                workspace, same adapters, no other dbmm call in between);
+ *   lr_dev       if not NULL the learning rate is read from this device address when the update kernel runs (a
+ *                captured CUDA graph can then be replayed with a new schedule). */
+int dbmm_train_step_ex(int phases, int fresh,
+                       const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                       int B_local, int64_t B_global, int D, int H, int C, int G,
+                       const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                       const float* That, float inv_tau,
+                       float* grads, float* momentum_buf, float lr, const float* lr_dev, float momentum, float weight_decay,
+                       int first_step, dbmm_batch_stats stats, int64_t slot,
+                       void* ws, size_t ws_bytes, void* stream);
+
 /*
  * A whole single-GPU epoch: ceil(n_rows / batch_size) steps over rows order[0..n_rows-1] (device int32,
  * the injected batch order), learning rate per step from lr_host[] (HOST array, one entry per step:
@@ -152,6 +167,31 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
                      float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
                      int first_step, dbmm_batch_stats stats,
                      void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Data-parallel epoch over the GPUs of one NVSwitch box, one process per GPU.  The library owns its NCCL communicator
+ * (libnccl.so.2 is bound with dlopen, preferring the copy PyTorch has already loaded): rank 0 calls
+ * dbmm_comm_unique_id, the host broadcasts the 128 bytes (torch.distributed), every rank calls dbmm_comm_init.
+ * dbmm_train_epoch_dp is dbmm_train_epoch with, per step, the all-reduces of the BatchNorm column sums, the (dgamma,
+ * dbeta) sums and the flat gradient between the phases, so that BatchNorm and the CE mean see the GLOBAL batch
+ * (the reference is single-process); kernels and collectives are captured in one CUDA graph.
+ *   local_batches == 0: `order` is the global batch order (identical on all ranks); each rank trains on its contiguous
+ *                       shard of every batch -- same result as one GPU.
+ *   local_batches != 0: `order` lists this rank's own rows (equal n_rows / batch_size on all ranks); the global batch is
+ *                       the union, world x batch_size rows (weak scaling).
+ *   reduce_stats  != 0: the per-batch loss sums / group counters are all-reduced at the end of the epoch.
+ */
+int dbmm_comm_unique_id(void* id_out_128_bytes);
+int dbmm_comm_init(const void* id_128_bytes, int world, int rank, void** comm_out);
+int dbmm_comm_destroy(void* comm);
+int dbmm_train_epoch_dp(void* comm, int world, int rank, int local_batches,
+                        const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                        const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
+                        const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                        const float* That, float inv_tau,
+                        float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
+                        int first_step, dbmm_batch_stats stats, int reduce_stats,
+                        void* ws, size_t ws_bytes, void* stream);
 
 /* Measurement aid: the same epoch as stream launches with CUDA events between the kernels of every step;
  * kernel_us_host[6] = mean device microseconds of GEMM-1, reduce/statistics, row kernel, dW1, gradient finalisation,
