@@ -27,6 +27,25 @@ void set_error(const char* fmt, ...) {
 }
 
 constexpr int64_t EVAL_CHUNK = 16384;
+constexpr int64_t EVAL_TC_CHUNK = 32768;       // rows per pass of the tensor-core eval path: its h tiles (32 MB) stay in L2
+constexpr int EVAL_TAIL_LD = 32;
+
+struct EvalTcWs { float *gram, *whi, *wlo, *hhi, *hlo, *rowdot, *tail, *bthi, *btlo, *bias; int64_t chunk; size_t total; };
+static EvalTcWs carve_eval_tc_ws(void* base, int64_t N, int D, int H, int C, int nad) {
+    EvalTcWs w; char* p = (char*)base; size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+    const int ldg = H + 1 + C;
+    w.chunk = N < EVAL_TC_CHUNK ? N : EVAL_TC_CHUNK;
+    const size_t o1 = take(sizeof(float) * (size_t)nad * (H + 1) * ldg), o2 = take(sizeof(float) * (size_t)nad * H * D),
+                 o3 = take(sizeof(float) * (size_t)nad * H * D), o4 = take(sizeof(float) * (size_t)nad * w.chunk * H),
+                 o5 = take(sizeof(float) * (size_t)nad * w.chunk * H), o6 = take(sizeof(float) * (size_t)nad * w.chunk),
+                 o7 = take(sizeof(float) * (size_t)nad * w.chunk * EVAL_TAIL_LD), o8 = take(sizeof(float) * (size_t)nad * ldg * H),
+                 o9 = take(sizeof(float) * (size_t)nad * ldg * H), o10 = take(sizeof(float) * (size_t)nad * 256);
+    w.total = off;
+    w.gram = (float*)(p + o1); w.whi = (float*)(p + o2); w.wlo = (float*)(p + o3); w.hhi = (float*)(p + o4); w.hlo = (float*)(p + o5);
+    w.rowdot = (float*)(p + o6); w.tail = (float*)(p + o7); w.bthi = (float*)(p + o8); w.btlo = (float*)(p + o9); w.bias = (float*)(p + o10);
+    return w;
+}
 
 static int check_dims(int D, int H, int C, int G) {
     DBMM_CHECK_SHAPE(D >= 4 && D % 4 == 0, "D=%d must be a positive multiple of 4", D);
@@ -163,6 +182,78 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
     return DBMM_OK;
 }
 
+static bool use_tc_eval(int D, int H, int C) {
+    const char* e = getenv("DBMM_EVAL");           // debugging switch: DBMM_EVAL=simt forces the fp32 SIMT row kernel
+    if (e && strcmp(e, "simt") == 0) return false;
+    return H == 128 && D % G1_BK == 0 && C <= 16;
+}
+
+// Eval forward on the tensor cores, three stages per pass of <= 32768 rows (their intermediates stay in L2):
+//   1. GEMM-1 (tcgen05, tf32 hi/lo weights) with the running-stat BatchNorm + ReLU in the epilogue -> h = hi + lo
+//   2. H-space GEMM t = [h, 1] G (tcgen05 + TMA, 3xTF32) reduced in the epilogue to  sum_j t_j h_j  and  t[H .. H+C]
+//   3. finishing kernel: n^2, cosine logits, CE, argmax, per-group counters
+static int eval_fwd_tc(const float* X, int64_t ldx, const int32_t* idx, const int32_t* y, const int32_t* grp,
+                       int64_t N, int D, int H, int C, int G, const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                       const float* That, float inv_tau, int64_t batch_size, dbmm_batch_stats stats, float* logits_out,
+                       int32_t* pred_out, void* ws, cudaStream_t st) {
+    const int nad = old_ad ? 2 : 1, ldg = H + 1 + C;
+    EvalTcWs w = carve_eval_tc_ws(ws, N, D, H, C, nad);
+    const dbmm_adapter* ads[2] = {old_ad ? old_ad : ad, ad};
+    DBMM_CUDA(cudaMemsetAsync(w.gram, 0, sizeof(float) * (size_t)nad * (H + 1) * ldg, st));
+    if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
+    for (int i = 0; i < nad; ++i) {
+        k_split_tf32<<<148, 256, 0, st>>>(ads[i]->W1, w.whi + (size_t)i * H * D, w.wlo + (size_t)i * H * D, (int64_t)H * D);
+        k_gram_operand<<<64, 256, 0, st>>>(w.gram + (size_t)i * (H + 1) * ldg, H, ldg, w.bthi + (size_t)i * ldg * H,
+                                           w.btlo + (size_t)i * ldg * H, w.bias + (size_t)i * 256);
+        DBMM_LAUNCH_CHECK();
+    }
+    for (int64_t pos0 = 0; pos0 < N; pos0 += w.chunk) {
+        const int B = (int)((N - pos0) < w.chunk ? (N - pos0) : w.chunk);
+        Gemm1TcArgs t;
+        memset(&t, 0, sizeof(t));
+        t.X = X; t.ldx = ldx; t.idx = idx; t.pos0 = pos0; t.B = B; t.D = D; t.H = H; t.nad = nad; t.ksplit = 1;
+        for (int i = 0; i < 2; ++i) {
+            const int k = nad == 2 ? i : 0;
+            t.Whi[i] = w.whi + (size_t)k * H * D; t.Wlo[i] = w.wlo + (size_t)k * H * D; t.b1[i] = ads[nad == 2 ? i : 1]->b1;
+            t.bn_mean[i] = ads[nad == 2 ? i : 1]->running_mean; t.bn_var[i] = ads[nad == 2 ? i : 1]->running_var;
+            t.bn_gamma[i] = ads[nad == 2 ? i : 1]->gamma; t.bn_beta[i] = ads[nad == 2 ? i : 1]->beta;
+        }
+        t.hhi = w.hhi; t.hlo = w.hlo;
+        if (idx == nullptr && ldx % 4 == 0) {
+            // contiguous rows: X tiles by TMA (one instruction per 16 KB tile instead of 1,024 16-byte cp.async)
+            for (int i = 0; i < nad; ++i) {
+                TcGemmArgs g;
+                memset(&g, 0, sizeof(g));
+                const dbmm_adapter* a_i = ads[nad == 2 ? i : 1];
+                g.M = B; g.N = H; g.K = D; g.scale = 1.f;
+                g.e_b1 = a_i->b1; g.e_mean = a_i->running_mean; g.e_var = a_i->running_var; g.e_gamma = a_i->gamma; g.e_beta = a_i->beta;
+                g.e_hhi = w.hhi + (size_t)i * B * H; g.e_hlo = w.hlo + (size_t)i * B * H;
+                if (int rc = launch_tc_gemm_nt<false, EPI_EVAL_H>(X + pos0 * ldx, nullptr, ldx, w.whi + (size_t)i * H * D,
+                                                                  w.wlo + (size_t)i * H * D, D, g, st)) return rc;
+            }
+        } else if (int rc = launch_gemm1_tc(t, 128, st)) return rc;
+        for (int i = 0; i < nad; ++i) {
+            TcGemmArgs g;
+            memset(&g, 0, sizeof(g));
+            g.M = B; g.N = ldg; g.K = H; g.scale = 1.f;
+            g.hs_hi = w.hhi + (size_t)i * B * H; g.hs_lo = w.hlo + (size_t)i * B * H; g.hs_ld = H; g.hs_bias = w.bias + (size_t)i * 256;
+            g.rowdot = w.rowdot + (size_t)i * w.chunk; g.tail = w.tail + (size_t)i * w.chunk * EVAL_TAIL_LD; g.tail_ld = EVAL_TAIL_LD;
+            if (int rc = launch_tc_gemm_nt<true, EPI_HSPACE>(g.hs_hi, g.hs_lo, H, w.bthi + (size_t)i * ldg * H, w.btlo + (size_t)i * ldg * H, H, g, st)) return rc;
+        }
+        EvalFinishArgs f;
+        memset(&f, 0, sizeof(f));
+        f.n = B; f.pos0 = pos0; f.nad = nad; f.C = C; f.G = G; f.tail_ld = EVAL_TAIL_LD;
+        for (int i = 0; i < nad; ++i) { f.rowdot[i] = w.rowdot + (size_t)i * w.chunk; f.tail[i] = w.tail + (size_t)i * w.chunk * EVAL_TAIL_LD; }
+        f.w_old = ebd_weight; f.inv_tau = inv_tau; f.idx = idx; f.y = y; f.grp = grp; f.batch_size = batch_size;
+        f.loss_sum = stats.loss_sum; f.counts = stats.counts; f.logits_out = logits_out; f.pred_out = pred_out;
+        int grid = ceil_div(B, 256);
+        if (grid > 148 * 8) grid = 148 * 8;
+        k_eval_finish<<<grid, 256, 0, st>>>(f);
+        DBMM_LAUNCH_CHECK();
+    }
+    return DBMM_OK;
+}
+
 }  // namespace dbmm
 
 using namespace dbmm;
@@ -182,9 +273,11 @@ size_t dbmm_workspace_bytes(int op, int64_t rows, int D, int H, int C, int n_ada
     if (op == DBMM_OP_TRAIN) return carve_train_ws(nullptr, rows, D, H, C, n_adapters).total;
     if (op == DBMM_OP_EVAL) {
         const int64_t chunk = rows < EVAL_CHUNK ? rows : EVAL_CHUNK;
-        return align_up(sizeof(float) * (size_t)n_adapters * (H + 1) * (H + 1 + C), 256) +
-               align_up(sizeof(float) * (size_t)n_adapters * chunk * H, 256) +
-               2 * align_up(sizeof(float) * (size_t)n_adapters * H * D, 256);
+        const size_t simt = align_up(sizeof(float) * (size_t)n_adapters * (H + 1) * (H + 1 + C), 256) +
+                            align_up(sizeof(float) * (size_t)n_adapters * chunk * H, 256) +
+                            2 * align_up(sizeof(float) * (size_t)n_adapters * H * D, 256);
+        const size_t tc = carve_eval_tc_ws(nullptr, rows, D, H, C, n_adapters).total;
+        return simt > tc ? simt : tc;
     }
     return 0;
 }
@@ -225,6 +318,8 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
     if (N == 0) return DBMM_OK;
     const int nad = old_ad ? 2 : 1;
     DBMM_CHECK_ARG(dbmm_workspace_bytes(DBMM_OP_EVAL, N, D, H, C, nad) <= ws_bytes, "workspace too small");
+    if (use_tc_eval(D, H, C)) return eval_fwd_tc(X, ldx, idx, y, grp, N, D, H, C, G, old_ad, ad, ebd_weight, That, inv_tau, batch_size,
+                                                 stats, logits_out, pred_out, ws, st);
     float* gram = (float*)ws;
     float* A = (float*)((char*)ws + align_up(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C), 256));
     const int64_t chunk_rows = N < EVAL_CHUNK ? N : EVAL_CHUNK;

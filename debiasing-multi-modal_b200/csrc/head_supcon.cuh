@@ -178,3 +178,92 @@ __global__ void __launch_bounds__(256) k_supcon_rows(float* __restrict__ S, int6
 __global__ void k_supcon_scale(const int* n_valid, float factor, float* scale) { scale[0] = factor / (float)max(n_valid[0], 1); }
 
 }  // namespace dbmm
+
+namespace dbmm {
+
+// ------------------------------------------------------------------------------------------------
+// Eval forward, tensor-core path (validate / validate_zs through the adapter): finishing kernel.
+//   n^2 = rowdot + tail[0] (= t[H]);  s_c = tail[1 + c];  logit_c = s_c / (n tau)  (two adapters: 0.5 / 0.5 mix of the two
+//   normalised outputs, final_main.py:121-140), then CE / argmax / per-group counters as update_dict (final_main.py:383-391).
+// ------------------------------------------------------------------------------------------------
+struct EvalFinishArgs {
+    int64_t n, pos0; int nad, C, G; int tail_ld;
+    const float* rowdot[2]; const float* tail[2];
+    float w_old, inv_tau;
+    const int32_t* idx; const int32_t* y; const int32_t* grp;
+    int64_t batch_size; double* loss_sum; int64_t* counts; float* logits_out; int32_t* pred_out;
+};
+
+__global__ void __launch_bounds__(256) k_eval_finish(EvalFinishArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp_global * 32; base < a.n; base += nwarps * 32) {
+        const int64_t r = base + lane;
+        const bool valid = r < a.n;
+        int gv = -1, corr = 0; float nll = 0.f;
+        if (valid) {
+            const int64_t pos = a.pos0 + r;
+            const int64_t dsrow = a.idx ? (int64_t)a.idx[pos] : pos;
+            const int yv = a.y ? a.y[dsrow] : -1;
+            gv = a.grp ? a.grp[dsrow] : 0;
+            float l[DBMM_MAX_C];
+            float mx = -INFINITY; int am = 0;
+            const float inv_n1 = 1.0f / sqrtf(a.rowdot[a.nad - 1][r] + a.tail[a.nad - 1][(size_t)r * a.tail_ld]);
+            const float inv_n0 = a.nad == 2 ? 1.0f / sqrtf(a.rowdot[0][r] + a.tail[0][(size_t)r * a.tail_ld]) : 0.f;
+            const float coef = a.nad == 2 ? (1.0f - a.w_old) : 1.0f;
+            for (int c = 0; c < a.C; ++c) {
+                const float lnew = a.inv_tau * a.tail[a.nad - 1][(size_t)r * a.tail_ld + 1 + c] * inv_n1;
+                float v = lnew;
+                if (a.nad == 2) v = fmaf(coef, lnew, a.w_old * a.inv_tau * a.tail[0][(size_t)r * a.tail_ld + 1 + c] * inv_n0);
+                l[c] = v;
+                if (v > mx) { mx = v; am = c; }
+                if (a.logits_out) a.logits_out[(size_t)pos * a.C + c] = v;
+            }
+            float se = 0.f, ly = 0.f;
+            for (int c = 0; c < a.C; ++c) { se += expf(l[c] - mx); if (c == yv) ly = l[c]; }
+            nll = a.y ? (logf(se) + mx - ly) : 0.f;
+            corr = am == yv;
+            if (a.pred_out) a.pred_out[pos] = am;
+        }
+        const int64_t slot = valid ? (a.pos0 + r) / a.batch_size : -1;
+        const int64_t slot0 = __shfl_sync(0xffffffffu, slot, 0);
+        const bool uniform = __all_sync(0xffffffffu, !valid || slot == slot0);
+        if (uniform) {
+            const double tot = warp_sum((double)nll);
+            if (lane == 0 && a.loss_sum) atomicAdd(&a.loss_sum[slot0], tot);
+            const unsigned cmask = __ballot_sync(0xffffffffu, corr != 0);
+            for (int g = 0; g < a.G; ++g) {
+                const unsigned gm = __ballot_sync(0xffffffffu, gv == g);
+                if (lane == 0 && gm && a.counts) {
+                    int64_t* cnt = a.counts + (size_t)slot0 * 2 * a.G;
+                    const int nc = __popc(gm & cmask);
+                    if (nc) atomicAdd((unsigned long long*)&cnt[g], (unsigned long long)nc);
+                    atomicAdd((unsigned long long*)&cnt[a.G + g], (unsigned long long)__popc(gm));
+                }
+            }
+        } else if (valid) {
+            if (a.loss_sum) atomicAdd(&a.loss_sum[slot], (double)nll);
+            if (a.counts && gv >= 0 && gv < a.G) {
+                int64_t* cnt = a.counts + (size_t)slot * 2 * a.G;
+                if (corr) atomicAdd((unsigned long long*)&cnt[gv], 1ull);
+                atomicAdd((unsigned long long*)&cnt[a.G + gv], 1ull);
+            }
+        }
+    }
+}
+
+// B operand of the H-space GEMM from the Gram matrix G [(H+1)][ldg]:  Bt[n][k] = G[k][n] (k < H), split hi + lo;
+// bias[n] = G[H][n] (the row that multiplies the constant 1 of [h, 1]).
+__global__ void __launch_bounds__(256) k_gram_operand(const float* __restrict__ G, int H, int ldg, float* __restrict__ bt_hi,
+                                                      float* __restrict__ bt_lo, float* __restrict__ bias) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ldg * H; e += gridDim.x * blockDim.x) {
+        const int n = e / H, k = e - n * H;
+        const float v = G[(size_t)k * ldg + n];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        bt_hi[e] = h; bt_lo[e] = v - h;
+    }
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < ldg; n += gridDim.x * blockDim.x) bias[n] = G[(size_t)H * ldg + n];
+}
+
+}  // namespace dbmm

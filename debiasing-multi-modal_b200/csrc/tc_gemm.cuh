@@ -21,7 +21,7 @@ namespace dbmm {
 
 constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 32, TG_THREADS = 192;
 constexpr int TG_TILE_BYTES = 128 * 128;                    // one 128-row x 32-float operand tile
-enum { EPI_STORE = 0, EPI_SOFTMAX_PART = 1 };
+enum { EPI_STORE = 0, EPI_SOFTMAX_PART = 1, EPI_HSPACE = 2, EPI_EVAL_H = 3 };
 
 struct SoftmaxPart { float mx, se, ly; int am; };           // per (row, column tile): max, sum exp(l - max), target logit, argmax
 
@@ -33,6 +33,11 @@ struct TcGemmArgs {
     const int32_t* y; const int32_t* idx;                   // EPI_SOFTMAX_PART: target column per DATASET row, row list (or null)
     int64_t pos0;
     SoftmaxPart* part;                                      // [M][gridDim.x]
+    // EPI_HSPACE (eval forward, t = [h, 1] G with G^T as the B operand): column tile 0 reduces t[0:128] to
+    // rowdot[m] = sum_j t_j h_j (h = Ahi + Alo, re-read from global), further tiles store t[128 + j] to tail[m][j]
+    const float* hs_hi; const float* hs_lo; int64_t hs_ld; const float* hs_bias; float* rowdot; float* tail; int tail_ld;
+    // EPI_EVAL_H (GEMM-1 of the eval forward): h = relu(BatchNorm_running(acc + b1)) split into tf32 hi + lo, [M][N] each
+    const float* e_b1; const float* e_mean; const float* e_var; const float* e_gamma; const float* e_beta; float* e_hhi; float* e_hlo;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -177,6 +182,69 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         if (nb + j < a.N) crow[ch * 32 + j] = scale * __uint_as_float(r[j]) + (a.accumulate ? crow[ch * 32 + j] : 0.f);
                 }
             }
+        } else if (EPI == EPI_EVAL_H) {
+#pragma unroll 1
+            for (int ch = 0; ch < TG_BN / 32; ++ch) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, r);
+                ptx::tmem_ld_wait();
+                const int nb = n0 + ch * 32;
+                if (!row_ok || nb >= a.N) continue;
+                float hi[32], lo[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.e_b1 + nb) + j4);
+                    const float4 mu = __ldg(reinterpret_cast<const float4*>(a.e_mean + nb) + j4);
+                    const float4 va = __ldg(reinterpret_cast<const float4*>(a.e_var + nb) + j4);
+                    const float4 ga = __ldg(reinterpret_cast<const float4*>(a.e_gamma + nb) + j4);
+                    const float4 be = __ldg(reinterpret_cast<const float4*>(a.e_beta + nb) + j4);
+                    const float b1x[4] = {b1.x, b1.y, b1.z, b1.w}, mux[4] = {mu.x, mu.y, mu.z, mu.w}, vax[4] = {va.x, va.y, va.z, va.w};
+                    const float gax[4] = {ga.x, ga.y, ga.z, ga.w}, bex[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 4 * j4 + e;
+                        const float ah = (__uint_as_float(r[j]) + b1x[e] - mux[e]) * (1.0f / sqrtf(vax[e] + DBMM_BN_EPS));
+                        const float h = fmaxf(fmaf(ah, gax[e], bex[e]), 0.f);
+                        hi[j] = __uint_as_float(__float_as_uint(h) & 0xffffe000u);
+                        lo[j] = h - hi[j];
+                    }
+                }
+                const size_t off = (size_t)m * a.N + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    *reinterpret_cast<float4*>(a.e_hhi + off + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+                    *reinterpret_cast<float4*>(a.e_hlo + off + j) = make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+                }
+            }
+        } else if (EPI == EPI_HSPACE) {
+            float dot = 0.f;
+#pragma unroll 1
+            for (int ch = 0; ch < TG_BN / 32; ++ch) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, r);
+                ptx::tmem_ld_wait();
+                if (!row_ok) continue;
+                const int nb = n0 + ch * 32;
+                if (nb >= a.N) continue;
+                if (blockIdx.x == 0) {
+                    const float4* hh = reinterpret_cast<const float4*>(a.hs_hi + (size_t)m * a.hs_ld + nb);
+                    const float4* hl = reinterpret_cast<const float4*>(a.hs_lo + (size_t)m * a.hs_ld + nb);
+                    const float4* gb = reinterpret_cast<const float4*>(a.hs_bias + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 x = __ldcg(hh + j), y4 = __ldcg(hl + j), b = __ldg(gb + j);
+                        dot = fmaf(__uint_as_float(r[4 * j + 0]) + b.x, x.x + y4.x, dot);
+                        dot = fmaf(__uint_as_float(r[4 * j + 1]) + b.y, x.y + y4.y, dot);
+                        dot = fmaf(__uint_as_float(r[4 * j + 2]) + b.z, x.z + y4.z, dot);
+                        dot = fmaf(__uint_as_float(r[4 * j + 3]) + b.w, x.w + y4.w, dot);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < a.N) a.tail[(size_t)m * a.tail_ld + (nb - TG_BN) + j] = __uint_as_float(r[j]) + __ldg(a.hs_bias + nb + j);
+                }
+            }
+            if (row_ok && blockIdx.x == 0) a.rowdot[m] = dot;
         } else {
             int yv = -1;
             if (row_ok && a.y) {
