@@ -11,6 +11,7 @@
 #include "update.cuh"
 #include "head_supcon.cuh"
 #include "nccl_dyn.cuh"
+#include "linear_probe.cuh"
 
 #include <mutex>
 #include <vector>
@@ -721,8 +722,8 @@ size_t dbmm_supcon_workspace_bytes(int Bl, int Bg, int d) {
 }
 
 int dbmm_logits_ce(const float* U, int64_t ldu, const int32_t* idx, const int32_t* y, const int32_t* grp,
-                   int64_t N, int D, int C, int G, const float* That, float inv_tau, int normalize_rows, int64_t batch_size,
-                   dbmm_batch_stats stats, int32_t* pred_out, void* ws, size_t ws_bytes, void* stream) {
+                   int64_t N, int D, int C, int G, const float* That, const float* col_bias, float inv_tau, int normalize_rows,
+                   int64_t batch_size, dbmm_batch_stats stats, int32_t* pred_out, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     DBMM_CHECK_ARG(U && That && ws, "NULL U / That / workspace");
     DBMM_CHECK_SHAPE(D >= 4 && D % 4 == 0 && C >= 1 && G >= 1 && G <= DBMM_MAX_G, "bad D=%d C=%d G=%d", D, C, G);
@@ -749,7 +750,7 @@ int dbmm_logits_ce(const float* U, int64_t ldu, const int32_t* idx, const int32_
         }
         TcGemmArgs g;
         memset(&g, 0, sizeof(g));
-        g.M = (int)n; g.N = C; g.K = D; g.scale = inv_tau; g.rowscale = normalize_rows ? w.inv_norm : nullptr;
+        g.M = (int)n; g.N = C; g.K = D; g.scale = inv_tau; g.rowscale = normalize_rows ? w.inv_norm : nullptr; g.col_bias = col_bias;
         g.y = y; g.idx = idx; g.pos0 = pos0; g.part = w.part;
         if (int rc = launch_tc_gemm_nt<false, EPI_SOFTMAX_PART>(A, nullptr, lda, w.thi, w.tlo, D, g, st)) return rc;
         k_head_finish<<<ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8, 256, 0, st>>>(
@@ -862,6 +863,36 @@ int dbmm_train_epoch_profile(const float* X, int64_t ldx, const int32_t* order, 
     }
     for (auto& e : ev) cudaEventDestroy(e);
     return rc;
+}
+
+// Linear probing epoch (train_one_epoch with LinearClassifier, final_main.py:426-496): per step one forward / CE /
+// gradient kernel and the SGD update of W [C, D] and b [C]; grads / momentum: flat [C*D + C] buffers (W | b).
+int dbmm_linear_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                            const int32_t* y, const int32_t* grp, int D, int C, int G, float* W, float* b,
+                            float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
+                            int first_step, dbmm_batch_stats stats, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DBMM_CHECK_ARG(X && order && y && W && b && grads && momentum_buf && lr_host, "NULL argument");
+    DBMM_CHECK_SHAPE(D >= 1 && C >= 1 && C <= LP_MAXC && G >= 1 && G <= DBMM_MAX_G, "bad D=%d C=%d G=%d", D, C, G);
+    DBMM_CHECK_ARG(n_rows >= 1 && batch_size >= 1 && ldx >= D, "bad n_rows / batch_size / ldx");
+    const int64_t steps = (n_rows + batch_size - 1) / batch_size;
+    const size_t nW = (size_t)C * D;
+    for (int64_t s = 0; s < steps; ++s) {
+        const int64_t p0 = s * batch_size;
+        const int B = (int)((n_rows - p0) < batch_size ? (n_rows - p0) : batch_size);
+        DBMM_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (nW + C), st));
+        LinearStepArgs a;
+        a.X = X; a.ldx = ldx; a.idx = order + p0; a.y = y; a.grp = grp; a.B = B; a.D = D; a.C = C; a.G = G; a.W = W; a.b = b;
+        a.gW = grads; a.gb = grads + nW; a.loss_sum = stats.loss_sum; a.counts = stats.counts; a.slot = s;
+        k_linear_train<<<ceil_div(B, LP_ROWS), LP_THREADS, 0, st>>>(a);
+        DBMM_LAUNCH_CHECK();
+        const int first = (first_step && s == 0) ? 1 : 0;
+        k_sgd_flat<<<ceil_div((int64_t)nW, 256 * 4) > 1184 ? 1184 : ceil_div((int64_t)nW, 256 * 4), 256, 0, st>>>(
+            W, grads, momentum_buf, (int64_t)nW, lr_host[s], momentum, weight_decay, first);
+        k_sgd_flat<<<1, 32, 0, st>>>(b, grads + nW, momentum_buf + nW, (int64_t)C, lr_host[s], momentum, weight_decay, first);
+        DBMM_LAUNCH_CHECK();
+    }
+    return DBMM_OK;
 }
 
 int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float momentum, float weight_decay,

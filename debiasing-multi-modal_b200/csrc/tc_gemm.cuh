@@ -9,6 +9,8 @@
 //   * "3xTF32": the B side always arrives pre-split (B = Bhi + Blo, Bhi tf32-exact); the A side either arrives
 //     pre-split too (SPLIT_A: terms Ahi*Bhi + Alo*Bhi + Ahi*Blo, fp32-level accuracy for arbitrary data) or is used as
 //     stored (terms A*Bhi + A*Blo: exact when A is tf32-representable, e.g. fp16-valued CLIP embeddings).
+//   * persistent CTAs (one per SM) walk the output tiles; the fp32 accumulator is double-buffered in TMEM (2 x 128
+//     columns) so the epilogue of tile i overlaps the MMAs of tile i+1, and set-up costs are paid once per SM;
 //   * one elected thread issues 2-D tiled TMA loads (SWIZZLE_128B boxes of 32 floats x 128 rows) into a 3-4 stage
 //     ring guarded by full/empty mbarriers; one thread issues the MMAs; four warps drain TMEM.
 //   * epilogues: EPI_STORE writes the scaled tile; EPI_SOFTMAX_PART reduces the tile to per-row online-softmax
@@ -29,10 +31,11 @@ struct TcGemmArgs {
     int M, N, K;
     float scale;                                            // acc * scale * (*scale_dev) * rowscale[m]
     const float* scale_dev; const float* rowscale;          // optional (null = 1)
+    const float* col_bias;                                  // EPI_SOFTMAX_PART: optional additive bias per column (linear probe)
     float* C; int64_t ldc; int accumulate;                  // EPI_STORE: C = [C +] scaled tile
     const int32_t* y; const int32_t* idx;                   // EPI_SOFTMAX_PART: target column per DATASET row, row list (or null)
     int64_t pos0;
-    SoftmaxPart* part;                                      // [M][gridDim.x]
+    SoftmaxPart* part;                                      // [M][number of column tiles]
     // EPI_HSPACE (eval forward, t = [h, 1] G with G^T as the B operand): column tile 0 reduces t[0:128] to
     // rowdot[m] = sum_j t_j h_j (h = Ahi + Alo, re-read from global), further tiles store t[128 + j] to tail[m][j]
     const float* hs_hi; const float* hs_lo; int64_t hs_ld; const float* hs_bias; float* rowdot; float* tail; int tail_ld;
@@ -83,21 +86,23 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     uint8_t* smem = (uint8_t*)(((uintptr_t)tg_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + (size_t)S * Cfg::STAGE_BYTES);
     uint64_t* empty = full + S;
-    uint64_t* tmem_full = empty + S;
-    uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
+    uint64_t* tmem_full = empty + S;                                  // [2] accumulator stage ready for the epilogue
+    uint64_t* tmem_empty = tmem_full + 2;                             // [2] accumulator stage drained by the epilogue
+    uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n0 = blockIdx.x * TG_BN, m0 = blockIdx.y * TG_BM;       // column tiles fastest: CTAs sharing an A row tile run together
+    const int n_ntiles = (a.N + TG_BN - 1) / TG_BN, n_mtiles = (a.M + TG_BM - 1) / TG_BM;
+    const int total_tiles = n_ntiles * n_mtiles;                      // column tiles fastest: CTAs sharing an A row tile run together
     const int KB = (a.K + TG_BK - 1) / TG_BK;                         // the K tail is zero-filled by TMA
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-        ptx::mbar_init(tmem_full, 1);
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 128); }
         ptx::fence_mbar_init();
         ptx::tma_prefetch_desc(&mapA); ptx::tma_prefetch_desc(&mapBhi); ptx::tma_prefetch_desc(&mapBlo);
         if (SPLIT_A) ptx::tma_prefetch_desc(&mapAlo);
     }
-    if (warp == 0) ptx::tmem_alloc<TG_BN>(tmem_ptr);
+    if (warp == 0) ptx::tmem_alloc<2 * TG_BN>(tmem_ptr);
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
@@ -106,9 +111,12 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     if (warp == 0) {
         // ===================== TMA producer: one thread =====================
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % S;
-                ptx::mbar_wait(&empty[s], ((kb / S) & 1) ^ 1);
+            uint32_t g = 0;                                           // k-blocks issued so far (ring position across tiles)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_ntiles) * TG_BM, n0 = (tile % n_ntiles) * TG_BN;
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const int s = g % S;
+                ptx::mbar_wait(&empty[s], ((g / S) & 1) ^ 1);
                 uint8_t* st = smem + (size_t)s * Cfg::STAGE_BYTES;
                 ptx::mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
                 const int k0 = kb * TG_BK;
@@ -118,15 +126,25 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 ptx::tma_load_2d(&mapBhi, &full[s], st + (t++) * TG_TILE_BYTES, k0, n0);
                 ptx::tma_load_2d(&mapBlo, &full[s], st + (t++) * TG_TILE_BYTES, k0, n0);
             }
+            }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer: one thread =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc(/*tf32*/ 2, TG_BM, TG_BN, 0, 0);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % S;
-                ptx::mbar_wait(&full[s], (kb / S) & 1);
+            uint32_t g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int n0 = (tile % n_ntiles) * TG_BN;
+            int ncols = (a.N - n0 + 15) & ~15;                        // a narrow last column tile issues narrow MMAs
+            if (ncols > TG_BN) ncols = TG_BN;
+            const uint32_t idesc = ptx::umma_idesc(/*tf32*/ 2, TG_BM, ncols, 0, 0);
+            const uint32_t as = it & 1u;
+            const uint32_t tmem_acc = tmem_base + as * TG_BN;
+            ptx::mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator stage
+            ptx::tc_fence_after_sync();
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const int s = g % S;
+                ptx::mbar_wait(&full[s], (g / S) & 1);
                 ptx::tc_fence_after_sync();
                 const uint32_t base = ptx::smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
                 const uint32_t sAhi = base, sAlo = base + TG_TILE_BYTES;
@@ -136,22 +154,28 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     const uint64_t ahi = ptx::umma_smem_desc(sAhi + kk * 32, 0, 1024);
                     const uint64_t bhi = ptx::umma_smem_desc(sBhi + kk * 32, 0, 1024);
                     const uint64_t blo = ptx::umma_smem_desc(sBlo + kk * 32, 0, 1024);
-                    ptx::mma_tf32_ss(tmem_base, ahi, bhi, idesc, (kb | kk) != 0 ? 1u : 0u);
-                    ptx::mma_tf32_ss(tmem_base, ahi, blo, idesc, 1u);
+                    ptx::mma_tf32_ss(tmem_acc, ahi, bhi, idesc, (kb | kk) != 0 ? 1u : 0u);
+                    ptx::mma_tf32_ss(tmem_acc, ahi, blo, idesc, 1u);
                     if (SPLIT_A) {
                         const uint64_t alo = ptx::umma_smem_desc(sAlo + kk * 32, 0, 1024);
-                        ptx::mma_tf32_ss(tmem_base, alo, bhi, idesc, 1u);
+                        ptx::mma_tf32_ss(tmem_acc, alo, bhi, idesc, 1u);
                     }
                 }
                 ptx::mma_commit(&empty[s]);
             }
-            ptx::mma_commit(tmem_full);
+            ptx::mma_commit(&tmem_full[as]);
+            }
         }
         __syncwarp();
     } else {
         // ===================== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====================
         const int q = warp & 3;
-        ptx::mbar_wait(tmem_full, 0);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int nt = tile % n_ntiles, m0 = (tile / n_ntiles) * TG_BM, n0 = nt * TG_BN;
+        const uint32_t as = it & 1u;
+        const uint32_t tmem_acc = tmem_base + as * TG_BN;
+        ptx::mbar_wait(&tmem_full[as], (it >> 1) & 1);
         ptx::tc_fence_after_sync();
         const int m = m0 + q * 32 + lane;
         const bool row_ok = m < a.M;
@@ -163,7 +187,7 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll 1
             for (int ch = 0; ch < TG_BN / 32; ++ch) {
                 uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, r);
+                ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + ch * 32, r);
                 ptx::tmem_ld_wait();
                 if (!row_ok) continue;
                 const int nb = n0 + ch * 32;
@@ -186,7 +210,7 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll 1
             for (int ch = 0; ch < TG_BN / 32; ++ch) {
                 uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, r);
+                ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + ch * 32, r);
                 ptx::tmem_ld_wait();
                 const int nb = n0 + ch * 32;
                 if (!row_ok || nb >= a.N) continue;
@@ -221,12 +245,12 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll 1
             for (int ch = 0; ch < TG_BN / 32; ++ch) {
                 uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, r);
+                ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + ch * 32, r);
                 ptx::tmem_ld_wait();
                 if (!row_ok) continue;
                 const int nb = n0 + ch * 32;
                 if (nb >= a.N) continue;
-                if (blockIdx.x == 0) {
+                if (nt == 0) {
                     const float4* hh = reinterpret_cast<const float4*>(a.hs_hi + (size_t)m * a.hs_ld + nb);
                     const float4* hl = reinterpret_cast<const float4*>(a.hs_lo + (size_t)m * a.hs_ld + nb);
                     const float4* gb = reinterpret_cast<const float4*>(a.hs_bias + nb);
@@ -244,7 +268,7 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         if (nb + j < a.N) a.tail[(size_t)m * a.tail_ld + (nb - TG_BN) + j] = __uint_as_float(r[j]) + __ldg(a.hs_bias + nb + j);
                 }
             }
-            if (row_ok && blockIdx.x == 0) a.rowdot[m] = dot;
+            if (row_ok && nt == 0) a.rowdot[m] = dot;
         } else {
             int yv = -1;
             if (row_ok && a.y) {
@@ -255,13 +279,13 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll 1
             for (int ch = 0; ch < TG_BN / 32; ++ch) {
                 uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * 32, r);
+                ptx::tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(q * 32) << 16) + ch * 32, r);
                 ptx::tmem_ld_wait();
                 const int nb = n0 + ch * 32;
                 float cmx = -INFINITY; int cam = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float l = (nb + j < a.N) ? scale * __uint_as_float(r[j]) : -INFINITY;
+                    const float l = (nb + j < a.N) ? fmaf(scale, __uint_as_float(r[j]), a.col_bias ? __ldg(a.col_bias + nb + j) : 0.f) : -INFINITY;
                     r[j] = __float_as_uint(l);
                     if (l > cmx) { cmx = l; cam = nb + j; }           // strict >: first maximum wins, as torch.argmax
                     if (nb + j == yv) ly = l;
@@ -274,13 +298,15 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             }
             if (row_ok) {
                 SoftmaxPart p; p.mx = mx; p.se = se; p.ly = ly; p.am = am;
-                a.part[(size_t)m * gridDim.x + blockIdx.x] = p;
+                a.part[(size_t)m * n_ntiles + nt] = p;
             }
         }
         ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&tmem_empty[as]);                            // 128 epilogue threads: accumulator stage reusable
+        }
     }
     __syncthreads();
-    if (warp == 0) ptx::tmem_dealloc<TG_BN>(tmem_base);
+    if (warp == 0) ptx::tmem_dealloc<2 * TG_BN>(tmem_base);
 }
 
 template <bool SPLIT_A, int EPI>
@@ -295,7 +321,8 @@ static int launch_tc_gemm_nt(const float* A, const float* Alo, int64_t lda, cons
     if (int rc = make_tmap_2d(&mBlo, Blo, a.N, a.K, ldb)) return rc;
     auto kern = k_tc_gemm_nt<SPLIT_A, EPI>;
     DBMM_CUDA(set_smem(kern, Cfg::SMEM));
-    dim3 grid(ceil_div(a.N, TG_BN), ceil_div(a.M, TG_BM));
+    int grid = ceil_div(a.N, TG_BN) * ceil_div(a.M, TG_BM);
+    if (grid > 148) grid = 148;                                  // persistent: one CTA per SM walks the tiles
     kern<<<grid, TG_THREADS, Cfg::SMEM, st>>>(mA, mAlo, mBhi, mBlo, a);
     DBMM_LAUNCH_CHECK();
     return DBMM_OK;

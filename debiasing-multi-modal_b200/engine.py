@@ -101,6 +101,16 @@ def _run_train_epoch(opt, loader, classifier, optimizer, target, use_group, warm
     bs = loader.batch_size
     sizes = _batch_sizes(n, bs)
     lrs = _lr_table(len(sizes), optimizer, warm_fn)
+    if hasattr(classifier, "fc"):                                 # linear probing (final_main.py:43-49)
+        stats = _stats_buffers(len(sizes), base.n_groups, base.device, "train")
+        t0 = time.time()
+        ops.linear_train_epoch(base.x, _order_to_device(base, rows), bs, base.labels[target], base.labels["group"],
+                               classifier.fc.weight.data, classifier.fc.bias.data, optimizer.grads, optimizer.momentum_buf,
+                               lrs, stats, first_step=optimizer.first_step, G=base.n_groups, momentum=optimizer.momentum,
+                               weight_decay=optimizer.weight_decay)
+        optimizer.first_step = False
+        loss_sum, counts = stats.host()
+        return loss_sum, counts, sizes, time.time() - t0
     old, ad, w = classifier.kernel_adapters()
     That = classifier.prompt_matrix(use_group=use_group)
     labels = base.labels["group"] if use_group else base.labels[target]
@@ -169,11 +179,16 @@ def _run_eval(loader, classifier, target, spurious_prompts=False):
     base, rows = loader.base_rows(loader.draw_order())
     n, bs = len(rows), loader.batch_size
     sizes = _batch_sizes(n, bs)
-    old, ad, w = classifier.kernel_adapters()
-    That = classifier.prompt_matrix(spurious=spurious_prompts)
     stats = _stats_buffers(len(sizes), base.n_groups, base.device, "eval")
     contiguous = len(rows) == len(base) and np.array_equal(rows, np.arange(len(base)))
     idx = None if contiguous else _order_to_device(base, rows)
+    if hasattr(classifier, "fc"):                                 # linear probe: logits = x W^T + b on the raw embeddings
+        ops.logits_ce(base.x, base.labels[target], base.labels["group"], classifier.fc.weight.data.t().contiguous(), 1.0, stats, bs,
+                      idx=idx, n_rows=n, G=base.n_groups, normalize_rows=False, col_bias=classifier.fc.bias.data)
+        loss_sum, counts = stats.host()
+        return loss_sum, counts, sizes, base.n_groups
+    old, ad, w = classifier.kernel_adapters()
+    That = classifier.prompt_matrix(spurious=spurious_prompts)
     ops.eval_fwd(base.x, base.labels[target], base.labels["group"], ad, That, 1.0 / classifier.temperature, stats, bs,
                  idx=idx, n_rows=n, old_ad=old, ebd_weight=w, G=base.n_groups)
     loss_sum, counts = stats.host()
@@ -194,11 +209,25 @@ def validate_zs(opt, val_loader, classifier, criterion, get_yp_func, train_group
                 print_label='Zero-shot Prediction (Test) (Class)'):
     """Feature-quality check with class or spurious prompts (final_main.py:725-803)."""
     _check_criterion(criterion)
-    if opt.tl_method == "linear_probing":
-        raise NotImplementedError("linear_probing is not on the B200 path yet (SURVEY.md section 8 row a4)")
     if target not in ("class", "spurious"):
         raise ValueError(target)
-    loss_sum, counts, sizes, n_groups = _run_eval(val_loader, classifier, target, spurious_prompts=(target == "spurious"))
+    if opt.tl_method == "linear_probing":
+        # same as the CLIP zero-shot head on the raw embeddings (final_main.py:730-738, 757-759)
+        from .modules import get_text_embedding
+        raw = get_text_embedding(opt.text_embedding_dir if target == "class" else opt.text_spurious_embedding_dir)
+        classifier.eval()
+        base, rows = val_loader.base_rows(val_loader.draw_order())
+        n, bs = len(rows), val_loader.batch_size
+        sizes = _batch_sizes(n, bs)
+        That = ops.normalize_text(raw.to(base.device, torch.float32).contiguous())
+        stats = _stats_buffers(len(sizes), base.n_groups, base.device, "eval")
+        contiguous = len(rows) == len(base) and np.array_equal(rows, np.arange(len(base)))
+        ops.logits_ce(base.x, base.labels[target], base.labels["group"], That, 1.0 / opt.zs_temperature, stats, bs,
+                      idx=None if contiguous else _order_to_device(base, rows), n_rows=n, G=base.n_groups, normalize_rows=True)
+        loss_sum, counts = stats.host()
+        n_groups = base.n_groups
+    else:
+        loss_sum, counts, sizes, n_groups = _run_eval(val_loader, classifier, target, spurious_prompts=(target == "spurious"))
     losses, acc, acc_groups = replay_epoch(loss_sum, counts, sizes, n_groups)
     group_acc = eval_group_acc(acc_groups, get_yp_func, train_group_ratio)
     print(f"{print_label}:", str(group_acc))

@@ -38,7 +38,10 @@ class LinearClassifier(nn.Module):
         self.fc = nn.Linear(input_dim, num_classes)
 
     def forward(self, features):
-        raise NotImplementedError("linear_probing is not on the B200 path yet (SURVEY.md section 8 row a4)")
+        """logits = x W^T + b (eval / no-grad; training runs through engine.train_one_epoch's fused linear-probe step)."""
+        x = features.contiguous()
+        That = self.fc.weight.data.t().contiguous()               # [D, C]
+        return ops.linear_logits(x, That, self.fc.bias.data)
 
 
 class Adapter(nn.Module):

@@ -286,7 +286,7 @@ def group_counts(logits: torch.Tensor, y, grp, stats: BatchStatsBuffers, batch_s
 
 
 def logits_ce(U: torch.Tensor, y, grp, That: torch.Tensor, inv_tau: float, stats: BatchStatsBuffers | None, batch_size: int, *,
-              idx=None, n_rows=None, G: int = 4, normalize_rows=True, want_pred=False):
+              idx=None, n_rows=None, G: int = 4, normalize_rows=True, want_pred=False, col_bias=None):
     """Zero-shot head on raw embeddings (validate_zs, final_main.py:757-768; BASELINE config 4): cosine logits against
     the prompt columns, CE, argmax and per-group counters without materialising the [N, C] logits."""
     lib = _lib.load()
@@ -304,8 +304,8 @@ def logits_ce(U: torch.Tensor, y, grp, That: torch.Tensor, inv_tau: float, stats
     ws = workspace(lib.dbmm_head_workspace_bytes(max(N, 1), D, Cn, 1 if idx is not None else 0), U.device)
     pred = torch.empty((N,), dtype=torch.int32, device=U.device) if want_pred else None
     st = stats.c() if stats is not None else BatchStats(None, None)
-    _lib.check(lib.dbmm_logits_ce(U.data_ptr(), U.stride(0), _ptr(idx), _ptr(y), _ptr(grp), N, D, Cn, G, That.data_ptr(), inv_tau,
-                                  1 if normalize_rows else 0, batch_size, st, _ptr(pred), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    _lib.check(lib.dbmm_logits_ce(U.data_ptr(), U.stride(0), _ptr(idx), _ptr(y), _ptr(grp), N, D, Cn, G, That.data_ptr(),
+                                  _ptr(col_bias), inv_tau, 1 if normalize_rows else 0, batch_size, st, _ptr(pred), ws.data_ptr(), ws.numel(), _stream_ptr()))
     return pred
 
 
@@ -354,3 +354,32 @@ def supcon_bwd(Z_all: torch.Tensor, state: SupconState, *, row0=0, n_local=None,
     _lib.check(lib.dbmm_supcon_bwd(Z_all.data_ptr(), Bg, d, row0, Bl, 1.0 / tau_cl, state.n_valid.data_ptr(), dZ_local.data_ptr(),
                                    dZ_all.data_ptr(), 1 if accumulate_all else 0, ws.data_ptr(), ws.numel(), _stream_ptr()))
     return dZ_local, dZ_all
+
+
+def linear_train_epoch(X, order: torch.Tensor, batch_size: int, y, grp, W: torch.Tensor, b: torch.Tensor, grads: torch.Tensor,
+                       momentum_buf: torch.Tensor, lrs, stats: BatchStatsBuffers, *, first_step=False, G=4, momentum=0.9,
+                       weight_decay=5e-5):
+    """One epoch of linear probing (LinearClassifier under train_one_epoch, final_main.py:43-49, 426-496)."""
+    lib = _lib.load()
+    _check(X, torch.float32, "X", contiguous=False)
+    _check(order, torch.int32, "order")
+    _check(W, torch.float32, "W"); _check(b, torch.float32, "b")
+    Cn, D = W.shape
+    G = _label_args(y, grp, G)
+    n = order.numel()
+    steps = (n + batch_size - 1) // batch_size
+    lrs = np.ascontiguousarray(lrs, dtype=np.float32)
+    if len(lrs) < steps or stats.n_slots < steps or grads.numel() < Cn * D + Cn or momentum_buf.numel() < Cn * D + Cn:
+        raise DbmmError("linear_train_epoch: learning-rate table / stat slots / flat buffers too small")
+    _lib.check(lib.dbmm_linear_train_epoch(X.data_ptr(), X.stride(0), order.data_ptr(), n, batch_size, y.data_ptr(), _ptr(grp),
+                                           D, Cn, G, W.data_ptr(), b.data_ptr(), grads.data_ptr(), momentum_buf.data_ptr(),
+                                           lrs.ctypes.data_as(C.POINTER(C.c_float)), momentum, weight_decay,
+                                           1 if first_step else 0, stats.c(), _stream_ptr()))
+    return steps
+
+
+def linear_logits(X: torch.Tensor, Wt: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """LinearClassifier.forward (final_main.py:48-49): materialised logits through the tensor-core GEMM of the
+    contrastive path would be overkill for C = 2; this is plumbing-sized, so it is the one place torch.addmm is used."""
+    _check(X, torch.float32, "X")
+    return torch.addmm(bias, X, Wt)

@@ -40,6 +40,27 @@ class AdapterSGD:
         self.buffers.grads.zero_()
 
 
+class LinearSGD:
+    """Optimizer state of a LinearClassifier (linear probing): flat gradient / momentum buffers W | b."""
+
+    def __init__(self, module, lr, momentum, weight_decay):
+        self.module = module
+        self.param_groups = [{"lr": lr, "momentum": momentum, "weight_decay": weight_decay}]
+        w = module.fc.weight
+        n = w.numel() + module.fc.bias.numel()
+        import torch
+        self.grads = torch.zeros(n, dtype=torch.float32, device=w.device)
+        self.momentum_buf = torch.zeros(n, dtype=torch.float32, device=w.device)
+        self.first_step = True
+
+    lr = AdapterSGD.lr
+    momentum = AdapterSGD.momentum
+    weight_decay = AdapterSGD.weight_decay
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+
 def trainable_adapter(model):
     """The adapter whose tensors the optimizer updates: `new_adapter` of a MultipleAdapter (stage 2 freezes every
     parameter whose name contains "old_cls", demo/util.py:128), else the classifier's only adapter."""
@@ -47,6 +68,8 @@ def trainable_adapter(model):
 
 
 def set_optimizer(opt, model):
+    if hasattr(model, "fc"):                                      # LinearClassifier (--tl_method linear_probing)
+        return LinearSGD(model, opt.learning_rate, opt.momentum, opt.weight_decay)
     return AdapterSGD(trainable_adapter(model), opt.learning_rate, opt.momentum, opt.weight_decay)
 
 

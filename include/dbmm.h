@@ -216,12 +216,24 @@ int dbmm_group_counts(const float* logits, const int32_t* y, const int32_t* grp,
  * final_main.py:757-768, and BASELINE config 4: N rows x C up to 1,000+ prompt columns):
  *   logits = (u / ||u||) . That * inv_tau  (normalize_rows != 0), CE against y, argmax, per-group counters.
  * The logits are never materialised: a tcgen05 GEMM reduces each 128-column tile to online-softmax partials.
- *   U[N_total, D] row stride ldu (multiple of 4), idx == NULL -> rows 0..N-1; That: [D, C] column-normalised prompts.
+ *   U[N_total, D] row stride ldu (multiple of 4), idx == NULL -> rows 0..N-1; That: [D, C] column-normalised prompts;
+ *   col_bias: optional [C] additive bias (NULL for the cosine head).
  */
 size_t dbmm_head_workspace_bytes(int64_t N, int D, int C, int gathered);
 int dbmm_logits_ce(const float* U, int64_t ldu, const int32_t* idx, const int32_t* y, const int32_t* grp,
-                   int64_t N, int D, int C, int G, const float* That, float inv_tau, int normalize_rows, int64_t batch_size,
-                   dbmm_batch_stats stats, int32_t* pred_out, void* ws, size_t ws_bytes, void* stream);
+                   int64_t N, int D, int C, int G, const float* That, const float* col_bias, float inv_tau, int normalize_rows,
+                   int64_t batch_size, dbmm_batch_stats stats, int32_t* pred_out, void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Linear probing (--tl_method linear_probing: LinearClassifier, final_main.py:43-49, trained by train_one_epoch,
+ * final_main.py:426-496): one epoch of logits = x W^T + b, CE, dW / db, SGD (momentum, weight decay) over rows
+ * order[0..n_rows-1] in batches of batch_size; W [C, D], b [C] updated in place; grads / momentum_buf: flat [C*D + C].
+ * Evaluation of a linear probe = dbmm_logits_ce with That = W^T ([D, C]), col_bias = b, inv_tau = 1, normalize_rows = 0.
+ */
+int dbmm_linear_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
+                            const int32_t* y, const int32_t* grp, int D, int C, int G, float* W, float* b,
+                            float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
+                            int first_step, dbmm_batch_stats stats, void* stream);
 
 /*
  * Contrastive regulariser, all anchors of the batch at once (formula: SupervisedContrastiveLoss.forward,

@@ -399,3 +399,25 @@ def head_logits(U, That, tau, normalize_rows=True, dtype=np.float64):
     if normalize_rows:
         U = U / np.sqrt((U * U).sum(1, keepdims=True))
     return (U @ That.astype(dtype)) / tau
+
+
+def linear_probe_epoch(X, y, order, batch_size, W, b, lrs, momentum=0.9, wd=5e-5, dtype=np.float64):
+    """LinearClassifier (final_main.py:43-49) trained by train_one_epoch (final_main.py:455-466) with torch SGD semantics."""
+    W, b = W.astype(dtype).copy(), b.astype(dtype).copy()
+    vW = vb = None
+    losses, logits_all = [], []
+    for s, lo in enumerate(range(0, len(order), batch_size)):
+        rows = order[lo:lo + batch_size]
+        x, yy = X[rows].astype(dtype), y[rows]
+        logits = x @ W.T + b
+        losses.append(-log_softmax(logits)[np.arange(len(rows)), yy].sum())
+        logits_all.append(logits)
+        dl = softmax(logits)
+        dl[np.arange(len(rows)), yy] -= 1
+        dl /= len(rows)
+        gW, gb = dl.T @ x + wd * W, dl.sum(0) + wd * b
+        vW = gW if vW is None else momentum * vW + gW
+        vb = gb if vb is None else momentum * vb + gb
+        W -= lrs[s] * vW
+        b -= lrs[s] * vb
+    return W, b, np.array(losses), logits_all

@@ -113,3 +113,54 @@ def test_supcon_sharded_anchors_equal_single_rank(ops):
         locals_.append(dl)
     dZ = (torch.cat(locals_) + dZ_all).cpu().numpy()
     assert np.abs(dZ - ref["dZ"]).max() <= 1e-3 * np.abs(ref["dZ"]).max()
+
+
+def test_linear_probe_epoch_and_eval(ops):
+    """--tl_method linear_probing: LinearClassifier trained by the fused linear-probe step, evaluated through the
+    tensor-core head with a bias (final_main.py:43-49, 426-496, 655-719)."""
+    rng = np.random.default_rng(77)
+    N, D, C, bs = 1500, 1024, 2, 512
+    x, y, mu = _embeddings(rng, N, D, C)
+    g = (2 * y + rng.integers(0, 2, N))
+    W0 = (rng.uniform(-1, 1, (C, D)) / np.sqrt(D)).astype(np.float32)
+    b0 = (rng.uniform(-1, 1, C) / np.sqrt(D)).astype(np.float32)
+    order = rng.permutation(N)
+    lrs = np.array([0.002, 0.002, 0.001], np.float32)
+    Wr, br, losses, logits_all = am.linear_probe_epoch(x, y, order, bs, W0, b0, lrs)
+    W, b = dev(W0), dev(b0)
+    grads = torch.zeros(C * D + C, device="cuda"); mom = torch.zeros_like(grads)
+    st = ops.BatchStatsBuffers(3, 4)
+    ops.linear_train_epoch(dev(x), dev(order, torch.int32), bs, dev(y, torch.int32), dev(g, torch.int32), W, b, grads, mom, lrs, st,
+                           first_step=True, G=4)
+    ls, cn = st.host()
+    np.testing.assert_allclose(ls, losses, rtol=1e-3, atol=1e-3)
+    assert np.abs(W.cpu().numpy() - Wr).max() <= 1e-3 * np.abs(Wr).max()
+    assert np.abs(b.cpu().numpy() - br).max() <= 1e-3 * np.abs(br).max() + 1e-6
+    for s in range(3):
+        rows = order[s * bs:(s + 1) * bs]
+        cc, tt, _ = am.group_counts(logits_all[s], y[rows], g[rows], 4)
+        assert np.array_equal(cn[s, 1], tt) and np.abs(cn[s, 0] - cc).max() <= 1           # one sub-ulp tie at most
+    # eval of the trained probe: logits = x W^T + b through the head kernel
+    st2 = ops.BatchStatsBuffers(1, 4)
+    pred = ops.logits_ce(dev(x), dev(y, torch.int32), dev(g, torch.int32), W.t().contiguous(), 1.0, st2, 1 << 20, G=4,
+                         normalize_rows=False, col_bias=b, want_pred=True)
+    ref = x.astype(np.float64) @ W.cpu().numpy().astype(np.float64).T + b.cpu().numpy()
+    margin = np.abs(ref[:, 0] - ref[:, 1])
+    assert np.array_equal(pred.cpu().numpy()[margin > 1e-4], ref.argmax(1)[margin > 1e-4])
+    ls2, _ = st2.host()
+    assert ls2[0] == pytest.approx(-am.log_softmax(ref)[np.arange(N), y].sum(), rel=1e-3)
+
+
+def test_linear_probing_cli_runs(tmp_path):
+    """End-to-end: final_main.py --tl_method linear_probing on a small synthetic Waterbirds-shaped set."""
+    import dbmm
+    from dbmm import cli, synth
+    ds = synth.make_dataset(name="waterbirds", dim=1024, seed=5, scale=0.2, k=0.4, k_text=0.5, text_noise=0.02)
+    paths = synth.write_reference_files(ds, str(tmp_path))
+    argv = ["--dataset", "waterbirds", "--tl_method", "linear_probing", "--batch_size", "128", "--learning_rate", "0.001",
+            "--epochs", "5", "--train_target", "class", "--random_seed", "42"]
+    for k, v in paths.items():
+        argv += [f"--{k}", v]
+    (tr, va, te), (zs_c, zs_s) = cli.train_all_epochs(cli.parse_option(argv))
+    assert 0.5 < float(te["mean_acc"]) <= 1.0 and 0.0 <= float(zs_s["worst_acc"]) <= 1.0
+    assert set(te) == {"weighted_mean_acc", "worst_acc", "acc_0_0", "acc_0_1", "acc_1_0", "acc_1_1", "mean_acc"}
