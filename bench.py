@@ -77,7 +77,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -354,7 +354,8 @@ def main():
         ev = N_TRAIN / (ms_e * 1e-3)
         out["eval"] = {"value": ev * world, "unit": "embeddings/s", "ms_per_pass": ms_e,
                        "roofline": {"bound": "hbm", "achieved": ev * ALG_BYTES_PER_EMB / 1e9, "peak": P["hbm"], "unit": "GB/s",
-                                    "frac": ev * ALG_BYTES_PER_EMB / 1e9 / P["hbm"], "traffic": None}}
+                                    "frac": ev * ALG_BYTES_PER_EMB / 1e9 / P["hbm"],
+                                    "traffic": traffic_from_profiles("eval_fwd_per_row"), "traffic_unit": "DRAM bytes per row (algorithmic 4096)"}}
 
     # ---- kernels of BASELINE configs 3 / 4 (tcgen05 + TMA GEMMs), short legs, N = 1 only
     if rank == 0 and world == 1:
