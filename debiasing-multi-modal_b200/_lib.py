@@ -85,6 +85,7 @@ SIGNATURES = {
     "dbmm_comm_unique_id": (C.c_int, [_vp]),
     "dbmm_comm_init": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
     "dbmm_comm_destroy": (C.c_int, [_vp]),
+    "dbmm_comm_has_p2p": (C.c_int, [_vp]),
     "dbmm_train_epoch_dp": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _AP, _AP,
                                       _f32, _vp, _f32, _vp, _vp, C.POINTER(C.c_float), _f32, _f32, _i32, BatchStats, _i32,
                                       _vp, _sz, _vp]),

@@ -145,7 +145,7 @@ static int gemm1_ksplit(int B, int nad, int D) {
 static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t pos0, int B, int D, int H,
                         const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, double* colsum,
                         float* whi, float* wlo, bool split_weights, int ksplit, float* g1part, cudaStream_t st,
-                        cudaEvent_t* ev = nullptr) {
+                        cudaEvent_t* ev = nullptr, const P2pArgs* p2p = nullptr) {
     const int nad = old_ad ? 2 : 1;
     if (ev && !split_weights) cudaEventRecord(ev[0], st);
     if (!use_tc_gemm1(D, H)) {
@@ -177,6 +177,8 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
         ReduceStatsArgs r;
         r.part = g1part; r.ksplit = ksplit; r.nad = nad; r.B = B; r.H = H; r.b1[0] = t.b1[0]; r.b1[1] = t.b1[1];
         r.A = A; r.colsum = colsum;
+        memset(&r.p2p, 0, sizeof(r.p2p));
+        if (p2p) r.p2p = *p2p;
         DBMM_CUDA(set_smem(k_reduce_stats, 0));
         DBMM_CUDA(launch_pdl(k_reduce_stats, dim3(ceil_div(B, RS_ROWS), nad), dim3(RS_THREADS), 0, st, r));
     }
@@ -354,7 +356,8 @@ static int train_step_impl(int phases, bool fresh,
                            const float* That, float inv_tau,
                            float* grads, float* momentum_buf, float lr, const float* lr_dev, float momentum, float weight_decay,
                            dbmm_batch_stats stats, int64_t slot, const TrainWs& w, cudaStream_t st,
-                           cudaEvent_t* ev = nullptr /* 7 events: before each of the 6 step kernels + after the last */) {
+                           cudaEvent_t* ev = nullptr /* 7 events: before each of the 6 step kernels + after the last */,
+                           const P2pArgs* p2p = nullptr /* fused peer-memory all-reduce of the column sums / (dgamma, dbeta) */) {
     const int nad = old_ad ? 2 : 1;
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
     const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
@@ -370,7 +373,7 @@ static int train_step_impl(int phases, bool fresh,
             if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
         }
         const int ks = tc1 ? gemm1_ksplit(B, nad, D) : 1;
-        if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, fresh, ks, w.g1part, st, ev)) return rc;
+        if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, fresh, ks, w.g1part, st, ev, p2p)) return rc;
     }
     if (phases & DBMM_PHASE_ROWS) {
         mark(2);
@@ -382,6 +385,7 @@ static int train_step_impl(int phases, bool fresh,
         ra.w_old = ebd_weight; ra.inv_tau = inv_tau; ra.inv_B = 1.0f / (float)B_global;
         ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.slot = slot;
         ra.dahat = w.dahat; ra.dgb = w.dgb; ra.S = w.S;
+        if (p2p) { ra.p2p = *p2p; ra.colsum_wb = w.colsum; }
         if (int rc = launch_rows_train(ra, nad, st)) return rc;
     }
     if (phases & DBMM_PHASE_WGRAD) {
@@ -394,6 +398,8 @@ static int train_step_impl(int phases, bool fresh,
             WgradTcArgs t;
             t.X = X; t.ldx = ldx; t.idx = idx; t.B = B; t.Bg = B_global; t.D = D; t.H = H;
             t.A = A_t; t.dahat = w.dahat; t.colsum = colsum_t; t.dgb = w.dgb; t.gamma = ad->gamma; t.part = w.part;
+            memset(&t.p2p, 0, sizeof(t.p2p)); t.dgb_wb = w.dgb;
+            if (p2p) t.p2p = *p2p;
             nchunk = wgrad_tc_chunks(B, &t.rows_per_chunk);
             if (int rc = launch_wgrad_tc(t, nchunk, st)) return rc;
         } else {
@@ -514,7 +520,17 @@ static bool graphs_enabled() {
 // dbeta) sums and the flat gradient are enqueued on ONE stream, captured into a CUDA graph (NCCL supports capture) and
 // replayed.  local_batches: every rank's `order` lists its OWN rows (weak scaling, global batch = world x batch_size);
 // otherwise `order` is the global order and each rank takes its contiguous shard of every batch.
-static int train_epoch_impl(ncclComm_t comm, int world, int rank, int local_batches,
+struct DbmmComm {
+    ncclComm_t nccl; int world, rank;
+    char* p2p_local; char* p2p_peer[P2P_MAX_WORLD]; bool p2p_ok;
+};
+
+static bool p2p_enabled() {
+    const char* e = getenv("DBMM_P2P");            // DBMM_P2P=0: NCCL all-reduces for the small vectors as well
+    return !(e && strcmp(e, "0") == 0);
+}
+
+static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batches,
                             const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
                             const int32_t* y, const int32_t* grp, int D, int H, int C, int G,
                             const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
@@ -527,6 +543,7 @@ static int train_epoch_impl(ncclComm_t comm, int world, int rank, int local_batc
     const int64_t steps = (n_rows + batch_size - 1) / batch_size;
     const int B0 = (int)(n_rows < batch_size ? n_rows : batch_size);
     const int64_t last_B = n_rows - (steps - 1) * batch_size;
+    ncclComm_t comm = dcomm ? dcomm->nccl : nullptr;
     const bool dp = comm != nullptr && world > 1;
     if (int rc = check_train_args(X, ldx, y, B0, (int64_t)B0 * (dp && local_batches ? world : 1), D, H, C, G, old_ad, ad, That, ws, grads)) return rc;
     DBMM_CHECK_ARG(last_B * (dp && local_batches ? world : 1) > 1, "BatchNorm needs more than 1 row per batch in training (trailing batch of %lld)", (long long)last_B);
@@ -538,6 +555,11 @@ static int train_epoch_impl(ncclComm_t comm, int world, int rank, int local_batc
     NcclApi* nc = dp ? nccl_api() : nullptr;
     DBMM_CHECK_ARG(!dp || nc->ok, "NCCL is not available in this process");
     const size_t np = dbmm_param_count(D, H);
+    // fused peer-memory all-reduce of the two small vectors: needs the tensor-core kernels on every step (their
+    // prologues / tails carry the push and wait) and the D-sliced GEMM-1 (k_reduce_stats is the push site)
+    const bool use_p2p = dp && dcomm->p2p_ok && p2p_enabled() && use_tc_gemm1(D, H) && use_tc_wgrad(D, H) &&
+                         gemm1_ksplit(B0 < (int)last_B ? B0 : (int)last_B, nad, D) > 1 && gemm1_ksplit(B0, nad, D) > 1 &&
+                         (local_batches || last_B / world >= 1);
 
     if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * np, st));
     DBMM_CUDA(cudaMemcpyAsync(w.lr, lr_host, sizeof(float) * (size_t)steps, cudaMemcpyHostToDevice, st));
@@ -555,18 +577,30 @@ static int train_epoch_impl(ncclComm_t comm, int world, int rank, int local_batc
                 B = base + (rank < extra ? 1 : 0);
                 idx += lo;
             }
+            P2pArgs pa;
+            memset(&pa, 0, sizeof(pa));
+            if (use_p2p) {
+                pa.world = world; pa.rank = rank; pa.step = (int)s;
+                for (int r = 0; r < world; ++r) pa.peer[r] = dcomm->p2p_peer[r];
+            }
             auto phase = [&](int ph) {
                 return train_step_impl(ph, s == 0, X, ldx, idx, y, grp, B, Bg, D, H, C, G, old_ad, ad, ebd_weight, That, inv_tau,
-                                       grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, s_);
+                                       grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, s_, nullptr,
+                                       use_p2p ? &pa : nullptr);
             };
             if (!dp) { if (int rc = phase(DBMM_PHASE_ALL)) return rc; continue; }
             if (int rc = phase(DBMM_PHASE_GEMM1)) return rc;
-            DBMM_NCCL(nc->AllReduce(w.colsum, w.colsum, (size_t)nad * 2 * H, ncclFloat64, ncclSum, comm, s_));
+            if (!use_p2p) DBMM_NCCL(nc->AllReduce(w.colsum, w.colsum, (size_t)nad * 2 * H, ncclFloat64, ncclSum, comm, s_));
             if (int rc = phase(DBMM_PHASE_ROWS)) return rc;
-            DBMM_NCCL(nc->AllReduce(w.dgb, w.dgb, (size_t)2 * H, ncclFloat64, ncclSum, comm, s_));
+            if (!use_p2p) DBMM_NCCL(nc->AllReduce(w.dgb, w.dgb, (size_t)2 * H, ncclFloat64, ncclSum, comm, s_));
             if (int rc = phase(DBMM_PHASE_WGRAD)) return rc;
-            DBMM_NCCL(nc->AllReduce(grads, grads, np, ncclFloat32, ncclSum, comm, s_));
+            static const bool skip_grad_ar = getenv("DBMM_SKIP_GRAD_AR") != nullptr;      // timing experiments only
+            if (!skip_grad_ar) DBMM_NCCL(nc->AllReduce(grads, grads, np, ncclFloat32, ncclSum, comm, s_));
             if (int rc = phase(DBMM_PHASE_UPDATE)) return rc;
+        }
+        if (use_p2p) {                                           // instance numbers stay unique across replays of this graph
+            k_p2p_bump<<<1, 1, 0, s_>>>(dcomm->p2p_local, (unsigned)steps);
+            DBMM_LAUNCH_CHECK();
         }
         if (dp && reduce_stats) {
             if (stats.loss_sum) DBMM_NCCL(nc->AllReduce(stats.loss_sum, stats.loss_sum, (size_t)steps, ncclFloat64, ncclSum, comm, s_));
@@ -584,8 +618,8 @@ static int train_epoch_impl(ncclComm_t comm, int world, int rank, int local_batc
     key.D = D; key.H = H; key.C = C; key.G = G; key.ad = *ad; key.has_old = old_ad ? 1 : 0; if (old_ad) key.old_ad = *old_ad;
     key.ebd_weight = ebd_weight; key.That = That; key.inv_tau = inv_tau; key.grads = grads; key.mom = momentum_buf;
     key.momentum = momentum; key.wd = weight_decay; key.loss_sum = stats.loss_sum; key.counts = stats.counts; key.ws = ws;
-    key.device = device; key.comm = comm; key.world = dp ? world : 1; key.rank = dp ? rank : 0;
-    key.local_batches = (dp ? local_batches : 0) | (reduce_stats ? 2 : 0);
+    key.device = device; key.comm = dcomm; key.world = dp ? world : 1; key.rank = dp ? rank : 0;
+    key.local_batches = (dp ? local_batches : 0) | (reduce_stats ? 2 : 0) | (use_p2p ? 4 : 0);
 
     std::lock_guard<std::mutex> lock(g_graph_mu);
     cudaGraphExec_t exec = nullptr;
@@ -623,7 +657,7 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
                      float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
                      int first_step, dbmm_batch_stats stats,
                      void* ws, size_t ws_bytes, void* stream) {
-    return train_epoch_impl(nullptr, 1, 0, 0, X, ldx, order, n_rows, batch_size, y, grp, D, H, C, G, old_ad, ad, ebd_weight, That,
+    return train_epoch_impl((DbmmComm*)nullptr, 1, 0, 0, X, ldx, order, n_rows, batch_size, y, grp, D, H, C, G, old_ad, ad, ebd_weight, That,
                             inv_tau, grads, momentum_buf, lr_host, momentum, weight_decay, first_step, stats, 0, ws, ws_bytes,
                             (cudaStream_t)stream);
 }
@@ -644,20 +678,64 @@ int dbmm_comm_init(const void* id_128_bytes, int world, int rank, void** comm_ou
     DBMM_CHECK_ARG(nc->ok, "NCCL (libnccl.so.2) could not be loaded");
     ncclUniqueId id;
     memcpy(&id, id_128_bytes, sizeof(id));
-    ncclComm_t comm = nullptr;
-    DBMM_NCCL(nc->CommInitRank(&comm, world, id, rank));
-    *comm_out = comm;
+    DbmmComm* c = new DbmmComm();
+    memset(c, 0, sizeof(*c));
+    c->world = world; c->rank = rank;
+    ncclResult_t r = nc->CommInitRank(&c->nccl, world, id, rank);
+    if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", nc->GetErrorString(r)); delete c; return DBMM_ERR_CUDA; }
+    *comm_out = c;
+    // Symmetric buffers for the fused one-shot all-reduces: cudaMalloc + CUDA IPC, handles exchanged with ncclAllGather.
+    // Any failure leaves p2p_ok = false and the epoch falls back to NCCL all-reduces (same results).
+    if (world > P2P_MAX_WORLD || world < 2 || !p2p_enabled()) return DBMM_OK;
+    do {
+        if (cudaMalloc((void**)&c->p2p_local, P2P_BYTES) != cudaSuccess) break;
+        if (cudaMemset(c->p2p_local, 0, P2P_BYTES) != cudaSuccess) break;
+        cudaIpcMemHandle_t mine;
+        if (cudaIpcGetMemHandle(&mine, c->p2p_local) != cudaSuccess) break;
+        char* dev_handles = nullptr;
+        if (cudaMalloc((void**)&dev_handles, sizeof(mine) * (size_t)world) != cudaSuccess) break;
+        bool ok = cudaMemcpy(dev_handles + sizeof(mine) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && nc->AllGather(dev_handles + sizeof(mine) * (size_t)rank, dev_handles, sizeof(mine), ncclUint8, c->nccl, 0) == ncclSuccess;
+        ok = ok && cudaStreamSynchronize(0) == cudaSuccess;
+        std::vector<cudaIpcMemHandle_t> all((size_t)world);
+        ok = ok && cudaMemcpy(all.data(), dev_handles, sizeof(mine) * (size_t)world, cudaMemcpyDeviceToHost) == cudaSuccess;
+        cudaFree(dev_handles);
+        if (!ok) break;
+        for (int p = 0; p < world && ok; ++p) {
+            if (p == rank) { c->p2p_peer[p] = c->p2p_local; continue; }
+            void* ptr = nullptr;
+            ok = cudaIpcOpenMemHandle(&ptr, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            c->p2p_peer[p] = (char*)ptr;
+        }
+        if (!ok) break;
+        // nobody may start pushing before every rank has mapped every buffer and zeroed its own
+        float* dummy = nullptr;
+        if (cudaMalloc((void**)&dummy, sizeof(float)) != cudaSuccess) break;
+        ok = nc->AllReduce(dummy, dummy, 1, ncclFloat32, ncclSum, c->nccl, 0) == ncclSuccess && cudaStreamSynchronize(0) == cudaSuccess;
+        cudaFree(dummy);
+        c->p2p_ok = ok;
+    } while (0);
+    if (!c->p2p_ok) cudaGetLastError();          // clear the sticky-free error state of the failed optional set-up
     return DBMM_OK;
 }
 
+int dbmm_comm_has_p2p(void* comm) { return comm && ((DbmmComm*)comm)->p2p_ok ? 1 : 0; }
+
 int dbmm_comm_destroy(void* comm) {
     if (!comm) return DBMM_OK;
+    DbmmComm* c = (DbmmComm*)comm;
     {   // graphs that captured this communicator's collectives must not outlive it
         std::lock_guard<std::mutex> lock(g_graph_mu);
         for (size_t i = 0; i < g_graphs.size();)
             if (g_graphs[i].key.comm == comm) { cudaGraphExecDestroy(g_graphs[i].exec); g_graphs.erase(g_graphs.begin() + i); } else ++i;
     }
-    DBMM_NCCL(nccl_api()->CommDestroy((ncclComm_t)comm));
+    cudaDeviceSynchronize();
+    for (int p = 0; p < c->world && p < P2P_MAX_WORLD; ++p)
+        if (p != c->rank && c->p2p_peer[p]) cudaIpcCloseMemHandle(c->p2p_peer[p]);
+    if (c->p2p_local) cudaFree(c->p2p_local);
+    const ncclResult_t r = nccl_api()->CommDestroy(c->nccl);
+    delete c;
+    if (r != ncclSuccess) { set_error("ncclCommDestroy failed"); return DBMM_ERR_CUDA; }
     return DBMM_OK;
 }
 
@@ -670,7 +748,7 @@ int dbmm_train_epoch_dp(void* comm, int world, int rank, int local_batches,
                         int first_step, dbmm_batch_stats stats, int reduce_stats,
                         void* ws, size_t ws_bytes, void* stream) {
     DBMM_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && (world == 1 || comm != nullptr), "bad world=%d rank=%d / NULL communicator", world, rank);
-    return train_epoch_impl((ncclComm_t)comm, world, rank, local_batches, X, ldx, order, n_rows, batch_size, y, grp, D, H, C, G,
+    return train_epoch_impl((DbmmComm*)comm, world, rank, local_batches, X, ldx, order, n_rows, batch_size, y, grp, D, H, C, G,
                             old_ad, ad, ebd_weight, That, inv_tau, grads, momentum_buf, lr_host, momentum, weight_decay, first_step,
                             stats, reduce_stats, ws, ws_bytes, (cudaStream_t)stream);
 }

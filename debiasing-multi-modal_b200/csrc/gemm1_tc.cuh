@@ -12,6 +12,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "p2p.cuh"
 
 namespace dbmm {
 
@@ -264,6 +265,7 @@ struct ReduceStatsArgs {
     const float* b1[2];
     float* A;          // [nad][B][H]
     double* colsum;    // [nad][2][H] or nullptr
+    P2pArgs p2p;       // data parallel over peer memory: the last CTA pushes the column sums to every rank (channel 0)
 };
 constexpr int RS_ROWS = 16, RS_MAXK = 16, RS_THREADS = 256;
 
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_reduce_stats(ReduceStatsArgs a) 
         for (int rr = 0; rr < 8; ++rr) v += (double)sS[which][rr][j];
         atomicAdd(&a.colsum[((size_t)ad * 2 + which) * H + j], v);
     }
+    if (a.p2p.world) p2p_push_when_last(a.p2p, 0, a.colsum, a.nad * 2 * H, gridDim.x * gridDim.y);
 }
 
 }  // namespace dbmm

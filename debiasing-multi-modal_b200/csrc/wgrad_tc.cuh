@@ -13,6 +13,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "p2p.cuh"
 
 namespace dbmm {
 
@@ -34,6 +35,7 @@ struct WgradTcArgs {
     const float* gamma;
     float* part;           // [nchunk][H][D]
     int rows_per_chunk;    // multiple of WG_BK
+    P2pArgs p2p; double* dgb_wb;   // data parallel over peer memory: global dgamma / dbeta in (channel 1), written back by CTA (0, 0)
 };
 
 // byte offset of the 16-byte chunk (4 floats) `c16` (0..31 along the 128-float MN extent) of K-row `row` (0..63)
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     ptx::pdl_wait();                // dahat / dgamma / dbeta come from the row kernel (X, idx are constants)
     ptx::pdl_launch();
     if (warp < 4) load_da(0, 0, av, dv);
+    const int dgb_parity = a.p2p.world ? p2p_wait(a.p2p, 1) : 0;        // every rank's dgamma / dbeta have landed
     if (tid < WG_TILE) {
         float mu = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
         if (tid < H) {
@@ -152,8 +155,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
             if (v < 0.0) v = 0.0;
             mu = (float)m; rstd = 1.0f / sqrtf((float)v + DBMM_BN_EPS);
             const double gm = (double)a.gamma[tid];
-            m1 = (float)(gm * a.dgb[H + tid] / (double)a.Bg);
-            m2 = (float)(gm * a.dgb[tid] / (double)a.Bg);
+            double dg, db;
+            if (a.p2p.world) {
+                dg = p2p_sum(a.p2p, 1, dgb_parity, tid); db = p2p_sum(a.p2p, 1, dgb_parity, H + tid);
+                if (blockIdx.x == 0 && blockIdx.y == 0) { a.dgb_wb[tid] = dg; a.dgb_wb[H + tid] = db; }
+            } else { dg = a.dgb[tid]; db = a.dgb[H + tid]; }
+            m1 = (float)(gm * db / (double)a.Bg);
+            m2 = (float)(gm * dg / (double)a.Bg);
         }
         sCst[0][tid] = mu; sCst[1][tid] = rstd; sCst[2][tid] = m1; sCst[3][tid] = m2;
     }

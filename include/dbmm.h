@@ -175,6 +175,10 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
  * dbmm_train_epoch_dp is dbmm_train_epoch with, per step, the all-reduces of the BatchNorm column sums, the (dgamma,
  * dbeta) sums and the flat gradient between the phases, so that BatchNorm and the CE mean see the GLOBAL batch
  * (the reference is single-process); kernels and collectives are captured in one CUDA graph.
+ * When the ranks can map each other's memory (CUDA IPC over NVLink, world <= 8) the two small fp64 vectors are NOT sent
+ * through NCCL: the producing kernel's last CTA pushes them into every rank's symmetric buffer and raises flags, the
+ * consuming kernel's prologue waits on its local flags and sums the slots in rank order (csrc/p2p.cuh); only the 1 MB
+ * gradient goes through ncclAllReduce.  DBMM_P2P=0 forces NCCL for all three.
  *   local_batches == 0: `order` is the global batch order (identical on all ranks); each rank trains on its contiguous
  *                       shard of every batch -- same result as one GPU.
  *   local_batches != 0: `order` lists this rank's own rows (equal n_rows / batch_size on all ranks); the global batch is
@@ -183,6 +187,7 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
  */
 int dbmm_comm_unique_id(void* id_out_128_bytes);
 int dbmm_comm_init(const void* id_128_bytes, int world, int rank, void** comm_out);
+int dbmm_comm_has_p2p(void* comm);      /* 1 if the fused peer-memory all-reduce (below) is active, 0 if NCCL is used throughout */
 int dbmm_comm_destroy(void* comm);
 int dbmm_train_epoch_dp(void* comm, int world, int rank, int local_batches,
                         const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,

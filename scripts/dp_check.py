@@ -48,7 +48,11 @@ def run(dp):
 
 
 p1, (l1, c1) = run(None)
-p2, (l2, c2) = run(parallel.DataParallelTrainer())
+trainer = parallel.DataParallelTrainer()
+p2, (l2, c2) = run(trainer)
+if rank == 0:
+    import dbmm._lib as L
+    print('fused peer-memory all-reduce active:', bool(L.load().dbmm_comm_has_p2p(trainer._comm)) if trainer._comm else None)
 worst = 0.0
 for k in ("W1", "b1", "gamma", "beta", "W2", "b2", "running_mean", "running_var"):
     err = float(np.abs(p1[k] - p2[k]).max() / (np.abs(p1[k]).max() + 1e-30))
