@@ -127,6 +127,8 @@ struct TrainWs {
     double* dgb;      // [2][H]        dgamma, dbeta          (zero at the start of every step)
     float* S;         // [H+1+C][SP]   batch reduction for dW2, SP = H+1 rounded up to 4 (zero at the start of every step)
     float* gram;      // [nad][H+1][H+1+C]
+    float* S2;        // second half of the S double buffer (fused step tail)
+    float* gram2;     // second half of the Gram double buffer (fused step tail: step s reads half s & 1, fills the other)
     float* A;         // [nad][B][H]   pre-BatchNorm activations
     float* dahat;     // [B][H]        dL/d(normalised activation)
     float* whi;       // [nad][H][D]   tf32-exact part of W1 (tensor-core GEMM-1 operand)
@@ -147,6 +149,8 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     size_t o_dgb = take(sizeof(double) * 2 * H);
     size_t o_S = take(sizeof(float) * (size_t)(H + 1 + C) * s_stride(H));
     size_t o_gram = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));     // split-K target: zeroed with the sums
+    size_t o_S2 = take(sizeof(float) * (size_t)(H + 1 + C) * s_stride(H));
+    size_t o_gram2 = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));
     w.accum_bytes = off;
     size_t o_A = take(sizeof(float) * (size_t)nad * B * H);
     size_t o_da = take(sizeof(float) * (size_t)B * H);
@@ -158,7 +162,7 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     w.total = off;
     w.colsum = (double*)(p + o_colsum); w.dgb = (double*)(p + o_dgb);
     w.A = (float*)(p + o_A); w.dahat = (float*)(p + o_da);
-    w.gram = (float*)(p + o_gram); w.S = (float*)(p + o_S);
+    w.gram = (float*)(p + o_gram); w.gram2 = (float*)(p + o_gram2); w.S = (float*)(p + o_S); w.S2 = (float*)(p + o_S2);
     w.whi = (float*)(p + o_whi); w.wlo = (float*)(p + o_wlo); w.part = (float*)(p + o_part);
     w.g1part = (float*)(p + o_g1); w.lr = (float*)(p + o_lr);
     return w;

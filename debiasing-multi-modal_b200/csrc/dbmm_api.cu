@@ -9,6 +9,7 @@
 #include "rows_train.cuh"
 #include "wgrad_tc.cuh"
 #include "update.cuh"
+#include "step_tail.cuh"
 #include "head_supcon.cuh"
 #include "nccl_dyn.cuh"
 #include "linear_probe.cuh"
@@ -140,12 +141,21 @@ static int gemm1_ksplit(int B, int nad, int D) {
     return (kb_all + kb_per - 1) / kb_per;           // no empty slice
 }
 
+// Fused step tail: the per-step accumulators are re-zeroed by the NEXT step's head kernels (see step_tail.cuh).
+struct StepZero { double* dgb; int dgb_n; float* S; int S_n; };
+
+// How the tail of a training step runs.  nullptr / !fused: k_finalize_grads + k_update (stepwise API, data parallel).
+// fused: k_step_tail; with a side stream its W2 role is forked off after the row kernel and joined only before the NEXT
+// step's row kernel (the first consumer of the new Gram matrix): it overlaps the dW1 GEMM, the W1 role and the next
+// step's GEMM-1 / reduction.  S and the Gram matrix are double-buffered by step parity for that.
+struct TailPlan { bool fused; int parity; cudaStream_t side; cudaEvent_t ev_fork, ev_join; bool join_pending; };
+
 // a = x W1^T + b1 for one or two adapters (+ fp64 column sums).  whi/wlo: scratch [nad][H][D] each.
 // ksplit > 1 (training): D-sliced partial tiles into `g1part`, finished by k_reduce_stats.
 static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t pos0, int B, int D, int H,
                         const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, double* colsum,
                         float* whi, float* wlo, bool split_weights, int ksplit, float* g1part, cudaStream_t st,
-                        cudaEvent_t* ev = nullptr, const P2pArgs* p2p = nullptr) {
+                        cudaEvent_t* ev = nullptr, const P2pArgs* p2p = nullptr, const StepZero* zero = nullptr) {
     const int nad = old_ad ? 2 : 1;
     if (ev && !split_weights) cudaEventRecord(ev[0], st);
     if (!use_tc_gemm1(D, H)) {
@@ -169,6 +179,8 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
     if (nad == 1) { t.Whi[1] = t.Whi[0]; t.Wlo[1] = t.Wlo[0]; t.b1[1] = t.b1[0]; }
     if (ev && split_weights) cudaEventRecord(ev[0], st);
     t.A = A; t.colsum = colsum; t.ksplit = ksplit; t.part = g1part;
+    t.zero_colsum = nullptr; t.zero_colsum_n = 0;
+    if (zero && ksplit > 1) { t.zero_colsum = colsum; t.zero_colsum_n = nad * 2 * H; }
     int bn = 128;
     if (ksplit == 1 && B <= 4096) bn = (H % 32 == 0) ? 32 : H;      // few row tiles: narrow hidden slices -> more CTAs
     if (int rc = launch_gemm1_tc(t, bn, st)) return rc;
@@ -179,6 +191,8 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
         r.A = A; r.colsum = colsum;
         memset(&r.p2p, 0, sizeof(r.p2p));
         if (p2p) r.p2p = *p2p;
+        r.zero_dgb = nullptr; r.zero_dgb_n = 0; r.zero_S = nullptr; r.zero_S_n = 0;
+        if (zero) { r.zero_dgb = zero->dgb; r.zero_dgb_n = zero->dgb_n; r.zero_S = zero->S; r.zero_S_n = zero->S_n; }
         DBMM_CUDA(set_smem(k_reduce_stats, 0));
         DBMM_CUDA(launch_pdl(k_reduce_stats, dim3(ceil_div(B, RS_ROWS), nad), dim3(RS_THREADS), 0, st, r));
     }
@@ -357,12 +371,17 @@ static int train_step_impl(int phases, bool fresh,
                            float* grads, float* momentum_buf, float lr, const float* lr_dev, float momentum, float weight_decay,
                            dbmm_batch_stats stats, int64_t slot, const TrainWs& w, cudaStream_t st,
                            cudaEvent_t* ev = nullptr /* 7 events: before each of the 6 step kernels + after the last */,
-                           const P2pArgs* p2p = nullptr /* fused peer-memory all-reduce of the column sums / (dgamma, dbeta) */) {
+                           const P2pArgs* p2p = nullptr /* fused peer-memory all-reduce of the column sums / (dgamma, dbeta) */,
+                           TailPlan* tail = nullptr) {
     const int nad = old_ad ? 2 : 1;
+    const bool fused = tail && tail->fused;
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
     const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
     const size_t gram_floats = (size_t)(H + 1) * (H + 1 + C);
-    float* gram_t = w.gram + (size_t)(nad - 1) * gram_floats;
+    float* gram_cur = fused && tail->parity ? w.gram2 : w.gram;         // read by this step's row kernel
+    float* gram_nxt = fused && !tail->parity ? w.gram2 : w.gram;        // fused tail: filled for the next step
+    float* gram_t = gram_cur + (size_t)(nad - 1) * gram_floats;
+    float* S_cur = fused && tail->parity ? w.S2 : w.S;
     const bool tc1 = use_tc_gemm1(D, H);
     static const int skip = getenv("DBMM_SKIP") ? atoi(getenv("DBMM_SKIP")) : 0;   // timing experiments only: drop kernels by bit mask
     if (skip) phases &= ~skip;
@@ -371,22 +390,55 @@ static int train_step_impl(int phases, bool fresh,
         if (fresh) {
             DBMM_CUDA(cudaMemsetAsync(w.colsum, 0, w.accum_bytes, st));
             if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
+            if (fused && nad == 2)            // the frozen adapter's Gram matrix is constant: present in both halves
+                DBMM_CUDA(cudaMemcpyAsync(w.gram2, w.gram, sizeof(float) * gram_floats, cudaMemcpyDeviceToDevice, st));
         }
         const int ks = tc1 ? gemm1_ksplit(B, nad, D) : 1;
-        if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, fresh, ks, w.g1part, st, ev, p2p)) return rc;
+        StepZero sz;
+        sz.dgb = w.dgb; sz.dgb_n = 2 * H; sz.S = S_cur; sz.S_n = (H + 1 + C) * s_stride(H);
+        DBMM_CHECK_ARG(!fused || (tc1 && ks > 1), "fused step tail needs the D-sliced tensor-core GEMM-1");
+        if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, fresh, ks, w.g1part, st, ev, p2p,
+                                  fused && !fresh ? &sz : nullptr)) return rc;
     }
     if (phases & DBMM_PHASE_ROWS) {
+        if (fused && tail->join_pending) {                       // the previous step's W2 role: new Gram matrix
+            DBMM_CUDA(cudaStreamWaitEvent(st, tail->ev_join, 0));
+            tail->join_pending = false;
+        }
         mark(2);
         RowsTrainArgs ra;
         memset(&ra, 0, sizeof(ra));
         ra.B = B; ra.Bg = B_global; ra.idx = idx; ra.y = y; ra.grp = grp; ra.H = H; ra.C = C; ra.G = G;
-        ra.A = w.A; ra.strideA = (int64_t)B * H; ra.gram = w.gram; ra.colsum = w.colsum;
+        ra.A = w.A; ra.strideA = (int64_t)B * H; ra.gram = gram_cur; ra.colsum = w.colsum;
         ra.ad[0] = view_of(old_ad ? old_ad : ad); ra.ad[1] = view_of(ad);
         ra.w_old = ebd_weight; ra.inv_tau = inv_tau; ra.inv_B = 1.0f / (float)B_global;
         ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.slot = slot;
-        ra.dahat = w.dahat; ra.dgb = w.dgb; ra.S = w.S;
+        ra.dahat = w.dahat; ra.dgb = w.dgb; ra.S = S_cur;
         if (p2p) { ra.p2p = *p2p; ra.colsum_wb = w.colsum; }
         if (int rc = launch_rows_train(ra, nad, st)) return rc;
+    }
+    StepTailArgs ta;
+    if (fused) {
+        DBMM_CHECK_ARG((phases & (DBMM_PHASE_WGRAD | DBMM_PHASE_UPDATE)) == (DBMM_PHASE_WGRAD | DBMM_PHASE_UPDATE) || skip,
+                       "fused step tail runs whole steps only");
+        memset(&ta, 0, sizeof(ta));
+        ta.W1 = ad->W1; ta.b1 = ad->b1; ta.gamma = ad->gamma; ta.beta = ad->beta; ta.W2 = ad->W2; ta.b2 = ad->b2;
+        ta.g = grads; ta.v = momentum_buf; ta.lr_dev = lr_dev; ta.lr = lr; ta.momentum = momentum; ta.wd = weight_decay;
+        ta.part = w.part; ta.whi = w.whi + (size_t)(nad - 1) * H * D; ta.wlo = w.wlo + (size_t)(nad - 1) * H * D;
+        ta.That = That; ta.S = S_cur;
+        ta.gram_next = gram_nxt + (size_t)(nad - 1) * gram_floats; ta.gram_zero = gram_t;
+        ta.dgb = w.dgb; ta.colsum = w.colsum; ta.D = D; ta.H = H; ta.C = C; ta.nad = nad; ta.Bg = B_global;
+        const dbmm_adapter* a0 = old_ad ? old_ad : ad;
+        ta.rm[0] = a0->running_mean; ta.rv[0] = a0->running_var; ta.nbt[0] = (long long*)a0->num_batches_tracked;
+        ta.rm[1] = ad->running_mean; ta.rv[1] = ad->running_var; ta.nbt[1] = (long long*)ad->num_batches_tracked;
+        if (tail->side && (phases & DBMM_PHASE_UPDATE)) {        // W2 role off the critical path: concurrent with the dW1 GEMM
+            DBMM_CUDA(cudaEventRecord(tail->ev_fork, st));
+            DBMM_CUDA(cudaStreamWaitEvent(tail->side, tail->ev_fork, 0));
+            ta.roles = 2;
+            if (int rc = launch_step_tail(ta, tail->side)) return rc;
+            DBMM_CUDA(cudaEventRecord(tail->ev_join, tail->side));
+            tail->join_pending = true;
+        }
     }
     if (phases & DBMM_PHASE_WGRAD) {
         const bool tc = use_tc_wgrad(D, H);
@@ -414,7 +466,18 @@ static int train_step_impl(int phases, bool fresh,
             DBMM_LAUNCH_CHECK();
         }
         mark(4);
+        if (fused) {
+            DBMM_CHECK_ARG(tc || (skip & 32), "fused step tail needs the tensor-core dW1 kernel");
+            ta.nchunk = nchunk;
+            if (phases & DBMM_PHASE_UPDATE) {
+                ta.roles = tail->side ? 1 : 3;
+                if (int rc = launch_step_tail(ta, st)) return rc;
+            }
+            mark(5); mark(6);
+            return DBMM_OK;
+        }
         FinalizeArgs fa;
+        memset(&fa, 0, sizeof(fa));
         fa.part = tc ? w.part : nullptr; fa.nchunk = nchunk;
         fa.W2 = ad->W2; fa.b2 = ad->b2; fa.That = That; fa.S = w.S; fa.dgb = w.dgb;
         fa.gW1 = grads + oW1; fa.gb1 = grads + ob1; fa.ggamma = grads + og; fa.gbeta = grads + obeta;
@@ -432,7 +495,7 @@ static int train_step_impl(int phases, bool fresh,
         ua.whi = tc1 ? w.whi + (size_t)(nad - 1) * H * D : nullptr; ua.wlo = tc1 ? w.wlo + (size_t)(nad - 1) * H * D : nullptr;
         ua.That = That; ua.gram = gram_t;
         ua.D = D; ua.H = H; ua.C = C; ua.nad = nad; ua.Bg = B_global;
-        ua.colsum = w.colsum; ua.dgb = w.dgb; ua.S = w.S; ua.zero_accum = 1;
+        ua.colsum = w.colsum; ua.dgb = w.dgb; ua.S = w.S; ua.zero_accum = 3;
         const dbmm_adapter* a0 = old_ad ? old_ad : ad;
         ua.rm[0] = a0->running_mean; ua.rv[0] = a0->running_var; ua.nbt[0] = (long long*)a0->num_batches_tracked;
         ua.rm[1] = ad->running_mean; ua.rv[1] = ad->running_var; ua.nbt[1] = (long long*)ad->num_batches_tracked;
@@ -506,6 +569,8 @@ static std::mutex g_graph_mu;
 static std::vector<EpochGraph> g_graphs;
 static uint64_t g_graph_clock = 0;
 static cudaStream_t g_capture_stream[64] = {};
+static cudaStream_t g_side_stream[64] = {};          // second branch of the captured step (fused tail, W2 role)
+static cudaEvent_t g_fork_event[64] = {}, g_join_event[64] = {};
 constexpr size_t MAX_EPOCH_GRAPHS = 24;
 
 static bool graphs_enabled() {
@@ -524,6 +589,17 @@ struct DbmmComm {
     ncclComm_t nccl; int world, rank;
     char* p2p_local; char* p2p_peer[P2P_MAX_WORLD]; bool p2p_ok;
 };
+
+// Single-GPU epochs run the fused step tail (step_tail.cuh) when every step of the epoch takes the tensor-core kernels
+// with a D-sliced GEMM-1.  DBMM_TAIL=split keeps k_finalize_grads + k_update; DBMM_TAIL=serial fuses without the fork.
+static int tail_mode(int B0, int last_B, int nad, int D, int H, int C) {
+    const char* e = getenv("DBMM_TAIL");
+    if (e && strcmp(e, "split") == 0) return 0;
+    if (getenv("DBMM_SKIP")) return 0;
+    if (!(use_tc_gemm1(D, H) && use_tc_wgrad(D, H) && step_tail_supported(D, H, C))) return 0;
+    if (gemm1_ksplit(B0, nad, D) <= 1 || gemm1_ksplit(last_B, nad, D) <= 1) return 0;
+    return (e && strcmp(e, "serial") == 0) ? 1 : 2;
+}
 
 static bool p2p_enabled() {
     const char* e = getenv("DBMM_P2P");            // DBMM_P2P=0: NCCL all-reduces for the small vectors as well
@@ -564,6 +640,11 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
     if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * np, st));
     DBMM_CUDA(cudaMemcpyAsync(w.lr, lr_host, sizeof(float) * (size_t)steps, cudaMemcpyHostToDevice, st));
 
+    const int tmode = dp ? 0 : tail_mode(B0, (int)last_B, nad, D, H, C);
+    TailPlan tplan;
+    memset(&tplan, 0, sizeof(tplan));
+    tplan.fused = tmode > 0;
+
     auto enqueue = [&](cudaStream_t s_) -> int {
         for (int64_t s = 0; s < steps; ++s) {
             const int64_t p0 = s * batch_size;
@@ -583,10 +664,11 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
                 pa.world = world; pa.rank = rank; pa.step = (int)s;
                 for (int r = 0; r < world; ++r) pa.peer[r] = dcomm->p2p_peer[r];
             }
+            tplan.parity = (int)(s & 1);
             auto phase = [&](int ph) {
                 return train_step_impl(ph, s == 0, X, ldx, idx, y, grp, B, Bg, D, H, C, G, old_ad, ad, ebd_weight, That, inv_tau,
                                        grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, s_, nullptr,
-                                       use_p2p ? &pa : nullptr);
+                                       use_p2p ? &pa : nullptr, tplan.fused ? &tplan : nullptr);
             };
             if (!dp) { if (int rc = phase(DBMM_PHASE_ALL)) return rc; continue; }
             if (int rc = phase(DBMM_PHASE_GEMM1)) return rc;
@@ -597,6 +679,10 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
             static const bool skip_grad_ar = getenv("DBMM_SKIP_GRAD_AR") != nullptr;      // timing experiments only
             if (!skip_grad_ar) DBMM_NCCL(nc->AllReduce(grads, grads, np, ncclFloat32, ncclSum, comm, s_));
             if (int rc = phase(DBMM_PHASE_UPDATE)) return rc;
+        }
+        if (tplan.join_pending) {                                // last step's W2 role
+            DBMM_CUDA(cudaStreamWaitEvent(s_, tplan.ev_join, 0));
+            tplan.join_pending = false;
         }
         if (use_p2p) {                                           // instance numbers stay unique across replays of this graph
             k_p2p_bump<<<1, 1, 0, s_>>>(dcomm->p2p_local, (unsigned)steps);
@@ -619,7 +705,7 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
     key.ebd_weight = ebd_weight; key.That = That; key.inv_tau = inv_tau; key.grads = grads; key.mom = momentum_buf;
     key.momentum = momentum; key.wd = weight_decay; key.loss_sum = stats.loss_sum; key.counts = stats.counts; key.ws = ws;
     key.device = device; key.comm = dcomm; key.world = dp ? world : 1; key.rank = dp ? rank : 0;
-    key.local_batches = (dp ? local_batches : 0) | (reduce_stats ? 2 : 0) | (use_p2p ? 4 : 0);
+    key.local_batches = (dp ? local_batches : 0) | (reduce_stats ? 2 : 0) | (use_p2p ? 4 : 0) | (tmode << 3);
 
     std::lock_guard<std::mutex> lock(g_graph_mu);
     cudaGraphExec_t exec = nullptr;
@@ -629,6 +715,14 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
         DBMM_CHECK_ARG(device >= 0 && device < 64, "device index %d out of range", device);
         if (!g_capture_stream[device]) DBMM_CUDA(cudaStreamCreateWithFlags(&g_capture_stream[device], cudaStreamNonBlocking));
         cudaStream_t cs = g_capture_stream[device];
+        if (tmode == 2) {                      // the fork lives inside the captured graph only (under g_graph_mu)
+            if (!g_side_stream[device]) {
+                DBMM_CUDA(cudaStreamCreateWithFlags(&g_side_stream[device], cudaStreamNonBlocking));
+                DBMM_CUDA(cudaEventCreateWithFlags(&g_fork_event[device], cudaEventDisableTiming));
+                DBMM_CUDA(cudaEventCreateWithFlags(&g_join_event[device], cudaEventDisableTiming));
+            }
+            tplan.side = g_side_stream[device]; tplan.ev_fork = g_fork_event[device]; tplan.ev_join = g_join_event[device];
+        }
         DBMM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         const int rc = enqueue(cs);
         cudaGraph_t graph = nullptr;
@@ -918,7 +1012,11 @@ int dbmm_train_epoch_profile(const float* X, int64_t ldx, const int32_t* order, 
     std::vector<cudaEvent_t> ev((size_t)steps * 7);
     for (auto& e : ev) DBMM_CUDA(cudaEventCreate(&e));
     int rc = DBMM_OK;
+    TailPlan tplan;                                              // the fused tail is timed serialised (both roles in one launch)
+    memset(&tplan, 0, sizeof(tplan));
+    tplan.fused = tail_mode(B0, (int)(n_rows - (steps - 1) * batch_size), nad, D, H, C) > 0;
     for (int64_t s = 0; s < steps && !rc; ++s) {
+        tplan.parity = (int)(s & 1);
         const int64_t p0 = s * batch_size;
         const int B = (int)((n_rows - p0) < batch_size ? (n_rows - p0) : batch_size);
         if (s % 48 == 1) {                                       // a window of 48 steps (~620 queue entries) behind each hold
@@ -926,7 +1024,8 @@ int dbmm_train_epoch_profile(const float* X, int64_t ldx, const int32_t* order, 
             DBMM_LAUNCH_CHECK();
         }
         rc = train_step_impl(DBMM_PHASE_ALL, s == 0, X, ldx, order + p0, y, grp, B, B, D, H, C, G, old_ad, ad, ebd_weight, That,
-                             inv_tau, grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, st, &ev[(size_t)s * 7]);
+                             inv_tau, grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, st, &ev[(size_t)s * 7],
+                             nullptr, tplan.fused ? &tplan : nullptr);
     }
     if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("stream synchronize failed"); rc = DBMM_ERR_CUDA; }
     if (!rc) {

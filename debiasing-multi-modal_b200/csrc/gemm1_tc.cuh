@@ -29,6 +29,7 @@ struct Gemm1TcArgs {
     const float* bn_mean[2]; const float* bn_var[2]; const float* bn_gamma[2]; const float* bn_beta[2];
     int ksplit;        // > 1: blockIdx.z owns a slice of D and stores its raw partial tile (no bias, no sums) to
     float* part;       //      part[kpart][nad][B][H]; k_reduce_stats finishes the job
+    double* zero_colsum; int zero_colsum_n;     // ksplit > 1 only: CTA 0 resets the column sums k_reduce_stats will accumulate
 };
 
 __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ w, float* __restrict__ hi,
@@ -84,6 +85,8 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
         if (blockIdx.y == 0 && m0 + tid < a.B) ptx::prefetch_l2_bulk(a.X + r * a.ldx + (size_t)kb_lo * G1_BK, (uint32_t)KB * G1_BK * 4);
     }
     if (tid < BN) { sCol[0][tid] = 0.0; sCol[1][tid] = 0.0; }
+    if (a.zero_colsum && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        for (int e = tid; e < a.zero_colsum_n; e += G1_THREADS) a.zero_colsum[e] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { ptx::mbar_init(&full[s], G1_PRODUCERS); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(tmem_full, 1);
@@ -266,6 +269,8 @@ struct ReduceStatsArgs {
     float* A;          // [nad][B][H]
     double* colsum;    // [nad][2][H] or nullptr
     P2pArgs p2p;       // data parallel over peer memory: the last CTA pushes the column sums to every rank (channel 0)
+    double* zero_dgb; int zero_dgb_n;           // fused step tail: CTA 0 resets (dgamma, dbeta) and all CTAs share the reset of
+    float* zero_S; int zero_S_n;                //                  S -- the row kernel accumulates both next
 };
 constexpr int RS_ROWS = 16, RS_MAXK = 16, RS_THREADS = 256;
 
@@ -281,6 +286,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_reduce_stats(ReduceStatsArgs a) 
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     ptx::pdl_wait();
     ptx::pdl_launch();
+    if (a.zero_dgb && blockIdx.x == 0 && blockIdx.y == 0)
+        for (int e = tid; e < a.zero_dgb_n; e += RS_THREADS) a.zero_dgb[e] = 0.0;
+    if (a.zero_S) {
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
+        for (int e = cta * RS_THREADS + tid; e < a.zero_S_n; e += ncta * RS_THREADS) a.zero_S[e] = 0.f;
+    }
     if (c < H4) {
         const float4 bias = __ldg(reinterpret_cast<const float4*>(a.b1[ad]) + c);
 #pragma unroll

@@ -36,7 +36,7 @@ static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT, int RT
     return fl * 4 + 16;
 }
 
-template <int NAD, int CT, int NW>
+template <int NAD, int CT, int NW, bool P2P>
 __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
     constexpr int RT_WARPS = NW, RT_THREADS = NW * 32;
     extern __shared__ __align__(16) float dyn_smem[];
@@ -85,11 +85,12 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
             av_pre[s] = (warp < RT_ROWS && s < HS && j < H && r < a.B) ? __ldcg(a.A + (size_t)r * H + j) : 0.f;
         }
     }
-    const int cs_parity = a.p2p.world ? p2p_wait(a.p2p, 0) : 0;        // every rank's column sums have landed in the local slots
+    int cs_parity = 0;
+    if constexpr (P2P) cs_parity = p2p_wait(a.p2p, 0);                  // every rank's column sums have landed in the local slots
     for (int e = tid; e < NAD * H; e += RT_THREADS) {
         const int ad = e / H, j = e - ad * H;
         double s1, s2;
-        if (a.p2p.world) {
+        if constexpr (P2P) {
             s1 = p2p_sum(a.p2p, 0, cs_parity, (ad * 2 + 0) * H + j); s2 = p2p_sum(a.p2p, 0, cs_parity, (ad * 2 + 1) * H + j);
             if (blockIdx.x == 0) { a.colsum_wb[((size_t)ad * 2 + 0) * H + j] = s1; a.colsum_wb[((size_t)ad * 2 + 1) * H + j] = s2; }
         } else {
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
     }
     __syncthreads();
     for (int e = tid; e < 2 * H; e += RT_THREADS) atomicAdd(&a.dgb[e], (double)sDgb[e]);
-    if (a.p2p.world) p2p_push_when_last(a.p2p, 1, a.dgb, 2 * H, gridDim.x);
+    if constexpr (P2P) p2p_push_when_last(a.p2p, 1, a.dgb, 2 * H, gridDim.x);
 }
 
 static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) {
@@ -367,7 +368,7 @@ static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) 
     if (grid > 148 * 2) grid = 148 * 2;
 #define DBMM_RT_CASE(NAD_, CT_, NW_)                                                                      \
     do {                                                                                                  \
-        auto kern = k_rows_train<NAD_, CT_, NW_>;                                                         \
+        auto kern = ra.p2p.world ? k_rows_train<NAD_, CT_, NW_, true> : k_rows_train<NAD_, CT_, NW_, false>; \
         DBMM_CUDA(set_smem(kern, smem));    \
         DBMM_CUDA(launch_pdl(kern, dim3(grid), dim3(NW_ * 32), smem, st, ra));                            \
     } while (0)
