@@ -177,7 +177,8 @@ def _read_csv(path):
         return list(csv.DictReader(f))
 
 
-def _build_split(name, data_dir, embedding_dir, split, device=None):
+def read_split_arrays(name, data_dir, embedding_dir, split):
+    """(x fp32 [n, D], y, place, y_pred, filenames) of one split from the reference's own files."""
     emb = read_embedding_json(embedding_dir)
     sid = SPLIT_ID[split]
     if name == "waterbirds":
@@ -203,6 +204,16 @@ def _build_split(name, data_dir, embedding_dir, split, device=None):
             raise AssertionError(f"inconsistency between metadata in {data_dir} and {embedding_dir} for {fn}")
         x[i] = e["image_embedding"]
         y_pred[i] = int(e["y_pred"])
+    return x, y, place, y_pred, files
+
+
+def _build_split(name, data_dir, embedding_dir, split, device=None):
+    """One split as a device-resident dataset: from the packed store next to the JSON when there is a fresh one
+    (pack.py: no JSON parse at all), else from the reference's files."""
+    from . import pack
+    pk = pack.usable_pack(name, data_dir, embedding_dir)
+    x, y, place, y_pred, files = pk.split_arrays(split) if pk is not None else \
+        read_split_arrays(name, data_dir, embedding_dir, split)
     return EmbeddingDataset(x, y, place, y_pred, files, split=split, device=device, data_dir=data_dir,
                             embedding_dir=embedding_dir)
 
