@@ -470,10 +470,15 @@ static int train_step_impl(int phases, bool fresh,
             DBMM_CHECK_ARG(tc || (skip & 32), "fused step tail needs the tensor-core dW1 kernel");
             ta.nchunk = nchunk;
             if (phases & DBMM_PHASE_UPDATE) {
-                ta.roles = tail->side ? 1 : 3;
+                ta.roles = 1;
                 if (int rc = launch_step_tail(ta, st)) return rc;
+                mark(5);
+                if (!tail->side) {                               // no fork (stream launches, profiling): W2 role in line
+                    ta.roles = 2;
+                    if (int rc = launch_step_tail(ta, st)) return rc;
+                }
             }
-            mark(5); mark(6);
+            mark(6);
             return DBMM_OK;
         }
         FinalizeArgs fa;
@@ -1079,6 +1084,23 @@ int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float
     int grid = ceil_div(n, 256 * 4);
     if (grid > 148 * 8) grid = 148 * 8;
     k_sgd_flat<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, v, n, lr, momentum, weight_decay, first_step);
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+int dbmm_train_tail_mode(int batch_size, int last_batch, int n_adapters, int D, int H, int C) {
+    return tail_mode(batch_size, last_batch, n_adapters, D, H, C);
+}
+
+int dbmm_widen_f16(const void* src_f16, int64_t ld_src, float* dst, int64_t ld_dst, int64_t n_rows, int D, void* stream) {
+    DBMM_CHECK_ARG(src_f16 && dst && n_rows >= 0 && D >= 1 && ld_src >= D && ld_dst >= D, "bad widen arguments (n_rows=%lld D=%d)",
+                   (long long)n_rows, D);
+    if (n_rows == 0) return DBMM_OK;
+    const int vec = (D % 8 == 0) && (ld_src % 8 == 0) && (ld_dst % 4 == 0) && ((uintptr_t)src_f16 % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    const int64_t work = vec ? n_rows * (D / 8) : n_rows * D;
+    int64_t grid = (work + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    k_widen_f16<<<(int)grid, 256, 0, (cudaStream_t)stream>>>((const __half*)src_f16, ld_src, dst, ld_dst, n_rows, D, vec);
     DBMM_LAUNCH_CHECK();
     return DBMM_OK;
 }

@@ -8,6 +8,7 @@
 // and the backward needs only  dh = ds M^T + c t[0:H]  plus two small batch reductions
 //     S = [c*h | c | ds]^T [h | 1]   ->   dW2a = [W2 | b2 | That] S          (see k_w2grad).
 #pragma once
+#include <cuda_fp16.h>
 #include "gemm_simt.cuh"
 
 namespace dbmm {
@@ -604,6 +605,34 @@ __global__ void __launch_bounds__(256) k_sgd_flat(float* __restrict__ p, const f
         const float vv = first ? gg : (momentum * v[i] + gg);
         v[i] = vv;
         p[i] = pv - lr * vv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ingest: fp16 -> fp32 rows (exact).  Streaming: 16-byte loads of 8 halves, two 16-byte stores; D % 8 == 0 and 16-byte
+// aligned rows take the vector path, anything else the scalar one.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_widen_f16(const __half* __restrict__ src, int64_t ld_src, float* __restrict__ dst,
+                                                   int64_t ld_dst, int64_t n_rows, int D, int vec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int d8 = D >> 3;
+        const int64_t n8 = n_rows * d8;
+        for (int64_t i = t0; i < n8; i += stride) {
+            const int64_t r = i / d8; const int c = (int)(i - r * d8) << 3;
+            const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(src + r * ld_src + c));
+            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+            const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c2 = __half22float2(h[2]), d = __half22float2(h[3]);
+            float4* o = reinterpret_cast<float4*>(dst + r * ld_dst + c);
+            o[0] = make_float4(a.x, a.y, b.x, b.y);
+            o[1] = make_float4(c2.x, c2.y, d.x, d.y);
+        }
+    } else {
+        const int64_t n = n_rows * D;
+        for (int64_t i = t0; i < n; i += stride) {
+            const int64_t r = i / D; const int c = (int)(i - r * D);
+            dst[r * ld_dst + c] = __half2float(src[r * ld_src + c]);
+        }
     }
 }
 

@@ -65,8 +65,13 @@ class EmbeddingDataset:
         self.group_ratio = self.group_counts / len(self)
         # device-resident store
         self.device = device if device is not None else _device()
-        x = np.ascontiguousarray(x, dtype=np.float32)
-        self.x = torch.from_numpy(x).to(self.device)
+        if x.dtype == np.float16 and torch.device(self.device).type == "cuda":
+            # fp16 packed store (pack.py): half the host -> device bytes, widened exactly on the device (dbmm_widen_f16)
+            from . import ops
+            with torch.cuda.device(self.device):
+                self.x = ops.widen_f16(torch.from_numpy(np.ascontiguousarray(x)).to(self.device))
+        else:
+            self.x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
         self.labels = {
             "class": torch.from_numpy(self.y_array.astype(np.int32)).to(self.device),
             "spurious": torch.from_numpy(self.confounder_array.astype(np.int32)).to(self.device),
@@ -212,7 +217,7 @@ def _build_split(name, data_dir, embedding_dir, split, device=None):
     (pack.py: no JSON parse at all), else from the reference's files."""
     from . import pack
     pk = pack.usable_pack(name, data_dir, embedding_dir)
-    x, y, place, y_pred, files = pk.split_arrays(split) if pk is not None else \
+    x, y, place, y_pred, files = pk.split_arrays(split, raw=True) if pk is not None else \
         read_split_arrays(name, data_dir, embedding_dir, split)
     return EmbeddingDataset(x, y, place, y_pred, files, split=split, device=device, data_dir=data_dir,
                             embedding_dir=embedding_dir)

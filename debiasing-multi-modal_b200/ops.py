@@ -240,6 +240,7 @@ def train_epoch(X, order: torch.Tensor, batch_size: int, y, grp, ad: AdapterTens
 
 
 STEP_KERNELS = ("gemm1_tc", "reduce_stats", "rows_train", "wgrad_tc", "finalize_grads", "update")
+STEP_KERNELS_FUSED = ("gemm1_tc", "reduce_stats", "rows_train", "wgrad_tc", "tail_w1", "tail_w2")     # fused step tail
 
 
 def train_epoch_profile(X, order: torch.Tensor, batch_size: int, y, grp, ad: AdapterTensors, That, inv_tau, buf: TrainBuffers,
@@ -261,7 +262,14 @@ def train_epoch_profile(X, order: torch.Tensor, batch_size: int, y, grp, ad: Ada
                                             lrs[:steps].ctypes.data_as(C.POINTER(C.c_float)), momentum, weight_decay, stats.c(),
                                             ws.data_ptr(), ws.numel(), _stream_ptr(), out))
     buf.first_step = False
-    return dict(zip(STEP_KERNELS, [float(v) for v in out]))
+    last = n - (steps - 1) * batch_size
+    fused = lib.dbmm_train_tail_mode(min(batch_size, n), last, nad, D, H, Cn) > 0
+    return dict(zip(STEP_KERNELS_FUSED if fused else STEP_KERNELS, [float(v) for v in out]))
+
+
+def train_tail_mode(batch_size: int, last_batch: int, nad: int, D: int, H: int, Cn: int) -> int:
+    """0: k_finalize_grads + k_update; 1: fused tail in line; 2: fused tail, W2 role on a second graph branch."""
+    return int(_lib.load().dbmm_train_tail_mode(batch_size, last_batch, nad, D, H, Cn))
 
 
 def sgd_step(p: torch.Tensor, g: torch.Tensor, v: torch.Tensor, lr, momentum=0.9, weight_decay=5e-5, first_step=False):
@@ -271,6 +279,20 @@ def sgd_step(p: torch.Tensor, g: torch.Tensor, v: torch.Tensor, lr, momentum=0.9
         _check(t, torch.float32, n)
     _lib.check(lib.dbmm_sgd_step(p.data_ptr(), g.data_ptr(), v.data_ptr(), p.numel(), lr, momentum, weight_decay,
                                  1 if first_step else 0, _stream_ptr()))
+
+
+def widen_f16(src: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp16 rows [N, D] on the device -> fp32 rows (exact): the ingest step behind the fp16 packed store (pack.py)."""
+    lib = _lib.load()
+    if src.dtype != torch.float16 or src.dim() != 2 or not src.is_cuda or src.stride(1) != 1:
+        raise DbmmError("widen_f16: a CUDA fp16 [N, D] tensor with unit column stride is required")
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    if out.shape != src.shape or out.dtype != torch.float32 or out.stride(1) != 1 or out.device != src.device:
+        raise DbmmError("widen_f16: output must be a CUDA fp32 tensor of the same shape")
+    _lib.check(lib.dbmm_widen_f16(src.data_ptr(), src.stride(0), out.data_ptr(), out.stride(0), src.shape[0], src.shape[1],
+                                  _stream_ptr()))
+    return out
 
 
 def group_counts(logits: torch.Tensor, y, grp, stats: BatchStatsBuffers, batch_size: int, G=4, want_pred=False):

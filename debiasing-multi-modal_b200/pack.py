@@ -157,13 +157,15 @@ class Pack:
     def rows_of(self, split: str) -> np.ndarray:
         return np.nonzero(np.asarray(self.split) == SPLIT_ID[split])[0]
 
-    def split_arrays(self, split: str):
+    def split_arrays(self, split: str, raw: bool = False):
+        """(x, y, place, y_pred, filenames) of one split; raw=True keeps x in the stored dtype (fp16 stores are widened
+        on the device by the dataset, dbmm_widen_f16)."""
         r = self.rows_of(split)
         lo, hi = (int(r[0]), int(r[-1]) + 1) if len(r) else (0, 0)
         if len(r) and hi - lo != len(r):
             raise PackError(f"{self.path}: rows of split {split} are not contiguous")
         sl = slice(lo, hi)
-        return (np.asarray(self.x[sl], dtype=np.float32), np.asarray(self.y[sl]).astype(np.int64),
+        return (np.asarray(self.x[sl]) if raw else np.asarray(self.x[sl], dtype=np.float32), np.asarray(self.y[sl]).astype(np.int64),
                 np.asarray(self.place[sl]).astype(np.int64), np.asarray(self.y_pred[sl]).astype(np.int64),
                 list(self.filenames[sl]))
 

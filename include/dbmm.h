@@ -12,6 +12,7 @@
  *                         demo/util.py:118-136      optim.SGD (momentum 0.9, weight decay)
  *   dbmm_train_epoch      final_main.py:426-496, 571-653   the per-batch loop of one epoch
  *   dbmm_sgd_step         demo/util.py:118-136      SGD on a flat buffer (data-parallel path)
+ *   dbmm_widen_f16        data/waterbirds_embeddings.py:69-78  embeddings -> float32 tensors (ingest, fp16 store)
  *   dbmm_group_counts     final_main.py:383-391     update_dict on given logits
  *   dbmm_logits_ce        final_main.py:757-759,768 raw-embedding cosine logits + CE (zero-shot head)
  *   dbmm_supcon_fwd/bwd   demo/visualizer_supcon.py:1532-1571  contrastive loss, all anchors at once
@@ -208,9 +209,20 @@ int dbmm_train_epoch_profile(const float* X, int64_t ldx, const int32_t* order, 
                              float momentum, float weight_decay, dbmm_batch_stats stats,
                              void* ws, size_t ws_bytes, void* stream, float* kernel_us_host);
 
+/* How single-GPU epochs of this shape run the tail of a step: 0 = k_finalize_grads + k_update, 1 = fused step tail
+ * (k_tail_w1, k_tail_w2) in line, 2 = fused with the W2 role on a second branch of the epoch graph (default when every
+ * step takes the tensor-core kernels).  Names the kernels behind dbmm_train_epoch_profile's slots 4 and 5. */
+int dbmm_train_tail_mode(int batch_size, int last_batch, int n_adapters, int D, int H, int C);
+
 /* torch.optim.SGD on a flat buffer: g += wd*p; v = g (first_step) or momentum*v + g; p -= lr*v */
 int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float momentum, float weight_decay,
                   int first_step, void* stream);
+
+/* Ingest: fp16 rows [n_rows, D] (row stride ld_src halves) -> fp32 rows (row stride ld_dst floats), exact.  CLIP emits
+ * fp16 embeddings (clip_inference.py:169), so the packed store keeps them as fp16 when that is lossless and the host ->
+ * device copy moves half the bytes; the widening runs on the device, on `stream` (the copy stream in the e2e path).
+ * Replaces the per-item np.array(list) -> float32 tensor of data/waterbirds_embeddings.py:69-78. */
+int dbmm_widen_f16(const void* src_f16, int64_t ld_src, float* dst, int64_t ld_dst, int64_t n_rows, int D, void* stream);
 
 /* update_dict (final_main.py:383-391) on given logits [N, C]: adds into stats slot row/batch_size. */
 int dbmm_group_counts(const float* logits, const int32_t* y, const int32_t* grp, int64_t N, int C, int G,
