@@ -431,6 +431,7 @@ static int train_step_impl(int phases, bool fresh,
         const dbmm_adapter* a0 = old_ad ? old_ad : ad;
         ta.rm[0] = a0->running_mean; ta.rv[0] = a0->running_var; ta.nbt[0] = (long long*)a0->num_batches_tracked;
         ta.rm[1] = ad->running_mean; ta.rv[1] = ad->running_var; ta.nbt[1] = (long long*)ad->num_batches_tracked;
+        if (p2p) ta.p2p = *p2p;
         if (tail->side && (phases & DBMM_PHASE_UPDATE)) {        // W2 role off the critical path: concurrent with the dW1 GEMM
             DBMM_CUDA(cudaEventRecord(tail->ev_fork, st));
             DBMM_CUDA(cudaStreamWaitEvent(tail->side, tail->ev_fork, 0));
@@ -645,7 +646,11 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
     if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * np, st));
     DBMM_CUDA(cudaMemcpyAsync(w.lr, lr_host, sizeof(float) * (size_t)steps, cudaMemcpyHostToDevice, st));
 
-    const int tmode = dp ? 0 : tail_mode(B0, (int)last_B, nad, D, H, C);
+    // data parallel: the fused tail needs the peer-memory exchange (it replaces the NCCL gradient all-reduce) and shapes
+    // that fit its slots; shards of a global batch may differ by one row between ranks, which changes nothing here
+    const int64_t B0_min = dp && !local_batches ? B0 / world : B0, last_min = dp && !local_batches ? last_B / world : last_B;
+    const int tmode = dp && !(use_p2p && (size_t)H * D <= P2P_G_FLOATS && (size_t)(H + 1 + C) * s_stride(H) <= P2P_S_FLOATS)
+                          ? 0 : tail_mode((int)B0_min, (int)last_min, nad, D, H, C);
     TailPlan tplan;
     memset(&tplan, 0, sizeof(tplan));
     tplan.fused = tmode > 0;
@@ -675,7 +680,7 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
                                        grads, momentum_buf, 0.f, w.lr + s, momentum, weight_decay, stats, s, w, s_, nullptr,
                                        use_p2p ? &pa : nullptr, tplan.fused ? &tplan : nullptr);
             };
-            if (!dp) { if (int rc = phase(DBMM_PHASE_ALL)) return rc; continue; }
+            if (!dp || tplan.fused) { if (int rc = phase(DBMM_PHASE_ALL)) return rc; continue; }
             if (int rc = phase(DBMM_PHASE_GEMM1)) return rc;
             if (!use_p2p) DBMM_NCCL(nc->AllReduce(w.colsum, w.colsum, (size_t)nad * 2 * H, ncclFloat64, ncclSum, comm, s_));
             if (int rc = phase(DBMM_PHASE_ROWS)) return rc;

@@ -15,11 +15,26 @@
 
 namespace dbmm {
 
-constexpr int P2P_MAX_WORLD = 8, P2P_VEC = 512, P2P_CHANNELS = 2;
-constexpr size_t P2P_SLOT_BYTES = sizeof(double) * P2P_CHANNELS * 2 * P2P_MAX_WORLD * P2P_VEC;       // 128 KB
+constexpr int P2P_MAX_WORLD = 8, P2P_VEC = 512, P2P_CHANNELS = 3;      // channel 2: flags / ticket of the fp32 S matrix (slots below)
+constexpr size_t P2P_SLOT_BYTES = sizeof(double) * 2 * 2 * P2P_MAX_WORLD * P2P_VEC;                   // fp64 slots of channels 0, 1: 128 KB
 constexpr size_t P2P_FLAG_STRIDE = 32;                                                                // uint32 per 128-byte line
 constexpr size_t P2P_CTRL_BYTES = 4096;                                                               // flags | tickets | base
-constexpr size_t P2P_BYTES = P2P_SLOT_BYTES + P2P_CTRL_BYTES;
+// Gradient exchange of the fused data-parallel step tail (no NCCL inside the step):
+//   S slots  [parity][rank][P2P_S_FLOATS]   k_tail_w2 CTA c pushes slice c of the rank's S = [c*h | c | ds]^T [h | 1]
+//   G slots  [parity][rank][P2P_G_FLOATS]   k_tail_w1 CTA i pushes its slice of the rank's dW1 and raises G flag [i][rank]
+//   G flags  [P2P_G_CTAS][32 words]          one 128-byte line per CTA, word r = rank r's instance
+constexpr size_t P2P_S_FLOATS = 20480, P2P_G_FLOATS = 128 * 2048;
+constexpr int P2P_G_CTAS = 128;
+constexpr size_t P2P_S_OFF = P2P_SLOT_BYTES + P2P_CTRL_BYTES;
+constexpr size_t P2P_G_OFF = P2P_S_OFF + sizeof(float) * 2 * P2P_MAX_WORLD * P2P_S_FLOATS;
+constexpr size_t P2P_GF_OFF = P2P_G_OFF + sizeof(float) * 2 * P2P_MAX_WORLD * P2P_G_FLOATS;
+// Small vectors (channels 0, 1) travel as "LL" words: every fp64 value is two 8-byte stores {32 data bits, instance + 1},
+// each atomic over NVLink, so the consumer polls the data words themselves -- no system fence, no separate flag store,
+// one NVLink write latency per exchange.      LL slots [channel][parity][rank][P2P_VEC][2] x 8 bytes
+constexpr int P2P_S_CTAS = 32;                                     // S flags [P2P_S_CTAS][32 words]: k_tail_w2 CTA c pushes slice c of S
+constexpr size_t P2P_SF_OFF = P2P_GF_OFF + (size_t)P2P_G_CTAS * 128;
+constexpr size_t P2P_LL_OFF = P2P_SF_OFF + (size_t)P2P_S_CTAS * 128;
+constexpr size_t P2P_BYTES = P2P_LL_OFF + (size_t)2 * 2 * P2P_MAX_WORLD * P2P_VEC * 16;
 
 struct P2pArgs {
     int world, rank;          // world == 0: disabled (single GPU, or NCCL all-reduce between the kernels)
@@ -40,6 +55,26 @@ __device__ __forceinline__ unsigned* p2p_base(char* buf) {
     return reinterpret_cast<unsigned*>(buf + P2P_SLOT_BYTES) + ((size_t)P2P_CHANNELS * P2P_MAX_WORLD + P2P_CHANNELS) * P2P_FLAG_STRIDE;
 }
 
+__device__ __forceinline__ unsigned long long* p2p_ll_slot(char* buf, int ch, int parity, int src) {
+    return reinterpret_cast<unsigned long long*>(buf + P2P_LL_OFF) + ((((size_t)ch * 2 + parity) * P2P_MAX_WORLD + src) * P2P_VEC) * 2;
+}
+__device__ __forceinline__ void p2p_ll_store(unsigned long long* slot, int e, double v, unsigned tag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)tag << 32);
+    const unsigned long long w1 = (bits >> 32) | ((unsigned long long)tag << 32);
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 2 * (size_t)e), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double p2p_ll_load(const unsigned long long* slot, int e, unsigned tag) {
+    unsigned long long w0 = 0, w1 = 0;
+    for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot + 2 * (size_t)e) : "memory");
+        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+    }
+    if ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) __trap();      // a rank never arrived: fail loudly, do not hang
+    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+__device__ __forceinline__ unsigned p2p_instance(const P2pArgs& p) { return __ldcg(p2p_base(p.peer[p.rank])) + (unsigned)p.step; }
+
 // Called by EVERY thread of EVERY CTA at the end of the producer kernel (after its own accumulator atomics).
 // `local` holds the rank's complete vector once all CTAs have passed; n <= P2P_VEC doubles.
 __device__ __forceinline__ void p2p_push_when_last(const P2pArgs& p, int ch, const double* local, int n, unsigned total_ctas) {
@@ -51,44 +86,62 @@ __device__ __forceinline__ void p2p_push_when_last(const P2pArgs& p, int ch, con
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const unsigned inst = __ldcg(p2p_base(me)) + (unsigned)p.step;
+    const unsigned inst = p2p_instance(p);
     const int parity = inst & 1u;
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         const double v = __ldcg(local + e);
-        for (int r = 0; r < p.world; ++r) p2p_slot(p.peer[r], ch, parity, p.rank)[e] = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < p.world) {
-        unsigned* f = p2p_flag(p.peer[threadIdx.x], ch, p.rank);
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(inst + 1u) : "memory");
+        for (int r = 0; r < p.world; ++r) p2p_ll_store(p2p_ll_slot(p.peer[r], ch, parity, p.rank), e, v, inst + 1u);
     }
     if (threadIdx.x == 0) *p2p_ticket(me, ch) = 0u;    // ready for the next instance (ordered by the kernel boundary)
 }
 
-// Called by every thread of a consumer CTA before it needs the global vector.  Returns the slot parity to read.
+// Consumer side: the token (instance number) to pass to p2p_sum; the waiting happens per element there.
 __device__ __forceinline__ int p2p_wait(const P2pArgs& p, int ch) {
-    char* me = p.peer[p.rank];
-    const unsigned inst = __ldcg(p2p_base(me)) + (unsigned)p.step;
-    if ((int)threadIdx.x < p.world) {
-        const unsigned* f = p2p_flag(me, ch, threadIdx.x);
-        unsigned v = 0;
-        for (unsigned spin = 0; spin < (1u << 28); ++spin) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if ((int)(v - (inst + 1u)) >= 0) break;
-        }
-        if ((int)(v - (inst + 1u)) < 0) __trap();      // a rank never arrived: fail loudly instead of hanging the GPU
-    }
-    __syncthreads();
-    return inst & 1u;
+    (void)ch;
+    return (int)p2p_instance(p);
 }
-__device__ __forceinline__ double p2p_sum(const P2pArgs& p, int ch, int parity, int e) {
+// Element e of the global vector: polls every rank's LL word pair until it carries this instance, sums in rank order
+// (every rank adds the same numbers in the same order: the replicas stay bit-identical).
+__device__ __forceinline__ double p2p_sum(const P2pArgs& p, int ch, int token, int e) {
     char* me = p.peer[p.rank];
+    const unsigned inst = (unsigned)token;
     double s = 0.0;
-    for (int r = 0; r < p.world; ++r) s += __ldcg(p2p_slot(me, ch, parity, r) + e);
+    for (int r = 0; r < p.world; ++r) s += p2p_ll_load(p2p_ll_slot(me, ch, inst & 1u, r), e, inst + 1u);
     return s;
 }
 
 __global__ void k_p2p_bump(char* buf, unsigned steps) { *p2p_base(buf) += steps; }
+
+__device__ __forceinline__ float* p2p_s_slot(char* buf, int parity, int src) {
+    return reinterpret_cast<float*>(buf + P2P_S_OFF) + ((size_t)parity * P2P_MAX_WORLD + src) * P2P_S_FLOATS;
+}
+__device__ __forceinline__ float* p2p_g_slot(char* buf, int parity, int src) {
+    return reinterpret_cast<float*>(buf + P2P_G_OFF) + ((size_t)parity * P2P_MAX_WORLD + src) * P2P_G_FLOATS;
+}
+__device__ __forceinline__ unsigned* p2p_s_flag(char* buf, int cta, int src) {
+    return reinterpret_cast<unsigned*>(buf + P2P_SF_OFF) + (size_t)cta * 32 + src;
+}
+__device__ __forceinline__ unsigned* p2p_g_flag(char* buf, int cta, int src) {
+    return reinterpret_cast<unsigned*>(buf + P2P_GF_OFF) + (size_t)cta * 32 + src;
+}
+// k_tail_w1 under data parallelism: the calling CTA has stored its slice of the rank's dW1 into slot [parity][rank] of
+// every rank; raise G flag [cta][rank] everywhere, then wait until the same CTA of every rank has done so.
+__device__ __forceinline__ void p2p_g_exchange(const P2pArgs& p, int cta, unsigned inst) {
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < p.world) {
+        unsigned* f = p2p_g_flag(p.peer[threadIdx.x], cta, p.rank);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(inst + 1u) : "memory");
+        const unsigned* w = p2p_g_flag(p.peer[p.rank], cta, threadIdx.x);
+        unsigned v = 0;
+        for (unsigned spin = 0; spin < (1u << 28); ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+            if ((int)(v - (inst + 1u)) >= 0) break;
+        }
+        if ((int)(v - (inst + 1u)) < 0) __trap();
+    }
+    __syncthreads();
+}
+
 
 }  // namespace dbmm

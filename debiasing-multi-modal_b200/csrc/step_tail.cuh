@@ -18,12 +18,14 @@
 #pragma once
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "p2p.cuh"
 
 namespace dbmm {
 
 constexpr int ST_THREADS = 256, ST_MAXCHUNK = 16;                 // W1 role
 constexpr int ST2_THREADS = 512, ST2_ROWS = 64, ST_NSLOT = 5;     // W2 role
-constexpr int ST2_LP = 32 * ST_NSLOT;                             // row stride of the staged [W2 | b2 | That] rows (zero padded)
+constexpr int ST2_LP = 168, ST2_SP = 136, ST2_K8MAX = 152;        // smem row strides (== 8 mod 32: conflict-free mma fragments)
+                                                                  // of the staged [W2 | b2 | That] rows / of S; max padded K
 
 struct StepTailArgs {
     int roles;
@@ -38,14 +40,17 @@ struct StepTailArgs {
     int D, H, C, nad; int64_t Bg;
     float* rm[2]; float* rv[2]; long long* nbt[2];
     int n_w1_ctas, n_w2_ctas;
+    P2pArgs p2p;                              // data parallel: dW1 slices and S are summed over the ranks through peer memory
 };
 
 static inline size_t step_tail_smem_bytes(int H, int C) {
     const size_t KP = (H + 1 + C + 3) & ~3, NP = (H + 1 + 3) & ~3;
-    return sizeof(float) * (KP * NP + (size_t)ST2_ROWS * ST2_LP) + 16;
+    (void)KP; (void)NP;
+    return sizeof(float) * ((size_t)ST2_K8MAX * ST2_SP + (size_t)ST2_ROWS * ST2_LP) + 16;
 }
 
 // ---- role bit 0: W1 CTAs + one chores CTA
+template <bool P2P>
 __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
     const int H = a.H, D = a.D;
     const int tid = threadIdx.x;
@@ -56,11 +61,37 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
         // chunk sum + SGD + tf32 split, 16-byte accesses (H * D is a multiple of 4)
         const int64_t n4 = (int64_t)H * D / 4;
         const size_t plane4 = (size_t)H * D / 4;
+        unsigned inst = 0; int parity = 0;
+        if constexpr (P2P) {
+            // the rank's chunk-summed slice goes to slot [parity][rank] of EVERY rank; then the same CTA of every rank
+            // exchanges flags (no grid-wide or NCCL synchronisation), and the slices are summed in rank order below
+            inst = p2p_instance(a.p2p); parity = inst & 1u;
+            for (int64_t i = (int64_t)bid * ST_THREADS + tid; i < n4; i += (int64_t)a.n_w1_ctas * ST_THREADS) {
+                float4 pt[ST_MAXCHUNK];
+#pragma unroll
+                for (int c = 0; c < ST_MAXCHUNK; ++c)
+                    pt[c] = c < a.nchunk ? __ldcg(reinterpret_cast<const float4*>(a.part) + c * plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 gs = pt[0];
+#pragma unroll
+                for (int c = 1; c < ST_MAXCHUNK; ++c) { gs.x += pt[c].x; gs.y += pt[c].y; gs.z += pt[c].z; gs.w += pt[c].w; }
+                for (int r = 0; r < a.p2p.world; ++r) reinterpret_cast<float4*>(p2p_g_slot(a.p2p.peer[r], parity, a.p2p.rank))[i] = gs;
+            }
+            p2p_g_exchange(a.p2p, bid, inst);
+        }
         for (int64_t i = (int64_t)bid * ST_THREADS + tid; i < n4; i += (int64_t)a.n_w1_ctas * ST_THREADS) {
             float4 pt[ST_MAXCHUNK];
+            if constexpr (P2P) {
+                char* me = a.p2p.peer[a.p2p.rank];
 #pragma unroll
-            for (int c = 0; c < ST_MAXCHUNK; ++c)
-                pt[c] = c < a.nchunk ? __ldcg(reinterpret_cast<const float4*>(a.part) + c * plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < P2P_MAX_WORLD; ++c)
+                    pt[c] = c < a.p2p.world ? __ldcg(reinterpret_cast<const float4*>(p2p_g_slot(me, parity, c)) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = P2P_MAX_WORLD; c < ST_MAXCHUNK; ++c) pt[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int c = 0; c < ST_MAXCHUNK; ++c)
+                    pt[c] = c < a.nchunk ? __ldcg(reinterpret_cast<const float4*>(a.part) + c * plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             const float4 pv = reinterpret_cast<const float4*>(a.W1)[i];
             const float4 vv = reinterpret_cast<const float4*>(a.v + oW1)[i];
             float4 gs = pt[0];
@@ -111,30 +142,96 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
     if (tid < a.nad) *a.nbt[tid] += 1;
 }
 
-// ---- role bit 1: W2 / b2 rows [d0, d0 + ST2_ROWS):  dW2a[d][n] = sum_k L[d][k] S[k][n],  L = [W2 | b2 | That]
+// ---- role bit 1: W2 / b2 rows [d0, d0 + ST2_ROWS):  dW2a[d][n] = sum_k L[d][k] S[k][n],  L = [W2 | b2 | That], then the
+// rows' share of the next Gram matrix.  Both small contractions run on the tensor cores as warp-level mma.sync m16n8k8
+// with 3xTF32 split operands (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~2^-20 relative, the policy of DESIGN.md 3.2);
+// 64-row tiles off the critical path do not warrant a tcgen05 / TMEM pipeline.
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;                 // tf32-exact head; the tensor core ignores the 13 low bits of lo
+    lo = __float_as_uint(x - __uint_as_float(hi));         // (|lo| < 2^-10 |x|, truncated at 2^-21 |x|)
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    mma_tf32(c, al, bh);
+    mma_tf32(c, ah, bl);
+    mma_tf32(c, ah, bh);
+}
+
+template <bool P2P>
 __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
     extern __shared__ __align__(16) float st_smem[];
     const int H = a.H, D = a.D, C = a.C;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const float lr = a.lr_dev ? __ldg(a.lr_dev) : a.lr;
     const size_t oW2 = (size_t)H * D + 3 * (size_t)H, ob2 = oW2 + (size_t)D * H;
-    const int K = H + 1 + C, N = H + 1, KP = (K + 3) & ~3, NP = (N + 3) & ~3;
+    const int K = H + 1 + C, N = H + 1, NPg = s_stride(H);            // NPg: row stride of S in global memory
+    const int KT = (K + 7) >> 3, K8 = KT * 8;                          // k-steps of the dW2a contraction
+    constexpr int LP = ST2_LP, SP = ST2_SP;
     const int w2 = blockIdx.x;
     {   // this step's Gram matrix has been consumed by k_rows_train: reset it for the step after next
         const int nz = N * K;
         for (int e = w2 * ST2_THREADS + tid; e < nz; e += (int)gridDim.x * ST2_THREADS) a.gram_zero[e] = 0.f;
     }
-    float* sS = st_smem;                        // [KP][NP]
-    float* sL = sS + (size_t)KP * NP;           // [ST2_ROWS][LP]; after the update: the NEW [W2 | b2 | That] rows
-    constexpr int LP = ST2_LP;
+    float* sS = st_smem;                        // [K8][SP], zero padded
+    float* sL = sS + (size_t)ST2_K8MAX * SP;    // [ST2_ROWS][LP], zero padded; after the update: the NEW [W2 | b2 | That] rows
     const int d0 = w2 * ST2_ROWS;
-    {   // S is stored with row stride NP: whole 16-byte chunks, everything in flight at once
-        const int n4 = K * NP / 4;
+    const int n4row = NPg >> 2;                 // 16-byte chunks per row of S
+    if constexpr (P2P) {
+        // Data parallel: this CTA pushes its slice of the rank's S to every rank (off the critical path: the row kernel
+        // only pushes the LL words of dgamma / dbeta), raises S flag [cta][rank] everywhere, then waits for every slice
+        // of every rank and sums the slots in rank order.
+        const unsigned inst = p2p_instance(a.p2p);
+        const int parity = inst & 1u;
+        const int n4 = K * n4row, per = (n4 + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int lo4 = w2 * per, hi4 = min(n4, lo4 + per);
+        for (int e = lo4 + tid; e < hi4; e += ST2_THREADS) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(a.S) + e);
+            for (int r = 0; r < a.p2p.world; ++r) reinterpret_cast<float4*>(p2p_s_slot(a.p2p.peer[r], parity, a.p2p.rank))[e] = v;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < a.p2p.world) {
+            unsigned* f = p2p_s_flag(a.p2p.peer[tid], w2, a.p2p.rank);
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(inst + 1u) : "memory");
+        }
+        if (tid < (int)gridDim.x * a.p2p.world) {
+            const unsigned* f = p2p_s_flag(a.p2p.peer[a.p2p.rank], tid / a.p2p.world, tid % a.p2p.world);
+            unsigned v = 0;
+            for (unsigned spin = 0; spin < (1u << 28); ++spin) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if ((int)(v - (inst + 1u)) >= 0) break;
+            }
+            if ((int)(v - (inst + 1u)) < 0) __trap();
+        }
+        __syncthreads();
+        char* me = a.p2p.peer[a.p2p.rank];
+        for (int e = tid; e < n4; e += ST2_THREADS) {
+            float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < a.p2p.world; ++r) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(p2p_s_slot(me, parity, r)) + e);
+                acc4.x += v.x; acc4.y += v.y; acc4.z += v.z; acc4.w += v.w;
+            }
+            const int k = e / n4row, q = e - k * n4row;
+            *reinterpret_cast<float4*>(sS + (size_t)k * SP + q * 4) = acc4;
+        }
+    } else {                // S rows: whole 16-byte chunks, everything in flight at once
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sS);
-        for (int e = tid; e < n4; e += ST2_THREADS) ptx::cp_async16(dst + e * 16, a.S + e * 4);
-        for (int e = K * NP + tid; e < KP * NP; e += ST2_THREADS) sS[e] = 0.f;
+        for (int e = tid; e < K * n4row; e += ST2_THREADS) {
+            const int k = e / n4row, q = e - k * n4row;
+            ptx::cp_async16(dst + ((size_t)k * SP + q * 4) * 4, a.S + (size_t)e * 4);
+        }
     }
-    {   // W2 rows: 16-byte copies (H % 4 == 0, KP % 4 == 0); b2 / That / padding: scalars
+    {   // zero padding of sS: columns [NPg, SP) of every row, rows [K, K8)
+        const int padc = SP - NPg;
+        for (int e = tid; e < K * padc; e += ST2_THREADS) { const int k = e / padc; sS[(size_t)k * SP + NPg + (e - k * padc)] = 0.f; }
+        for (int e = K * SP + tid; e < K8 * SP; e += ST2_THREADS) sS[e] = 0.f;
+    }
+    {   // W2 rows: 16-byte copies (H % 4 == 0); b2 / That / zero padding: scalars
         const int h4 = H >> 2;
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sL);
         for (int e = tid; e < ST2_ROWS * h4; e += ST2_THREADS) {
@@ -151,131 +248,113 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
             sL[(size_t)r * LP + k] = v;
         }
     }
-    // 4 x 4 register tiles: warp rq owns rows d0 + 4 rq .. + 3, lane cq columns 4 cq .. + 3 (< H); column H (b2) afterwards
-    const int rq = warp, cq = lane;
-    const bool worker = cq * 4 < H;
-    float4 vv[4];                                // momentum of the owned elements: requested before the contraction
+    // ---- dW2a: warp w owns the 16-row tile mt = w & 3 and the 8-column tiles nt = (w >> 2) + 4 j
+    constexpr int NJ = 5;                        // ceil(17 / 4) column tiles per warp at most (N <= 129 -> 17 tiles)
+    const int mt = warp & 3, nt0 = warp >> 2, NT = (N + 7) >> 3;
+    const int r0 = mt * 16 + g;                  // this lane's rows: r0 and r0 + 8
+    float2 vv[NJ][2];                            // momentum of the owned elements: requested before the contraction
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int d = d0 + rq * 4 + i;
-        vv[i] = (worker && d < D) ? *reinterpret_cast<const float4*>(a.v + oW2 + (size_t)d * H + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NJ; ++j) {
+        const int n = (nt0 + 4 * j) * 8 + 2 * t;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int d = d0 + r0 + 8 * hh;
+            vv[j][hh] = make_float2(0.f, 0.f);
+            if (nt0 + 4 * j < NT && d < D) {
+                if (n < H) vv[j][hh] = *reinterpret_cast<const float2*>(a.v + oW2 + (size_t)d * H + n);
+                else if (n == H) vv[j][hh].x = a.v[ob2 + d];
+            }
+        }
     }
-    float vb2 = 0.f;
-    if (lane < 4 && d0 + rq * 4 + lane < D) vb2 = a.v[ob2 + d0 + rq * 4 + lane];
     ptx::cp_async_wait<0>();
     __syncthreads();
-    float acc[4][4];
+    float acc[NJ][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < NJ; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    if (worker) {
-        for (int k = 0; k < KP; k += 4) {
-            float4 sv[4], lv[4];
+        for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
+    for (int ks = 0; ks < KT; ++ks) {
+        const int k0 = ks * 8;
+        uint32_t ah[4], al[4];
+        tf32_split(sL[(size_t)r0 * LP + k0 + t], ah[0], al[0]);
+        tf32_split(sL[(size_t)(r0 + 8) * LP + k0 + t], ah[1], al[1]);
+        tf32_split(sL[(size_t)r0 * LP + k0 + t + 4], ah[2], al[2]);
+        tf32_split(sL[(size_t)(r0 + 8) * LP + k0 + t + 4], ah[3], al[3]);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) sv[kk] = *reinterpret_cast<const float4*>(sS + (size_t)(k + kk) * NP + cq * 4);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) lv[i] = *reinterpret_cast<const float4*>(sL + (size_t)(rq * 4 + i) * LP + k);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float l[4] = {lv[i].x, lv[i].y, lv[i].z, lv[i].w};
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    acc[i][0] = fmaf(l[kk], sv[kk].x, acc[i][0]); acc[i][1] = fmaf(l[kk], sv[kk].y, acc[i][1]);
-                    acc[i][2] = fmaf(l[kk], sv[kk].z, acc[i][2]); acc[i][3] = fmaf(l[kk], sv[kk].w, acc[i][3]);
-                }
+        for (int j = 0; j < NJ; ++j) {
+            const int nt = nt0 + 4 * j;
+            if (nt < NT) {
+                uint32_t bh[2], bl[2];
+                tf32_split(sS[(size_t)(k0 + t) * SP + nt * 8 + g], bh[0], bl[0]);
+                tf32_split(sS[(size_t)(k0 + t + 4) * SP + nt * 8 + g], bh[1], bl[1]);
+                mma_3xtf32(acc[j], ah, al, bh, bl);
             }
         }
     }
-    // db2 of the warp's four rows: lane-strided dot products with column H of S
-    float gb2[4];
+    __syncthreads();                             // every warp is done reading the OLD rows in sL
+    // SGD on the owned elements (c fragment: rows r0 / r0 + 8, columns n, n + 1); the new values replace the old in sL
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float p = 0.f;
-        for (int k = lane; k < K; k += 32) p = fmaf(sL[(size_t)(rq * 4 + i) * LP + k], sS[(size_t)k * NP + H], p);
-        gb2[i] = warp_sum(p);
-    }
-    __syncthreads();                             // every thread is done reading the OLD rows in sL
+    for (int j = 0; j < NJ; ++j) {
+        const int nt = nt0 + 4 * j, n = nt * 8 + 2 * t;
+        if (nt >= NT) continue;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int d = d0 + rq * 4 + i;
-        if (d >= D) continue;
-        float* lrow = sL + (size_t)(rq * 4 + i) * LP;
-        if (worker) {
-            const float4 p4 = *reinterpret_cast<const float4*>(lrow + cq * 4);
-            const float px[4] = {p4.x, p4.y, p4.z, p4.w}, vx[4] = {vv[i].x, vv[i].y, vv[i].z, vv[i].w};
-            float po[4], vo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float g = acc[i][j] + a.wd * px[j];
-                vo[j] = a.momentum * vx[j] + g;
-                po[j] = px[j] - lr * vo[j];
+        for (int hh = 0; hh < 2; ++hh) {
+            const int r = r0 + 8 * hh, d = d0 + r;
+            if (d >= D) continue;
+            float* lrow = sL + (size_t)r * LP;
+            const float g0 = acc[j][2 * hh], g1 = acc[j][2 * hh + 1];
+            if (n < H) {
+                const float p0 = lrow[n], p1 = lrow[n + 1];
+                const float v0 = a.momentum * vv[j][hh].x + (g0 + a.wd * p0), v1 = a.momentum * vv[j][hh].y + (g1 + a.wd * p1);
+                const float q0 = p0 - lr * v0, q1 = p1 - lr * v1;
+                const size_t fo = (size_t)d * H + n;
+                *reinterpret_cast<float2*>(a.W2 + fo) = make_float2(q0, q1);
+                *reinterpret_cast<float2*>(a.v + oW2 + fo) = make_float2(v0, v1);
+                *reinterpret_cast<float2*>(a.g + oW2 + fo) = make_float2(g0, g1);
+                lrow[n] = q0; lrow[n + 1] = q1;
+            } else if (n == H) {
+                const float p0 = lrow[H];
+                const float v0 = a.momentum * vv[j][hh].x + (g0 + a.wd * p0);
+                const float q0 = p0 - lr * v0;
+                a.b2[d] = q0; a.v[ob2 + d] = v0; a.g[ob2 + d] = g0;
+                lrow[H] = q0;
             }
-            const size_t fo = (size_t)d * H + cq * 4;
-            *reinterpret_cast<float4*>(a.W2 + fo) = make_float4(po[0], po[1], po[2], po[3]);
-            *reinterpret_cast<float4*>(a.v + oW2 + fo) = make_float4(vo[0], vo[1], vo[2], vo[3]);
-            *reinterpret_cast<float4*>(a.g + oW2 + fo) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            *reinterpret_cast<float4*>(lrow + cq * 4) = make_float4(po[0], po[1], po[2], po[3]);
-        }
-        const float vb = __shfl_sync(0xffffffffu, vb2, i);
-        if (lane == 0) {
-            const float pv = lrow[H];
-            const float g = gb2[i] + a.wd * pv;
-            const float vn = a.momentum * vb + g;
-            const float pn = pv - lr * vn;
-            a.b2[d] = pn; a.v[ob2 + d] = vn; a.g[ob2 + d] = gb2[i];
-            lrow[H] = pn;
         }
     }
     __syncthreads();
-    // ---- Gram share of the new rows: warp w owns m in [8w, 8w + 8) and the last warp also the row m = H
-    const int ldg = K;
-    constexpr int MW = 8;
-    float gacc[MW][ST_NSLOT], gx[ST_NSLOT];
+    // ---- Gram share of the new rows: G[m][n] += sum_r L[r][m] L[r][n]  (m < N, n < K), 16 x 8 tiles dealt round-robin
+    const int ldg = K, MT = (N + 15) >> 4, NT2 = (K + 7) >> 3;
+    for (int tile = warp; tile < MT * NT2; tile += ST2_THREADS / 32) {
+        const int gm = tile / NT2, gn = tile - gm * NT2;
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int s = 0; s < ST_NSLOT; ++s) gx[s] = 0.f;
-#pragma unroll
-    for (int m = 0; m < MW; ++m)
-#pragma unroll
-        for (int s = 0; s < ST_NSLOT; ++s) gacc[m][s] = 0.f;
-    const int m0 = warp * MW;                    // the rows are zero padded to LP columns: no guards in the loop (columns
-    const float* rowp = sL + lane;               // m >= H of a short hidden layer produce products that are never stored)
-    const float* rowm = sL + m0;
-#pragma unroll 2
-    for (int r = 0; r < ST2_ROWS; ++r) {
-        float bv[ST_NSLOT];
-#pragma unroll
-        for (int s = 0; s < ST_NSLOT; ++s) bv[s] = rowp[r * LP + 32 * s];
-        const float ax = sL[r * LP + H];
-        const float4 a0 = *reinterpret_cast<const float4*>(rowm + r * LP), a1 = *reinterpret_cast<const float4*>(rowm + r * LP + 4);
-        const float amx[MW] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-        for (int s = 0; s < ST_NSLOT; ++s) gx[s] = fmaf(ax, bv[s], gx[s]);
-#pragma unroll
-        for (int q = 0; q < MW; ++q)
-#pragma unroll
-            for (int s = 0; s < ST_NSLOT; ++s) gacc[q][s] = fmaf(amx[q], bv[s], gacc[q][s]);
-    }
-#pragma unroll
-    for (int m = 0; m < MW; ++m) {
-        if (m0 + m >= H) break;
-#pragma unroll
-        for (int s = 0; s < ST_NSLOT; ++s) {
-            const int n = lane + 32 * s;
-            if (n < ldg) atomicAdd(&a.gram_next[(size_t)(m0 + m) * ldg + n], gacc[m][s]);
+        for (int ks = 0; ks < ST2_ROWS / 8; ++ks) {
+            const float* ra = sL + (size_t)(ks * 8 + t) * LP;
+            const float* rb = ra + 4 * LP;
+            uint32_t ah[4], al[4], bh[2], bl[2];
+            tf32_split(ra[gm * 16 + g], ah[0], al[0]);
+            tf32_split(ra[gm * 16 + g + 8], ah[1], al[1]);
+            tf32_split(rb[gm * 16 + g], ah[2], al[2]);
+            tf32_split(rb[gm * 16 + g + 8], ah[3], al[3]);
+            tf32_split(ra[gn * 8 + g], bh[0], bl[0]);
+            tf32_split(rb[gn * 8 + g], bh[1], bl[1]);
+            mma_3xtf32(c, ah, al, bh, bl);
         }
-    }
-    if (warp == ST2_THREADS / 32 - 1) {
+        const int n = gn * 8 + 2 * t;
 #pragma unroll
-        for (int s = 0; s < ST_NSLOT; ++s) {
-            const int n = lane + 32 * s;
-            if (n < ldg) atomicAdd(&a.gram_next[(size_t)H * ldg + n], gx[s]);
+        for (int hh = 0; hh < 2; ++hh) {
+            const int m = gm * 16 + g + 8 * hh;
+            if (m < N) {
+                if (n < ldg) atomicAdd(&a.gram_next[(size_t)m * ldg + n], c[2 * hh]);
+                if (n + 1 < ldg) atomicAdd(&a.gram_next[(size_t)m * ldg + n + 1], c[2 * hh + 1]);
+            }
         }
     }
 }
 
 static inline bool step_tail_supported(int D, int H, int C) {
-    return H % 4 == 0 && D % 4 == 0 && H <= 128 && (H + 1 + C) <= 32 * ST_NSLOT && step_tail_smem_bytes(H, C) <= 227 * 1024;
+    return H % 4 == 0 && D % 4 == 0 && H <= 128 && (H + 1 + C) <= ST2_K8MAX - 7 && s_stride(H) <= ST2_SP &&
+           step_tail_smem_bytes(H, C) <= 227 * 1024;
 }
 
 static int launch_step_tail(StepTailArgs a, cudaStream_t st) {
@@ -286,14 +365,23 @@ static int launch_step_tail(StepTailArgs a, cudaStream_t st) {
     a.n_w1_ctas = ceil_div((int64_t)a.H * a.D / 4, ST_THREADS);
     if (a.n_w1_ctas > 128) a.n_w1_ctas = 128;
     a.n_w2_ctas = ceil_div(a.D, ST2_ROWS);
+    const bool p2p = a.p2p.world > 1;
+    DBMM_CHECK_ARG(!p2p || (a.n_w1_ctas <= P2P_G_CTAS && a.n_w2_ctas <= P2P_S_CTAS && (size_t)a.H * a.D <= P2P_G_FLOATS &&
+                            (size_t)(a.H + 1 + a.C) * s_stride(a.H) <= P2P_S_FLOATS), "shape exceeds the peer-memory gradient slots");
     if (a.roles & 1) {
-        k_tail_w1<<<a.n_w1_ctas + 1, ST_THREADS, 0, st>>>(a);
+        if (p2p) k_tail_w1<true><<<a.n_w1_ctas + 1, ST_THREADS, 0, st>>>(a);
+        else k_tail_w1<false><<<a.n_w1_ctas + 1, ST_THREADS, 0, st>>>(a);
         DBMM_LAUNCH_CHECK();
     }
     if (a.roles & 2) {
         const size_t smem = step_tail_smem_bytes(a.H, a.C);
-        DBMM_CUDA(set_smem(k_tail_w2, smem));
-        k_tail_w2<<<a.n_w2_ctas, ST2_THREADS, smem, st>>>(a);
+        if (p2p) {
+            DBMM_CUDA(set_smem(k_tail_w2<true>, smem));
+            k_tail_w2<true><<<a.n_w2_ctas, ST2_THREADS, smem, st>>>(a);
+        } else {
+            DBMM_CUDA(set_smem(k_tail_w2<false>, smem));
+            k_tail_w2<false><<<a.n_w2_ctas, ST2_THREADS, smem, st>>>(a);
+        }
         DBMM_LAUNCH_CHECK();
     }
     return DBMM_OK;
