@@ -73,11 +73,11 @@ static inline cudaError_t set_smem(K kern, size_t dyn_bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes);
 }
 
-// Kernel launch with the programmatic-dependent-launch attribute (see ptx::pdl_wait).  Measured on B200 it does not
-// shorten the step (the kernels' own dependency chains dominate, not the boundaries: 58.6 vs 57.2 us/step), so it is
-// opt-in: DBMM_PDL=1.
+// Kernel launch with the programmatic-dependent-launch attribute (see ptx::pdl_wait): the next kernel's set-up and its
+// loads of data that do not depend on the predecessor overlap the predecessor's tail.  Measured on B200 with the fused
+// step tail: 40.1 vs 42.5 us/step.  DBMM_PDL=0 turns it off.
 static inline bool pdl_enabled() {
-    static const bool on = getenv("DBMM_PDL") && strcmp(getenv("DBMM_PDL"), "1") == 0;
+    static const bool on = !(getenv("DBMM_PDL") && strcmp(getenv("DBMM_PDL"), "0") == 0);
     return on;
 }
 template <typename... KArgs, typename... Args>

@@ -85,8 +85,6 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
         if (blockIdx.y == 0 && m0 + tid < a.B) ptx::prefetch_l2_bulk(a.X + r * a.ldx + (size_t)kb_lo * G1_BK, (uint32_t)KB * G1_BK * 4);
     }
     if (tid < BN) { sCol[0][tid] = 0.0; sCol[1][tid] = 0.0; }
-    if (a.zero_colsum && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
-        for (int e = tid; e < a.zero_colsum_n; e += G1_THREADS) a.zero_colsum[e] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { ptx::mbar_init(&full[s], G1_PRODUCERS); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(tmem_full, 1);
@@ -97,7 +95,24 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
+    // The embedding rows do not depend on the previous kernel: when the CTA's whole operand set fits the stage ring
+    // (training: 2 k-blocks), the producers put every X tile in flight BEFORE the dependency wait, so the HBM fetch
+    // overlaps the tail of the previous step (programmatic dependent launch); the weight slices follow after the wait.
+    const bool x_early = KB <= S;
+    if (warp < 4 && x_early) {
+        for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t sA = ptx::smem_u32(smem + (size_t)kb * Cfg::STAGE_BYTES);
+            const int k0 = (kb_lo + kb) * G1_BK;
+#pragma unroll
+            for (int id = tid; id < G1_BM * 8; id += G1_PRODUCERS) {
+                const int row = id >> 3, c = id & 7;
+                ptx::cp_async16(sA + ptx::sw128_offset(row, c), a.X + sRowOff[row] + k0 + c * 4);
+            }
+        }
+    }
     ptx::pdl_wait();                // W1 hi / lo come from the previous step's update kernel
+    if (a.zero_colsum && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)       // (its chores CTA read the column sums)
+        for (int e = tid; e < a.zero_colsum_n; e += G1_THREADS) a.zero_colsum[e] = 0.0;
     ptx::pdl_launch();
 
     if (warp < 4) {
@@ -114,10 +129,12 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
             uint8_t* stage = smem + (size_t)s * Cfg::STAGE_BYTES;
             const uint32_t sA = ptx::smem_u32(stage);
             const int k0 = (kb_lo + kb) * G1_BK;
+            if (!x_early) {
 #pragma unroll
-            for (int id = tid; id < G1_BM * 8; id += G1_PRODUCERS) {
-                const int row = id >> 3, c = id & 7;
-                ptx::cp_async16(sA + ptx::sw128_offset(row, c), a.X + sRowOff[row] + k0 + c * 4);
+                for (int id = tid; id < G1_BM * 8; id += G1_PRODUCERS) {
+                    const int row = id >> 3, c = id & 7;
+                    ptx::cp_async16(sA + ptx::sw128_offset(row, c), a.X + sRowOff[row] + k0 + c * 4);
+                }
             }
 #pragma unroll
             for (int t = 0; t < TERMS; ++t) {

@@ -61,6 +61,12 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
         // chunk sum + SGD + tf32 split, 16-byte accesses (H * D is a multiple of 4)
         const int64_t n4 = (int64_t)H * D / 4;
         const size_t plane4 = (size_t)H * D / 4;
+        // weights and momentum of the thread's first quad were written a whole step ago: requested before the wait
+        const int64_t i0 = (int64_t)bid * ST_THREADS + tid;
+        float4 pv0 = make_float4(0.f, 0.f, 0.f, 0.f), vv0 = pv0;
+        if (i0 < n4) { pv0 = reinterpret_cast<const float4*>(a.W1)[i0]; vv0 = reinterpret_cast<const float4*>(a.v + oW1)[i0]; }
+        ptx::pdl_wait();            // the chunk partials come from k_wgrad_tc
+        ptx::pdl_launch();
         unsigned inst = 0; int parity = 0;
         if constexpr (P2P) {
             // the rank's chunk-summed slice goes to slot [parity][rank] of EVERY rank; then the same CTA of every rank
@@ -92,8 +98,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
                 for (int c = 0; c < ST_MAXCHUNK; ++c)
                     pt[c] = c < a.nchunk ? __ldcg(reinterpret_cast<const float4*>(a.part) + c * plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            const float4 pv = reinterpret_cast<const float4*>(a.W1)[i];
-            const float4 vv = reinterpret_cast<const float4*>(a.v + oW1)[i];
+            const float4 pv = i == i0 ? pv0 : reinterpret_cast<const float4*>(a.W1)[i];
+            const float4 vv = i == i0 ? vv0 : reinterpret_cast<const float4*>(a.v + oW1)[i];
             float4 gs = pt[0];
 #pragma unroll
             for (int c = 1; c < ST_MAXCHUNK; ++c) { gs.x += pt[c].x; gs.y += pt[c].y; gs.z += pt[c].z; gs.w += pt[c].w; }
@@ -115,6 +121,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
         }
         return;
     }
+    ptx::pdl_wait();
+    ptx::pdl_launch();
     // ---- chores CTA (this role because k_wgrad_tc reads gamma and must have finished): b1 / gamma / beta (db1 = sum_B da
     // vanishes identically under BatchNorm: b1 moves by weight decay only, see k_finalize_grads), BatchNorm running
     // statistics of every adapter in the forward
@@ -369,9 +377,8 @@ static int launch_step_tail(StepTailArgs a, cudaStream_t st) {
     DBMM_CHECK_ARG(!p2p || (a.n_w1_ctas <= P2P_G_CTAS && a.n_w2_ctas <= P2P_S_CTAS && (size_t)a.H * a.D <= P2P_G_FLOATS &&
                             (size_t)(a.H + 1 + a.C) * s_stride(a.H) <= P2P_S_FLOATS), "shape exceeds the peer-memory gradient slots");
     if (a.roles & 1) {
-        if (p2p) k_tail_w1<true><<<a.n_w1_ctas + 1, ST_THREADS, 0, st>>>(a);
-        else k_tail_w1<false><<<a.n_w1_ctas + 1, ST_THREADS, 0, st>>>(a);
-        DBMM_LAUNCH_CHECK();
+        if (p2p) DBMM_CUDA(launch_pdl(k_tail_w1<true>, dim3(a.n_w1_ctas + 1), dim3(ST_THREADS), 0, st, a));
+        else DBMM_CUDA(launch_pdl(k_tail_w1<false>, dim3(a.n_w1_ctas + 1), dim3(ST_THREADS), 0, st, a));
     }
     if (a.roles & 2) {
         const size_t smem = step_tail_smem_bytes(a.H, a.C);

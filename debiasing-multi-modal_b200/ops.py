@@ -213,9 +213,15 @@ def train_step(X, y, grp, ad: AdapterTensors, That, inv_tau, buf: TrainBuffers, 
         buf.first_step = False
 
 
+def train_workspace_bytes(batch_size: int, D: int, H: int, Cn: int, nad: int = 1) -> int:
+    return int(_lib.load().dbmm_workspace_bytes(_lib.OP_TRAIN, batch_size, D, H, Cn, nad))
+
+
 def train_epoch(X, order: torch.Tensor, batch_size: int, y, grp, ad: AdapterTensors, That, inv_tau, buf: TrainBuffers,
-                lrs, stats: BatchStatsBuffers, *, old_ad=None, ebd_weight=0.5, G=4, momentum=0.9, weight_decay=5e-5):
-    """All steps of one epoch in a single C call (train_one_epoch / train_reg_seq_one_epoch loops)."""
+                lrs, stats: BatchStatsBuffers, *, old_ad=None, ebd_weight=0.5, G=4, momentum=0.9, weight_decay=5e-5, ws=None):
+    """All steps of one epoch in a single C call (train_one_epoch / train_reg_seq_one_epoch loops).
+    ws: caller-owned workspace (uint8 CUDA tensor of train_workspace_bytes) -- required when several members train
+    concurrently on different streams; default: the shared per-device scratch buffer."""
     lib = _lib.load()
     _check(X, torch.float32, "X", contiguous=False)
     _check(order, torch.int32, "order")
@@ -228,7 +234,8 @@ def train_epoch(X, order: torch.Tensor, batch_size: int, y, grp, ad: AdapterTens
     if len(lrs) != steps or stats.n_slots < steps:
         raise DbmmError(f"need {steps} learning rates / stat slots, got {len(lrs)} / {stats.n_slots}")
     nad = 2 if old_ad is not None else 1
-    ws = workspace(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, min(batch_size, n), D, H, Cn, nad), X.device)
+    if ws is None:
+        ws = workspace(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, min(batch_size, n), D, H, Cn, nad), X.device)
     old_p = old_ad.ptrs() if old_ad is not None else None
     _lib.check(lib.dbmm_train_epoch(X.data_ptr(), X.stride(0), order.data_ptr(), n, batch_size, y.data_ptr(), _ptr(grp),
                                     D, H, Cn, G, C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()),
