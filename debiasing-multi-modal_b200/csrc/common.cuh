@@ -119,6 +119,13 @@ static inline AdapterView view_of(const dbmm_adapter* a) {
 }
 
 // Train-step workspace carve-up (all offsets in bytes, 256-byte aligned).
+// Shared memory a training launch of the tensor-core kernels asks for: `pack` (data parallel) -> just the stage ring it
+// uses (two CTAs may share an SM, leaving SMs to the W2 role); otherwise the full ring, i.e. one CTA per SM.
+static inline size_t train_smem_bytes(size_t needed, size_t full, int pack) {
+    static const int env = getenv("DBMM_SOLO_KB") ? atoi(getenv("DBMM_SOLO_KB")) : -1;      // timing experiments
+    if (env >= 0) return needed > (size_t)env * 1024 ? needed : (size_t)env * 1024;
+    return pack ? needed : full;
+}
 constexpr int DBMM_LR_TABLE = 65536;          // learning rates (one per step) a single epoch graph can address
 constexpr int DBMM_G1_PART_ROWS = 16384;      // ksplit * nad * ceil128(B) never exceeds this (see gemm1_ksplit)
 

@@ -167,6 +167,7 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
         return DBMM_OK;
     }
     Gemm1TcArgs t;
+    memset(&t, 0, sizeof(t));
     t.X = X; t.ldx = ldx; t.idx = idx; t.pos0 = pos0; t.B = B; t.D = D; t.H = H; t.nad = nad;
     const dbmm_adapter* ads[2] = {old_ad ? old_ad : ad, ad};
     for (int i = 0; i < nad; ++i) {
@@ -178,7 +179,7 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
     }
     if (nad == 1) { t.Whi[1] = t.Whi[0]; t.Wlo[1] = t.Wlo[0]; t.b1[1] = t.b1[0]; }
     if (ev && split_weights) cudaEventRecord(ev[0], st);
-    t.A = A; t.colsum = colsum; t.ksplit = ksplit; t.part = g1part;
+    t.A = A; t.colsum = colsum; t.ksplit = ksplit; t.part = g1part; t.pack = p2p ? 1 : 0;
     t.zero_colsum = nullptr; t.zero_colsum_n = 0;
     if (zero && ksplit > 1) { t.zero_colsum = colsum; t.zero_colsum_n = nad * 2 * H; }
     int bn = 128;
@@ -414,7 +415,6 @@ static int train_step_impl(int phases, bool fresh,
         ra.w_old = ebd_weight; ra.inv_tau = inv_tau; ra.inv_B = 1.0f / (float)B_global;
         ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.slot = slot;
         ra.dahat = w.dahat; ra.dgb = w.dgb; ra.S = S_cur;
-        if (p2p) { ra.p2p = *p2p; ra.colsum_wb = w.colsum; }
         if (int rc = launch_rows_train(ra, nad, st)) return rc;
     }
     StepTailArgs ta;
@@ -449,10 +449,12 @@ static int train_step_impl(int phases, bool fresh,
         const double* colsum_t = w.colsum + (size_t)(nad - 1) * 2 * H;
         if (tc && !(skip & 32)) {
             WgradTcArgs t;
+            memset(&t, 0, sizeof(t));
             t.X = X; t.ldx = ldx; t.idx = idx; t.B = B; t.Bg = B_global; t.D = D; t.H = H;
             t.A = A_t; t.dahat = w.dahat; t.colsum = colsum_t; t.dgb = w.dgb; t.gamma = ad->gamma; t.part = w.part;
             memset(&t.p2p, 0, sizeof(t.p2p)); t.dgb_wb = w.dgb;
             if (p2p) t.p2p = *p2p;
+            t.pack = p2p ? 1 : 0;
             nchunk = wgrad_tc_chunks(B, &t.rows_per_chunk);
             if (int rc = launch_wgrad_tc(t, nchunk, st)) return rc;
         } else {
@@ -649,7 +651,8 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
     // data parallel: the fused tail needs the peer-memory exchange (it replaces the NCCL gradient all-reduce) and shapes
     // that fit its slots; shards of a global batch may differ by one row between ranks, which changes nothing here
     const int64_t B0_min = dp && !local_batches ? B0 / world : B0, last_min = dp && !local_batches ? last_B / world : last_B;
-    const int tmode = dp && !(use_p2p && (size_t)H * D <= P2P_G_FLOATS && (size_t)(H + 1 + C) * s_stride(H) <= P2P_S_FLOATS)
+    const int tmode = dp && !(use_p2p && (size_t)H * D <= P2P_G_FLOATS && (size_t)(H + 1 + C) * s_stride(H) <= P2P_S_FLOATS &&
+                              ceil_div(D, step_tail_w2_rows(true)) <= P2P_S_CTAS && ceil_div(D, step_tail_w2_rows(true)) * world <= ST2_THREADS)
                           ? 0 : tail_mode((int)B0_min, (int)last_min, nad, D, H, C);
     TailPlan tplan;
     memset(&tplan, 0, sizeof(tplan));
@@ -672,6 +675,8 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
             memset(&pa, 0, sizeof(pa));
             if (use_p2p) {
                 pa.world = world; pa.rank = rank; pa.step = (int)s;
+                static const int dp_skip = getenv("DBMM_DP_SKIP") ? atoi(getenv("DBMM_DP_SKIP")) : 0;      // timing experiments only
+                pa.skip = dp_skip;
                 for (int r = 0; r < world; ++r) pa.peer[r] = dcomm->p2p_peer[r];
             }
             tplan.parity = (int)(s & 1);

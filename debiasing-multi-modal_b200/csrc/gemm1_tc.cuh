@@ -29,6 +29,8 @@ struct Gemm1TcArgs {
     const float* bn_mean[2]; const float* bn_var[2]; const float* bn_gamma[2]; const float* bn_beta[2];
     int ksplit;        // > 1: blockIdx.z owns a slice of D and stores its raw partial tile (no bias, no sums) to
     float* part;       //      part[kpart][nad][B][H]; k_reduce_stats finishes the job
+    int pack;          // data parallel: request only the used part of the stage ring (two CTAs may share an SM)
+    int stages;        // set by the launcher: min(ring depth of the configuration, k-blocks per CTA)
     double* zero_colsum; int zero_colsum_n;     // ksplit > 1 only: CTA 0 resets the column sums k_reduce_stats will accumulate
 };
 
@@ -55,7 +57,7 @@ struct G1Cfg {
 template <int BN, int TERMS>
 __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
     using Cfg = G1Cfg<BN, TERMS>;
-    constexpr int S = Cfg::STAGES;
+    const int S = a.stages;                             // stage ring depth: the launch sizes the shared memory for it
     extern __shared__ uint8_t g1_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)g1_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + (size_t)S * Cfg::STAGE_BYTES);
@@ -257,7 +259,12 @@ static int launch_gemm1_tc_impl(const Gemm1TcArgs& a, cudaStream_t st) {
     auto kern = k_gemm1_tc<BN, TERMS>;
     DBMM_CUDA(set_smem(kern, Cfg::SMEM));
     dim3 grid(ceil_div(a.B, G1_BM), a.nad * (a.H / BN), a.ksplit);
-    DBMM_CUDA(launch_pdl(kern, grid, dim3(G1_THREADS), Cfg::SMEM, st, a));
+    // a D-sliced training CTA owns 2 k-blocks of the 4-deep ring; see train_smem_bytes for what is requested
+    Gemm1TcArgs b = a;
+    const int kb_per = (a.D / G1_BK + a.ksplit - 1) / a.ksplit;
+    b.stages = kb_per < Cfg::STAGES ? kb_per : Cfg::STAGES;
+    const size_t smem = train_smem_bytes((size_t)b.stages * Cfg::STAGE_BYTES + 1024 + 256, Cfg::SMEM, a.pack);
+    DBMM_CUDA(launch_pdl(kern, grid, dim3(G1_THREADS), smem, st, b));
     return DBMM_OK;
 }
 
@@ -285,7 +292,7 @@ struct ReduceStatsArgs {
     const float* b1[2];
     float* A;          // [nad][B][H]
     double* colsum;    // [nad][2][H] or nullptr
-    P2pArgs p2p;       // data parallel over peer memory: the last CTA pushes the column sums to every rank (channel 0)
+    P2pArgs p2p;       // data parallel over peer memory: the last CTA all-reduces the column sums in place (channel 0)
     double* zero_dgb; int zero_dgb_n;           // fused step tail: CTA 0 resets (dgamma, dbeta) and all CTAs share the reset of
     float* zero_S; int zero_S_n;                //                  S -- the row kernel accumulates both next
 };
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_reduce_stats(ReduceStatsArgs a) 
         for (int rr = 0; rr < 8; ++rr) v += (double)sS[which][rr][j];
         atomicAdd(&a.colsum[((size_t)ad * 2 + which) * H + j], v);
     }
-    if (a.p2p.world) p2p_push_when_last(a.p2p, 0, a.colsum, a.nad * 2 * H, gridDim.x * gridDim.y);
+    if (a.p2p.world) p2p_allreduce_when_last(a.p2p, 0, a.colsum, a.nad * 2 * H, gridDim.x * gridDim.y);
 }
 
 }  // namespace dbmm

@@ -21,17 +21,17 @@ constexpr size_t P2P_FLAG_STRIDE = 32;                                          
 constexpr size_t P2P_CTRL_BYTES = 4096;                                                               // flags | tickets | base
 // Gradient exchange of the fused data-parallel step tail (no NCCL inside the step):
 //   S slots  [parity][rank][P2P_S_FLOATS]   k_tail_w2 CTA c pushes slice c of the rank's S = [c*h | c | ds]^T [h | 1]
-//   G slots  [parity][rank][P2P_G_FLOATS]   k_tail_w1 CTA i pushes its slice of the rank's dW1 and raises G flag [i][rank]
-//   G flags  [P2P_G_CTAS][32 words]          one 128-byte line per CTA, word r = rank r's instance
+//   G slots  [parity][rank][P2P_G_FLOATS] x 2   k_tail_w1 pushes the rank's chunk-summed dW1 as LL words (32 data bits +
+//                                               instance tag per 8-byte store): the consumer polls the data itself
 constexpr size_t P2P_S_FLOATS = 20480, P2P_G_FLOATS = 128 * 2048;
-constexpr int P2P_G_CTAS = 128;
+constexpr int P2P_G_CTAS = 128;                                     // (size of the former flag region, kept as padding)
 constexpr size_t P2P_S_OFF = P2P_SLOT_BYTES + P2P_CTRL_BYTES;
 constexpr size_t P2P_G_OFF = P2P_S_OFF + sizeof(float) * 2 * P2P_MAX_WORLD * P2P_S_FLOATS;
-constexpr size_t P2P_GF_OFF = P2P_G_OFF + sizeof(float) * 2 * P2P_MAX_WORLD * P2P_G_FLOATS;
+constexpr size_t P2P_GF_OFF = P2P_G_OFF + 2 * sizeof(float) * 2 * P2P_MAX_WORLD * P2P_G_FLOATS;
 // Small vectors (channels 0, 1) travel as "LL" words: every fp64 value is two 8-byte stores {32 data bits, instance + 1},
 // each atomic over NVLink, so the consumer polls the data words themselves -- no system fence, no separate flag store,
 // one NVLink write latency per exchange.      LL slots [channel][parity][rank][P2P_VEC][2] x 8 bytes
-constexpr int P2P_S_CTAS = 32;                                     // S flags [P2P_S_CTAS][32 words]: k_tail_w2 CTA c pushes slice c of S
+constexpr int P2P_S_CTAS = 64;                                     // S flags [P2P_S_CTAS][32 words]: k_tail_w2 CTA c pushes slice c of S
 constexpr size_t P2P_SF_OFF = P2P_GF_OFF + (size_t)P2P_G_CTAS * 128;
 constexpr size_t P2P_LL_OFF = P2P_SF_OFF + (size_t)P2P_S_CTAS * 128;
 constexpr size_t P2P_BYTES = P2P_LL_OFF + (size_t)2 * 2 * P2P_MAX_WORLD * P2P_VEC * 16;
@@ -39,6 +39,8 @@ constexpr size_t P2P_BYTES = P2P_LL_OFF + (size_t)2 * 2 * P2P_MAX_WORLD * P2P_VE
 struct P2pArgs {
     int world, rank;          // world == 0: disabled (single GPU, or NCCL all-reduce between the kernels)
     int step;                 // instance = *base + step
+    int skip;                 // timing experiments only (DBMM_DP_SKIP): bit 0/1 sum only the own LL slot of channel 0/1, bit 2 no
+                              // wait for the dW1 slices, bit 3 no wait for S, bit 4 no system fence before the dW1 flags
     char* peer[P2P_MAX_WORLD];
 };
 
@@ -106,6 +108,7 @@ __device__ __forceinline__ double p2p_sum(const P2pArgs& p, int ch, int token, i
     char* me = p.peer[p.rank];
     const unsigned inst = (unsigned)token;
     double s = 0.0;
+    if (p.skip & (1 << ch)) return p2p_ll_load(p2p_ll_slot(me, ch, inst & 1u, p.rank), e, inst + 1u);
     for (int r = 0; r < p.world; ++r) s += p2p_ll_load(p2p_ll_slot(me, ch, inst & 1u, r), e, inst + 1u);
     return s;
 }
@@ -115,33 +118,65 @@ __global__ void k_p2p_bump(char* buf, unsigned steps) { *p2p_base(buf) += steps;
 __device__ __forceinline__ float* p2p_s_slot(char* buf, int parity, int src) {
     return reinterpret_cast<float*>(buf + P2P_S_OFF) + ((size_t)parity * P2P_MAX_WORLD + src) * P2P_S_FLOATS;
 }
-__device__ __forceinline__ float* p2p_g_slot(char* buf, int parity, int src) {
-    return reinterpret_cast<float*>(buf + P2P_G_OFF) + ((size_t)parity * P2P_MAX_WORLD + src) * P2P_G_FLOATS;
+__device__ __forceinline__ unsigned long long* p2p_g_ll(char* buf, int parity, int src) {        // 4 words per float4
+    return reinterpret_cast<unsigned long long*>(buf + P2P_G_OFF) + ((size_t)parity * P2P_MAX_WORLD + src) * P2P_G_FLOATS;
+}
+__device__ __forceinline__ void p2p_g_store(unsigned long long* slot, int64_t i, float4 v, unsigned tag) {
+    const unsigned long long t = (unsigned long long)tag << 32;
+    const unsigned long long w0 = __float_as_uint(v.x) | t, w1 = __float_as_uint(v.y) | t, w2 = __float_as_uint(v.z) | t, w3 = __float_as_uint(v.w) | t;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 4 * i), "l"(w0), "l"(w1) : "memory");
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 4 * i + 2), "l"(w2), "l"(w3) : "memory");
+}
+__device__ __forceinline__ float4 p2p_g_load(const unsigned long long* slot, int64_t i, unsigned tag, bool no_wait) {
+    unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    bool ok = false;
+    for (unsigned spin = 0; spin < (no_wait ? 1u : (1u << 26)); ++spin) {
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot + 4 * i) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(slot + 4 * i + 2) : "memory");
+        ok = (unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag && (unsigned)(w2 >> 32) == tag && (unsigned)(w3 >> 32) == tag;
+        if (ok) break;
+    }
+    if (!ok && !no_wait) __trap();                    // a rank never arrived: fail loudly, do not hang
+    return make_float4(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1), __uint_as_float((unsigned)w2), __uint_as_float((unsigned)w3));
 }
 __device__ __forceinline__ unsigned* p2p_s_flag(char* buf, int cta, int src) {
     return reinterpret_cast<unsigned*>(buf + P2P_SF_OFF) + (size_t)cta * 32 + src;
 }
-__device__ __forceinline__ unsigned* p2p_g_flag(char* buf, int cta, int src) {
-    return reinterpret_cast<unsigned*>(buf + P2P_GF_OFF) + (size_t)cta * 32 + src;
-}
-// k_tail_w1 under data parallelism: the calling CTA has stored its slice of the rank's dW1 into slot [parity][rank] of
-// every rank; raise G flag [cta][rank] everywhere, then wait until the same CTA of every rank has done so.
-__device__ __forceinline__ void p2p_g_exchange(const P2pArgs& p, int cta, unsigned inst) {
-    __threadfence_system();
+// Whole all-reduce of a small fp64 vector inside the producer kernel (k_reduce_stats: BatchNorm column sums): the LAST
+// CTA to finish (atomic ticket) pushes the rank's vector to every OTHER rank as LL words, polls theirs, adds everything
+// in rank order (own values from registers) and writes the global vector back over `local` -- the consumer kernels
+// read plain memory and need no peer-memory code at all.
+__device__ __forceinline__ void p2p_allreduce_when_last(const P2pArgs& p, int ch, double* local, int n, unsigned total_ctas) {
+    __shared__ unsigned s_last3;
+    __threadfence();
     __syncthreads();
-    if ((int)threadIdx.x < p.world) {
-        unsigned* f = p2p_g_flag(p.peer[threadIdx.x], cta, p.rank);
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(inst + 1u) : "memory");
-        const unsigned* w = p2p_g_flag(p.peer[p.rank], cta, threadIdx.x);
-        unsigned v = 0;
-        for (unsigned spin = 0; spin < (1u << 28); ++spin) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
-            if ((int)(v - (inst + 1u)) >= 0) break;
-        }
-        if ((int)(v - (inst + 1u)) < 0) __trap();
+    char* me = p.peer[p.rank];
+    if (threadIdx.x == 0) s_last3 = (atomicAdd(p2p_ticket(me, ch), 1u) == total_ctas - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last3) return;
+    __threadfence();
+    const unsigned inst = p2p_instance(p);
+    const int parity = inst & 1u;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const double v = __ldcg(local + e);
+        for (int r = 0; r < p.world; ++r)
+            if (r != p.rank) p2p_ll_store(p2p_ll_slot(p.peer[r], ch, parity, p.rank), e, v, inst + 1u);
+        double s = 0.0;
+        for (int r = 0; r < p.world; ++r)
+            s += (r == p.rank || (p.skip & (1 << ch))) ? (r == p.rank ? v : 0.0) : p2p_ll_load(p2p_ll_slot(me, ch, parity, r), e, inst + 1u);
+        local[e] = s;
     }
-    __syncthreads();
+    if (threadIdx.x == 0) *p2p_ticket(me, ch) = 0u;
 }
 
+// k_wgrad_tc prologue: CTA (0, 0) pushes the rank's (dgamma, dbeta) to every rank INCLUDING itself; every CTA then sums
+// all ranks' LL slots with p2p_sum (the row kernel stays free of peer-memory code).
+__device__ __forceinline__ void p2p_push_now(const P2pArgs& p, int ch, const double* local, int n) {
+    const unsigned inst = p2p_instance(p);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const double v = __ldcg(local + e);
+        for (int r = 0; r < p.world; ++r) p2p_ll_store(p2p_ll_slot(p.peer[r], ch, inst & 1u, p.rank), e, v, inst + 1u);
+    }
+}
 
 }  // namespace dbmm

@@ -8,7 +8,6 @@
 #pragma once
 #include "kernels_simt.cuh"
 #include "ptx_sm100.cuh"
-#include "p2p.cuh"
 
 namespace dbmm {
 
@@ -25,7 +24,6 @@ struct RowsTrainArgs {
     float w_old, inv_tau, inv_B;
     double* loss_sum; int64_t* counts; int64_t slot;
     float* dahat; double* dgb; float* S;  // outputs: [B][H], [2][H] (+=), [H+1+C][H+1] (+=)
-    P2pArgs p2p; double* colsum_wb;       // data parallel over peer memory: global column sums in (channel 0), dgamma / dbeta out (channel 1)
 };
 
 static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT, int RT_WARPS) {
@@ -36,7 +34,7 @@ static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT, int RT
     return fl * 4 + 16;
 }
 
-template <int NAD, int CT, int NW, bool P2P>
+template <int NAD, int CT, int NW>
 __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
     constexpr int RT_WARPS = NW, RT_THREADS = NW * 32;
     extern __shared__ __align__(16) float dyn_smem[];
@@ -85,17 +83,9 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
             av_pre[s] = (warp < RT_ROWS && s < HS && j < H && r < a.B) ? __ldcg(a.A + (size_t)r * H + j) : 0.f;
         }
     }
-    int cs_parity = 0;
-    if constexpr (P2P) cs_parity = p2p_wait(a.p2p, 0);                  // every rank's column sums have landed in the local slots
     for (int e = tid; e < NAD * H; e += RT_THREADS) {
         const int ad = e / H, j = e - ad * H;
-        double s1, s2;
-        if constexpr (P2P) {
-            s1 = p2p_sum(a.p2p, 0, cs_parity, (ad * 2 + 0) * H + j); s2 = p2p_sum(a.p2p, 0, cs_parity, (ad * 2 + 1) * H + j);
-            if (blockIdx.x == 0) { a.colsum_wb[((size_t)ad * 2 + 0) * H + j] = s1; a.colsum_wb[((size_t)ad * 2 + 1) * H + j] = s2; }
-        } else {
-            s1 = a.colsum[((size_t)ad * 2 + 0) * H + j]; s2 = a.colsum[((size_t)ad * 2 + 1) * H + j];
-        }
+        const double s1 = a.colsum[((size_t)ad * 2 + 0) * H + j], s2 = a.colsum[((size_t)ad * 2 + 1) * H + j];
         const double m = s1 / (double)a.Bg;
         double v = s2 / (double)a.Bg - m * m;
         if (v < 0.0) v = 0.0;
@@ -356,7 +346,6 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
     }
     __syncthreads();
     for (int e = tid; e < 2 * H; e += RT_THREADS) atomicAdd(&a.dgb[e], (double)sDgb[e]);
-    if constexpr (P2P) p2p_push_when_last(a.p2p, 1, a.dgb, 2 * H, gridDim.x);
 }
 
 static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) {
@@ -368,7 +357,7 @@ static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) 
     if (grid > 148 * 2) grid = 148 * 2;
 #define DBMM_RT_CASE(NAD_, CT_, NW_)                                                                      \
     do {                                                                                                  \
-        auto kern = ra.p2p.world ? k_rows_train<NAD_, CT_, NW_, true> : k_rows_train<NAD_, CT_, NW_, false>; \
+        auto kern = k_rows_train<NAD_, CT_, NW_>;                                                         \
         DBMM_CUDA(set_smem(kern, smem));    \
         DBMM_CUDA(launch_pdl(kern, dim3(grid), dim3(NW_ * 32), smem, st, ra));                            \
     } while (0)

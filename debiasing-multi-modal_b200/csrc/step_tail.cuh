@@ -4,9 +4,8 @@
 //   role bit 0 (after k_wgrad_tc):  dW1 = sum of the batch-chunk partial tiles -> SGD on W1 -> tf32 split of the new W1
 //                                   (everything elementwise: one pass, 16 partial loads + p + v in flight per thread)
 //   role bit 1 (after k_rows_train, concurrent with k_wgrad_tc):
-//       W2 CTAs (64 embedding rows each, 512 threads: D / 64 = 16 CTAs fit the SMs the 128-CTA tensor-core kernels of
-//       the main branch leave free -- those kernels fill a whole SM's shared memory, so a co-scheduled W2 CTA would
-//       push them into a second wave): dW2a = [W2 | b2 | That] S -> SGD on W2 / b2 -> the slice's share of NEXT step's
+//       W2 CTAs (32 embedding rows each, 512 threads, 104 KB of shared memory: they fit on an SM BESIDE a CTA of the
+//       main branch's tensor-core kernels, whose training launches ask for a 2-deep / 1-deep stage ring = 97 KB): dW2a = [W2 | b2 | That] S -> SGD on W2 / b2 -> the slice's share of NEXT step's
 //       Gram matrix G = [W2 | b2]^T [W2 | b2 | That] (coalesced fp32 reds into the other half of a double buffer; this
 //       step's half, consumed by k_rows_train, is re-zeroed here).
 //   One more CTA of role bit 0 (k_wgrad_tc reads gamma): dgamma / dbeta / db1 -> SGD on b1 / gamma / beta, BatchNorm
@@ -23,7 +22,7 @@
 namespace dbmm {
 
 constexpr int ST_THREADS = 256, ST_MAXCHUNK = 16;                 // W1 role
-constexpr int ST2_THREADS = 512, ST2_ROWS = 64, ST_NSLOT = 5;     // W2 role
+constexpr int ST2_THREADS = 512, ST2_ROWS_MAX = 64;               // W2 role: 32 or 64 embedding rows per CTA (template)
 constexpr int ST2_LP = 168, ST2_SP = 136, ST2_K8MAX = 152;        // smem row strides (== 8 mod 32: conflict-free mma fragments)
                                                                   // of the staged [W2 | b2 | That] rows / of S; max padded K
 
@@ -46,7 +45,7 @@ struct StepTailArgs {
 static inline size_t step_tail_smem_bytes(int H, int C) {
     const size_t KP = (H + 1 + C + 3) & ~3, NP = (H + 1 + 3) & ~3;
     (void)KP; (void)NP;
-    return sizeof(float) * ((size_t)ST2_K8MAX * ST2_SP + (size_t)ST2_ROWS * ST2_LP) + 16;
+    return sizeof(float) * ((size_t)ST2_K8MAX * ST2_SP + (size_t)ST2_ROWS_MAX * ST2_LP) + 16;
 }
 
 // ---- role bit 0: W1 CTAs + one chores CTA
@@ -68,35 +67,27 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
         ptx::pdl_wait();            // the chunk partials come from k_wgrad_tc
         ptx::pdl_launch();
         unsigned inst = 0; int parity = 0;
-        if constexpr (P2P) {
-            // the rank's chunk-summed slice goes to slot [parity][rank] of EVERY rank; then the same CTA of every rank
-            // exchanges flags (no grid-wide or NCCL synchronisation), and the slices are summed in rank order below
-            inst = p2p_instance(a.p2p); parity = inst & 1u;
-            for (int64_t i = (int64_t)bid * ST_THREADS + tid; i < n4; i += (int64_t)a.n_w1_ctas * ST_THREADS) {
-                float4 pt[ST_MAXCHUNK];
-#pragma unroll
-                for (int c = 0; c < ST_MAXCHUNK; ++c)
-                    pt[c] = c < a.nchunk ? __ldcg(reinterpret_cast<const float4*>(a.part) + c * plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 gs = pt[0];
-#pragma unroll
-                for (int c = 1; c < ST_MAXCHUNK; ++c) { gs.x += pt[c].x; gs.y += pt[c].y; gs.z += pt[c].z; gs.w += pt[c].w; }
-                for (int r = 0; r < a.p2p.world; ++r) reinterpret_cast<float4*>(p2p_g_slot(a.p2p.peer[r], parity, a.p2p.rank))[i] = gs;
-            }
-            p2p_g_exchange(a.p2p, bid, inst);
-        }
+        if constexpr (P2P) { inst = p2p_instance(a.p2p); parity = inst & 1u; }
         for (int64_t i = (int64_t)bid * ST_THREADS + tid; i < n4; i += (int64_t)a.n_w1_ctas * ST_THREADS) {
             float4 pt[ST_MAXCHUNK];
+#pragma unroll
+            for (int c = 0; c < ST_MAXCHUNK; ++c)
+                pt[c] = c < a.nchunk ? __ldcg(reinterpret_cast<const float4*>(a.part) + c * plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             if constexpr (P2P) {
+                // Data parallel: the rank's chunk-summed quad goes to every OTHER rank as LL words (data + instance tag in
+                // each 8-byte store: no fence, no flag, no barrier); the peers' quads are polled and everything is added
+                // in rank order, the own quad from registers -- every rank adds the same numbers in the same order.
+                float4 mine = pt[0];
+#pragma unroll
+                for (int c = 1; c < ST_MAXCHUNK; ++c) { mine.x += pt[c].x; mine.y += pt[c].y; mine.z += pt[c].z; mine.w += pt[c].w; }
+                for (int r = 0; r < a.p2p.world; ++r)
+                    if (r != a.p2p.rank) p2p_g_store(p2p_g_ll(a.p2p.peer[r], parity, a.p2p.rank), i, mine, inst + 1u);
                 char* me = a.p2p.peer[a.p2p.rank];
 #pragma unroll
+                for (int c = 0; c < ST_MAXCHUNK; ++c) pt[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
                 for (int c = 0; c < P2P_MAX_WORLD; ++c)
-                    pt[c] = c < a.p2p.world ? __ldcg(reinterpret_cast<const float4*>(p2p_g_slot(me, parity, c)) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int c = P2P_MAX_WORLD; c < ST_MAXCHUNK; ++c) pt[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-#pragma unroll
-                for (int c = 0; c < ST_MAXCHUNK; ++c)
-                    pt[c] = c < a.nchunk ? __ldcg(reinterpret_cast<const float4*>(a.part) + c * plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < a.p2p.world) pt[c] = c == a.p2p.rank ? mine : p2p_g_load(p2p_g_ll(me, parity, c), i, inst + 1u, (a.p2p.skip & 4) != 0);
             }
             const float4 pv = i == i0 ? pv0 : reinterpret_cast<const float4*>(a.W1)[i];
             const float4 vv = i == i0 ? vv0 : reinterpret_cast<const float4*>(a.v + oW1)[i];
@@ -170,7 +161,18 @@ __device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4
     mma_tf32(c, ah, bh);
 }
 
-template <bool P2P>
+static inline size_t step_tail_w2_smem(int rows) { return sizeof(float) * ((size_t)ST2_K8MAX * ST2_SP + (size_t)rows * ST2_LP) + 16; }
+// Embedding rows per W2-role CTA.  Measured on B200 (scripts/dp_time.py, scripts/train_only.py): one GPU runs best with 16
+// fat CTAs on the ~20 SMs the 128-CTA kernels of the main branch leave free (41 us/step); under data parallelism the role
+// also carries the S exchange and must be short, so it runs as 32 / 64 thin CTAs while the main branch's tensor-core
+// kernels ask only for the stage ring they use and pack two to an SM (2 GPUs: 56 vs 62-69 us/step).  DBMM_W2_ROWS overrides.
+static inline int step_tail_w2_rows(bool dp) {
+    static const int env = getenv("DBMM_W2_ROWS") ? atoi(getenv("DBMM_W2_ROWS")) : 0;
+    if (env == 16 || env == 32 || env == 64) return env;
+    return dp ? 32 : 64;
+}
+
+template <bool P2P, int ST2_ROWS>
 __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
     extern __shared__ __align__(16) float st_smem[];
     const int H = a.H, D = a.D, C = a.C;
@@ -190,9 +192,8 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
     const int d0 = w2 * ST2_ROWS;
     const int n4row = NPg >> 2;                 // 16-byte chunks per row of S
     if constexpr (P2P) {
-        // Data parallel: this CTA pushes its slice of the rank's S to every rank (off the critical path: the row kernel
-        // only pushes the LL words of dgamma / dbeta), raises S flag [cta][rank] everywhere, then waits for every slice
-        // of every rank and sums the slots in rank order.
+        // Data parallel: this CTA pushes its slice of the rank's S to every rank (off the critical path), raises S flag
+        // [cta][rank] everywhere, then waits for every slice of every rank and sums the slots in rank order.
         const unsigned inst = p2p_instance(a.p2p);
         const int parity = inst & 1u;
         const int n4 = K * n4row, per = (n4 + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -210,11 +211,11 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
         if (tid < (int)gridDim.x * a.p2p.world) {
             const unsigned* f = p2p_s_flag(a.p2p.peer[a.p2p.rank], tid / a.p2p.world, tid % a.p2p.world);
             unsigned v = 0;
-            for (unsigned spin = 0; spin < (1u << 28); ++spin) {
+            for (unsigned spin = 0; spin < ((a.p2p.skip & 8) ? 1u : (1u << 28)); ++spin) {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
                 if ((int)(v - (inst + 1u)) >= 0) break;
             }
-            if ((int)(v - (inst + 1u)) < 0) __trap();
+            if ((int)(v - (inst + 1u)) < 0 && !(a.p2p.skip & 8)) __trap();
         }
         __syncthreads();
         char* me = a.p2p.peer[a.p2p.rank];
@@ -256,19 +257,20 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
             sL[(size_t)r * LP + k] = v;
         }
     }
-    // ---- dW2a: warp w owns the 16-row tile mt = w & 3 and the 8-column tiles nt = (w >> 2) + 4 j
-    constexpr int NJ = 5;                        // ceil(17 / 4) column tiles per warp at most (N <= 129 -> 17 tiles)
-    const int mt = warp & 3, nt0 = warp >> 2, NT = (N + 7) >> 3;
+    // ---- dW2a: warp w owns the 16-row tile mt = w % MTILES and the 8-column tiles nt = w / MTILES + NGRP j
+    constexpr int MTILES = ST2_ROWS / 16, NGRP = (ST2_THREADS / 32) / MTILES;    // warps per 16-row tile
+    constexpr int NJ = (17 + NGRP - 1) / NGRP;  // column tiles per warp at most (N <= 129 -> 17 tiles)
+    const int mt = warp % MTILES, nt0 = warp / MTILES, NT = (N + 7) >> 3;
     const int r0 = mt * 16 + g;                  // this lane's rows: r0 and r0 + 8
     float2 vv[NJ][2];                            // momentum of the owned elements: requested before the contraction
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        const int n = (nt0 + 4 * j) * 8 + 2 * t;
+        const int n = (nt0 + NGRP * j) * 8 + 2 * t;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             const int d = d0 + r0 + 8 * hh;
             vv[j][hh] = make_float2(0.f, 0.f);
-            if (nt0 + 4 * j < NT && d < D) {
+            if (nt0 + NGRP * j < NT && d < D) {
                 if (n < H) vv[j][hh] = *reinterpret_cast<const float2*>(a.v + oW2 + (size_t)d * H + n);
                 else if (n == H) vv[j][hh].x = a.v[ob2 + d];
             }
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
         tf32_split(sL[(size_t)(r0 + 8) * LP + k0 + t + 4], ah[3], al[3]);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            const int nt = nt0 + 4 * j;
+            const int nt = nt0 + NGRP * j;
             if (nt < NT) {
                 uint32_t bh[2], bl[2];
                 tf32_split(sS[(size_t)(k0 + t) * SP + nt * 8 + g], bh[0], bl[0]);
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
     // SGD on the owned elements (c fragment: rows r0 / r0 + 8, columns n, n + 1); the new values replace the old in sL
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        const int nt = nt0 + 4 * j, n = nt * 8 + 2 * t;
+        const int nt = nt0 + NGRP * j, n = nt * 8 + 2 * t;
         if (nt >= NT) continue;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -372,23 +374,25 @@ static int launch_step_tail(StepTailArgs a, cudaStream_t st) {
     a.roles &= ~skip_roles;
     a.n_w1_ctas = ceil_div((int64_t)a.H * a.D / 4, ST_THREADS);
     if (a.n_w1_ctas > 128) a.n_w1_ctas = 128;
-    a.n_w2_ctas = ceil_div(a.D, ST2_ROWS);
+    const int w2_rows = step_tail_w2_rows(a.p2p.world > 1);
+    a.n_w2_ctas = ceil_div(a.D, w2_rows);
     const bool p2p = a.p2p.world > 1;
-    DBMM_CHECK_ARG(!p2p || (a.n_w1_ctas <= P2P_G_CTAS && a.n_w2_ctas <= P2P_S_CTAS && (size_t)a.H * a.D <= P2P_G_FLOATS &&
+    DBMM_CHECK_ARG(!p2p || (a.n_w2_ctas <= P2P_S_CTAS && (size_t)a.H * a.D <= P2P_G_FLOATS &&
                             (size_t)(a.H + 1 + a.C) * s_stride(a.H) <= P2P_S_FLOATS), "shape exceeds the peer-memory gradient slots");
     if (a.roles & 1) {
         if (p2p) DBMM_CUDA(launch_pdl(k_tail_w1<true>, dim3(a.n_w1_ctas + 1), dim3(ST_THREADS), 0, st, a));
         else DBMM_CUDA(launch_pdl(k_tail_w1<false>, dim3(a.n_w1_ctas + 1), dim3(ST_THREADS), 0, st, a));
     }
     if (a.roles & 2) {
-        const size_t smem = step_tail_smem_bytes(a.H, a.C);
-        if (p2p) {
-            DBMM_CUDA(set_smem(k_tail_w2<true>, smem));
-            k_tail_w2<true><<<a.n_w2_ctas, ST2_THREADS, smem, st>>>(a);
-        } else {
-            DBMM_CUDA(set_smem(k_tail_w2<false>, smem));
-            k_tail_w2<false><<<a.n_w2_ctas, ST2_THREADS, smem, st>>>(a);
-        }
+        const size_t smem = step_tail_w2_smem(w2_rows);
+#define DBMM_W2_LAUNCH(P2P_, ROWS_)                                                         \
+        do {                                                                                \
+            DBMM_CUDA(set_smem(k_tail_w2<P2P_, ROWS_>, smem));                              \
+            k_tail_w2<P2P_, ROWS_><<<a.n_w2_ctas, ST2_THREADS, smem, st>>>(a);              \
+        } while (0)
+        if (p2p) { if (w2_rows == 64) DBMM_W2_LAUNCH(true, 64); else if (w2_rows == 32) DBMM_W2_LAUNCH(true, 32); else DBMM_W2_LAUNCH(true, 16); }
+        else { if (w2_rows == 64) DBMM_W2_LAUNCH(false, 64); else if (w2_rows == 32) DBMM_W2_LAUNCH(false, 32); else DBMM_W2_LAUNCH(false, 16); }
+#undef DBMM_W2_LAUNCH
         DBMM_LAUNCH_CHECK();
     }
     return DBMM_OK;

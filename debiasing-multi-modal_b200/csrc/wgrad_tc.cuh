@@ -35,6 +35,8 @@ struct WgradTcArgs {
     const float* gamma;
     float* part;           // [nchunk][H][D]
     int rows_per_chunk;    // multiple of WG_BK
+    int pack;              // data parallel: request only the used part of the stage ring
+    int stages;            // set by the launcher: min(WG_STAGES, 64-row sub-tiles per chunk)
     P2pArgs p2p; double* dgb_wb;   // data parallel over peer memory: global dgamma / dbeta in (channel 1), written back by CTA (0, 0)
 };
 
@@ -60,9 +62,10 @@ __device__ __forceinline__ uint64_t wg_desc(uint32_t smem_addr) {
 __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     extern __shared__ uint8_t wg_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)wg_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = (uint64_t*)(smem + (size_t)WG_STAGES * WG_STAGE_BYTES);
-    uint64_t* empty = full + WG_STAGES;
-    uint64_t* tmem_full = empty + WG_STAGES;
+    const int NST = a.stages;                   // stage ring depth (1 when the chunk is a single 64-row sub-tile: 97 KB per CTA)
+    uint64_t* full = (uint64_t*)(smem + (size_t)NST * WG_STAGE_BYTES);
+    uint64_t* empty = full + NST;
+    uint64_t* tmem_full = empty + NST;
     uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
     __shared__ float sCst[4][WG_TILE];          // mu, rstd, mean(dahat), mean(dahat*ahat) per hidden unit
 
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     // ---- producer helpers (warps 0-3).  A thread owns 16 chunk ids per 64-row stage: id = tid + 128 * i,
     // row = id / 32 (batch row inside the stage), c16 = id % 32 (16-byte chunk along the 128-float tile edge).
     auto issue_x = [&](int sub) {            // X tile: gathered through the batch's index list, straight into shared memory
-        const uint32_t sX = ptx::smem_u32(smem + (size_t)(sub % WG_STAGES) * WG_STAGE_BYTES) + 2 * WG_OP_BYTES;
+        const uint32_t sX = ptx::smem_u32(smem + (size_t)(sub % NST) * WG_STAGE_BYTES) + 2 * WG_OP_BYTES;
         const int b0 = b_begin + sub * WG_BK;
         int64_t roff[16];
 #pragma unroll
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
         }
     };
     auto store_da = [&](int sub, int half, const float4 (&av)[8], const float4 (&dv)[8]) {
-        uint8_t* stage = smem + (size_t)(sub % WG_STAGES) * WG_STAGE_BYTES;
+        uint8_t* stage = smem + (size_t)(sub % NST) * WG_STAGE_BYTES;
         const int b0 = b_begin + sub * WG_BK;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     float4 av[8], dv[8];
     if (warp < 4) issue_x(0);
     if (tid == 0) {
-        for (int s = 0; s < WG_STAGES; ++s) { ptx::mbar_init(&full[s], 128); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NST; ++s) { ptx::mbar_init(&full[s], 128); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(tmem_full, 1);
         ptx::fence_mbar_init();
     }
@@ -146,7 +149,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     ptx::pdl_wait();                // dahat / dgamma / dbeta come from the row kernel (X, idx are constants)
     ptx::pdl_launch();
     if (warp < 4) load_da(0, 0, av, dv);
-    const int dgb_parity = a.p2p.world ? p2p_wait(a.p2p, 1) : 0;        // every rank's dgamma / dbeta have landed
+    if (a.p2p.world && blockIdx.x == 0 && blockIdx.y == 0) p2p_push_now(a.p2p, 1, a.dgb, 2 * H);     // this rank's sums -> every rank
+    const int dgb_parity = a.p2p.world ? p2p_wait(a.p2p, 1) : 0;
     if (tid < WG_TILE) {
         float mu = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
         if (tid < H) {
@@ -173,9 +177,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     if (warp < 4) {
         // ===================== producers =====================
         for (int sub = 0; sub < n_sub; ++sub) {
-            const int s = sub % WG_STAGES;
+            const int s = sub % NST;
             if (sub > 0) {
-                ptx::mbar_wait(&empty[s], ((sub / WG_STAGES) & 1) ^ 1);
+                ptx::mbar_wait(&empty[s], ((sub / NST) & 1) ^ 1);
                 issue_x(sub);
                 load_da(sub, 0, av, dv);
             }
@@ -210,8 +214,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::umma_idesc(/*tf32*/ 2, WG_TILE, WG_TILE, /*A MN-major*/ 1, /*B MN-major*/ 1);
             for (int sub = 0; sub < n_sub; ++sub) {
-                const int s = sub % WG_STAGES;
-                ptx::mbar_wait(&full[s], (sub / WG_STAGES) & 1);
+                const int s = sub % NST;
+                ptx::mbar_wait(&full[s], (sub / NST) & 1);
                 ptx::tc_fence_after_sync();
                 const uint32_t base = ptx::smem_u32(smem + (size_t)s * WG_STAGE_BYTES);
 #pragma unroll
@@ -245,7 +249,11 @@ static int launch_wgrad_tc(const WgradTcArgs& a, int nchunk, cudaStream_t st) {
     DBMM_CHECK_SHAPE(a.D % WG_TILE == 0 && a.H <= WG_TILE && a.H % 4 == 0, "tensor-core dW1 needs D %% 128 == 0 and H <= 128 (D=%d H=%d)", a.D, a.H);
     DBMM_CUDA(set_smem(k_wgrad_tc, WG_SMEM));
     dim3 grid(a.D / WG_TILE, nchunk);
-    DBMM_CUDA(launch_pdl(k_wgrad_tc, grid, dim3(WG_THREADS), WG_SMEM, st, a));
+    WgradTcArgs b = a;
+    const int n_sub_max = (a.rows_per_chunk + WG_BK - 1) / WG_BK;
+    b.stages = n_sub_max < WG_STAGES ? n_sub_max : WG_STAGES;
+    const size_t smem = train_smem_bytes((size_t)b.stages * WG_STAGE_BYTES + 1024 + 256, WG_SMEM, a.pack);
+    DBMM_CUDA(launch_pdl(k_wgrad_tc, grid, dim3(WG_THREADS), smem, st, b));
     return DBMM_OK;
 }
 
