@@ -93,6 +93,8 @@ SIGNATURES = {
                                            _vp, _f32, _vp, _vp, C.POINTER(C.c_float), _f32, _f32, BatchStats,
                                            _vp, _sz, _vp, C.POINTER(C.c_float)]),
     "dbmm_sgd_step": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _i32, _vp]),
+    "dbmm_export_embeddings": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _AP, _AP, _f32, _i32, _vp, _i32, _vp, _i32, _f32,
+                                         _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dbmm_train_tail_mode": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "dbmm_widen_f16": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
     "dbmm_head_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),

@@ -10,6 +10,7 @@
 #include "wgrad_tc.cuh"
 #include "update.cuh"
 #include "step_tail.cuh"
+#include "export_rows.cuh"
 #include "head_supcon.cuh"
 #include "nccl_dyn.cuh"
 #include "linear_probe.cuh"
@@ -357,6 +358,43 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
         ra.logits_out = logits_out; ra.pred_out = pred_out;
         ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.batch_size = batch_size; ra.slot_fixed = -1;
         if (int rc = launch_rows<false>(ra, nad, H, C, st)) return rc;
+    }
+    return DBMM_OK;
+}
+
+int dbmm_export_embeddings(const float* X, int64_t ldx, const int32_t* idx, int64_t N, int D, int H,
+                           const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight, int normalize_single,
+                           const float* That_a, int Ca, const float* That_b, int Cb, float inv_tau,
+                           float* out, int64_t ld_out, float* logits_a, float* logits_b,
+                           void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_dims(D, H, 1, 1)) return rc;
+    if (int rc = check_adapter(ad, "export")) return rc;
+    if (old_ad) if (int rc = check_adapter(old_ad, "old")) return rc;
+    DBMM_CHECK_ARG(N >= 0, "negative row count %lld", (long long)N);
+    if (N == 0) return DBMM_OK;
+    DBMM_CHECK_ARG(X && out && ws && ldx >= D && ld_out >= D, "bad export arguments (N=%lld)", (long long)N);
+    DBMM_CHECK_ARG((!logits_a || (That_a && Ca >= 1 && Ca <= DBMM_MAX_C)) && (!logits_b || (That_b && Cb >= 1 && Cb <= DBMM_MAX_C)),
+                   "logits requested without a prompt matrix");
+    if (N == 0) return DBMM_OK;
+    const int nad = old_ad ? 2 : 1;
+    DBMM_CHECK_ARG(dbmm_workspace_bytes(DBMM_OP_EVAL, N, D, H, 1, nad) <= ws_bytes, "workspace too small");
+    // same carve-up as the SIMT evaluation path: [gram area (unused)] [A] [whi] [wlo]
+    float* A = (float*)((char*)ws + align_up(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + 1), 256));
+    const int64_t chunk_rows = N < EVAL_CHUNK ? N : EVAL_CHUNK;
+    float* whi = (float*)((char*)A + align_up(sizeof(float) * (size_t)nad * chunk_rows * H, 256));
+    float* wlo = (float*)((char*)whi + align_up(sizeof(float) * (size_t)nad * H * D, 256));
+    for (int64_t pos0 = 0; pos0 < N; pos0 += EVAL_CHUNK) {
+        const int B = (int)((N - pos0) < EVAL_CHUNK ? (N - pos0) : EVAL_CHUNK);
+        if (int rc = launch_gemm1(X, ldx, idx, pos0, B, D, H, old_ad, ad, A, nullptr, whi, wlo, pos0 == 0, 1, nullptr, st)) return rc;
+        ExportArgs ea;
+        memset(&ea, 0, sizeof(ea));
+        ea.B = B; ea.D = D; ea.H = H; ea.nad = nad; ea.A = A; ea.strideA = (int64_t)B * H;
+        ea.ad[0] = view_of(old_ad ? old_ad : ad); ea.ad[1] = view_of(ad);
+        ea.w_old = ebd_weight; ea.normalize_single = normalize_single;
+        ea.That_a = That_a; ea.Ca = Ca; ea.That_b = That_b; ea.Cb = Cb; ea.inv_tau = inv_tau;
+        ea.out = out; ea.ld_out = ld_out; ea.pos0 = pos0; ea.logits_a = logits_a; ea.logits_b = logits_b;
+        if (int rc = launch_export_rows(ea, st)) return rc;
     }
     return DBMM_OK;
 }

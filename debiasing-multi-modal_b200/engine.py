@@ -205,6 +205,46 @@ def validate(opt, val_loader, classifier, criterion, get_yp_func, train_group_ra
     return losses.avg, acc.avg, group_acc
 
 
+def validate_adapter_with_return(opt, val_loader, classifier, criterion, get_yp_func, train_group_ratio, target, print_label='Test'):
+    """Validation that also returns the adapted embeddings for the visualisation notebooks
+    (demo/demo_visualization.ipynb:1117-1215): same return value,
+        (None, acc.avg, group_acc), (total_embeddings [N, D] numpy, {"targets", "spuriouss", "groups", "predictions",
+                                                                     "predictions_spurious"})
+    with the notebook's scoring rule -- logits = features @ That / temperature on the EXPORTED features, which for
+    tl_method == "adapter" are the un-normalised adapter outputs (unlike validate())."""
+    if "adapter" not in opt.tl_method:
+        raise AssertionError("validate_adapter_with_return is defined for the adapter methods")
+    classifier.eval()
+    base, rows = val_loader.base_rows(val_loader.draw_order())
+    n, bs = len(rows), val_loader.batch_size
+    sizes = _batch_sizes(n, bs)
+    contiguous = len(rows) == len(base) and np.array_equal(rows, np.arange(len(base)))
+    idx = None if contiguous else _order_to_device(base, rows)
+    old, ad, w = classifier.kernel_adapters()
+    if opt.tl_method == "adapter":
+        old = None
+    feats, logits, logits_sp = ops.export_embeddings(base.x, ad, old_ad=old, ebd_weight=w, That_a=classifier.prompt_matrix(),
+                                                     That_b=classifier.prompt_matrix(spurious=True),
+                                                     inv_tau=1.0 / classifier.temperature, idx=idx, n_rows=n)
+
+    def visit(t):
+        return t if idx is None else t.index_select(0, idx.long())
+    y_t, g_t, p_t = visit(base.labels[target]), visit(base.labels["group"]), visit(base.labels["spurious"])
+    stats = _stats_buffers(len(sizes), base.n_groups, base.device, "export")
+    stats.zero_()
+    pred = ops.group_counts(logits, y_t, g_t, stats, bs, G=base.n_groups, want_pred=True)
+    scratch = _stats_buffers(len(sizes), base.n_groups, base.device, "export_sp")
+    pred_sp = ops.group_counts(logits_sp, p_t, g_t, scratch, bs, G=base.n_groups, want_pred=True)
+    loss_sum, counts = stats.host()
+    _, acc, acc_groups = replay_epoch(loss_sum, counts, sizes, base.n_groups)
+    group_acc = eval_group_acc(acc_groups, get_yp_func, train_group_ratio)
+    print(f"{print_label}:", str(group_acc))
+    meta = {"targets": list(y_t.cpu().numpy().astype(np.int64)), "spuriouss": list(p_t.cpu().numpy().astype(np.int64)),
+            "groups": list(g_t.cpu().numpy().astype(np.int64)), "predictions": list(pred.cpu().numpy().astype(np.int64)),
+            "predictions_spurious": list(pred_sp.cpu().numpy().astype(np.int64))}
+    return (None, acc.avg, group_acc), (feats.cpu().numpy(), meta)
+
+
 def validate_zs(opt, val_loader, classifier, criterion, get_yp_func, train_group_ratio, target,
                 print_label='Zero-shot Prediction (Test) (Class)'):
     """Feature-quality check with class or spurious prompts (final_main.py:725-803)."""

@@ -288,6 +288,29 @@ def sgd_step(p: torch.Tensor, g: torch.Tensor, v: torch.Tensor, lr, momentum=0.9
                                  1 if first_step else 0, _stream_ptr()))
 
 
+def export_embeddings(X: torch.Tensor, ad: AdapterTensors, *, old_ad=None, ebd_weight=0.5, normalize_single=False,
+                      That_a=None, That_b=None, inv_tau=100.0, idx=None, n_rows=None):
+    """Adapted embeddings [N, D] (+ logits against up to two prompt matrices) as validate_adapter_with_return forms them
+    (demo/demo_visualization.ipynb:1117-1215): single adapter -> the un-normalised adapter output; with `old_ad` -> the
+    MultipleAdapter mix of the two normalised outputs.  Returns (features, logits_a | None, logits_b | None)."""
+    lib = _lib.load()
+    _check(X, torch.float32, "X", contiguous=False)
+    D, H = X.shape[1], ad.H
+    N = int(n_rows if n_rows is not None else (idx.numel() if idx is not None else X.shape[0]))
+    out = torch.empty((N, D), dtype=torch.float32, device=X.device)
+    la = torch.empty((N, That_a.shape[1]), dtype=torch.float32, device=X.device) if That_a is not None else None
+    lb = torch.empty((N, That_b.shape[1]), dtype=torch.float32, device=X.device) if That_b is not None else None
+    nad = 2 if old_ad is not None else 1
+    ws = workspace(lib.dbmm_workspace_bytes(_lib.OP_EVAL, max(N, 1), D, H, 1, nad), X.device)
+    old_p = old_ad.ptrs() if old_ad is not None else None
+    _lib.check(lib.dbmm_export_embeddings(X.data_ptr(), X.stride(0), _ptr(idx), N, D, H,
+                                          C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()), ebd_weight,
+                                          1 if normalize_single else 0, _ptr(That_a), That_a.shape[1] if That_a is not None else 0,
+                                          _ptr(That_b), That_b.shape[1] if That_b is not None else 0, inv_tau,
+                                          out.data_ptr(), out.stride(0), _ptr(la), _ptr(lb), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return out, la, lb
+
+
 def widen_f16(src: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """fp16 rows [N, D] on the device -> fp32 rows (exact): the ingest step behind the fp16 packed store (pack.py)."""
     lib = _lib.load()

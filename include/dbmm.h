@@ -12,6 +12,7 @@
  *                         demo/util.py:118-136      optim.SGD (momentum 0.9, weight decay)
  *   dbmm_train_epoch      final_main.py:426-496, 571-653   the per-batch loop of one epoch
  *   dbmm_sgd_step         demo/util.py:118-136      SGD on a flat buffer (data-parallel path)
+ *   dbmm_export_embeddings  demo/demo_visualization.ipynb:1117-1215  validate_adapter_with_return (features for the notebooks)
  *   dbmm_widen_f16        data/waterbirds_embeddings.py:69-78  embeddings -> float32 tensors (ingest, fp16 store)
  *   dbmm_group_counts     final_main.py:383-391     update_dict on given logits
  *   dbmm_logits_ce        final_main.py:757-759,768 raw-embedding cosine logits + CE (zero-shot head)
@@ -208,6 +209,16 @@ int dbmm_train_epoch_profile(const float* X, int64_t ldx, const int32_t* order, 
                              const float* That, float inv_tau, float* grads, float* momentum_buf, const float* lr_host,
                              float momentum, float weight_decay, dbmm_batch_stats stats,
                              void* ws, size_t ws_bytes, void* stream, float* kernel_us_host);
+
+/* Adapted-embedding export for the visualisation notebooks (validate_adapter_with_return, demo/demo_visualization.ipynb:
+ * 1117-1215): out[N, D] = the UN-normalised adapter output (single adapter; normalize_single != 0: L2-normalised rows) or
+ * the MultipleAdapter mix w * u_old + (1 - w) * u_new; optionally the notebook's logits = out @ That / tau for two prompt
+ * sets (class, spurious; That column-normalised [D, C]).  Eval mode (running statistics).  Workspace: DBMM_OP_EVAL. */
+int dbmm_export_embeddings(const float* X, int64_t ldx, const int32_t* idx, int64_t N, int D, int H,
+                           const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight, int normalize_single,
+                           const float* That_a, int Ca, const float* That_b, int Cb, float inv_tau,
+                           float* out, int64_t ld_out, float* logits_a, float* logits_b,
+                           void* ws, size_t ws_bytes, void* stream);
 
 /* How single-GPU epochs of this shape run the tail of a step: 0 = k_finalize_grads + k_update, 1 = fused step tail
  * (k_tail_w1, k_tail_w2) in line, 2 = fused with the W2 role on a second branch of the epoch graph (default when every

@@ -199,6 +199,17 @@ def eval_logits(X, p, That, tau, p_new=None, w=0.5, dtype=np.float32):
     return multiple_adapter_logits(X, p, p_new, That, tau, False, w, dtype)[0]
 
 
+def export_features(X, p, p_new=None, w=0.5, dtype=np.float32):
+    """validate_adapter_with_return (demo/demo_visualization.ipynb:1117-1215): the adapted embeddings handed to the
+    visualisation notebooks.  tl_method == "adapter": the UN-normalised adapter output `classifier.adapter(x)`; otherwise
+    the MultipleAdapter mix `w * u_old + (1 - w) * u_new` of the two L2-normalised outputs (not re-normalised).  The
+    notebook scores these features directly: logits = features @ That / tau (class and spurious prompts)."""
+    if p_new is None:
+        return adapter_forward(X, p, False, dtype)["z"]
+    fo, fn = adapter_forward(X, p, False, dtype), adapter_forward(X, p_new, False, dtype)
+    return dtype(w) * fo["u"] + dtype(1 - w) * fn["u"]
+
+
 # ----------------------------------------------------------------------------------------------
 # group metrics (final_main.py:383-412, demo/util.py:18-46)
 # ----------------------------------------------------------------------------------------------

@@ -1,7 +1,7 @@
 """ORACLE (test infrastructure).  Generates tests/golden/* by running the UNMODIFIED reference
 (/root/reference, imported through oracle/reference_shim.py) on the seeded cases of oracle/cases.py.
 
-Run in the build container only:   python -m oracle.make_golden [--only kernels|metrics|schedule|sampling|e2e|supcon]
+Run in the build container only:   python -m oracle.make_golden [--only kernels|metrics|schedule|sampling|e2e|supcon|export]
 
 The fixtures pin (a) the numpy oracle port and (b) the CUDA path to the reference's own PyTorch
 arithmetic: Adapter/CustomCLIP/MultipleAdapter + nn.CrossEntropyLoss + optim.SGD (final_main.py:53-174,
@@ -284,6 +284,52 @@ def gen_supcon(fm, ru):
     print("supcon_cases.json:", {k: v["loss"] for k, v in out.items()})
 
 
+def gen_export(fm, ru):
+    """Adapted-embedding export (demo/demo_visualization.ipynb:1117-1215, validate_adapter_with_return): its feature lines
+    run on the reference's own modules in eval mode.  The notebook cannot be imported, so the three statements that form
+    `image_features` and the two logit lines are executed here verbatim on final_main's classes."""
+    out = {}
+    tmp = tempfile.mkdtemp(prefix="dbmm_gold_")
+    for name in ("tiny_b33", "vitl_b256"):
+        c = cases.make_case(name)
+        D, H = c["D"], c["H"]
+        tc, ts, tg = (os.path.join(tmp, f"{name}_{k}.json") for k in ("class", "spurious", "group"))
+        _write_text_json(tc, c["T_class"]); _write_text_json(ts, c["T_spurious"]); _write_text_json(tg, c["T_group"])
+        clf = fm.CustomCLIP(fm.Adapter(D, H), tc, ts, tg, temperature=0.01)
+        _load_into(clf.adapter, c["p_old"])
+        new_ad = fm.Adapter(D, H)
+        _load_into(new_ad, c["p_new"])
+        ma = fm.MultipleAdapter(clf, new_ad, init_near_identity=False, ebd_weight=0.5)
+        rng = np.random.default_rng(5)
+        for ad in (clf.adapter, new_ad):                      # non-trivial running statistics
+            bn = ad.layers[1]
+            bn.running_mean.copy_(torch.from_numpy(rng.standard_normal(H).astype(np.float32) * 0.3))
+            bn.running_var.copy_(torch.from_numpy((0.5 + rng.random(H)).astype(np.float32)))
+        out[f"{name}/running"] = np.stack([clf.adapter.layers[1].running_mean.numpy(), clf.adapter.layers[1].running_var.numpy(),
+                                           new_ad.layers[1].running_mean.numpy(), new_ad.layers[1].running_var.numpy()])
+        clf.eval(); ma.eval()
+        with torch.no_grad():
+            embeddings = torch.from_numpy(c["Xe"][:96])
+            for tag, classifier, single in (("adapter", clf, True), ("multi", ma, False)):
+                if single:
+                    image_features = classifier.adapter(embeddings)
+                else:
+                    old_image_features = classifier.old_cls.adapter(embeddings)
+                    old_image_features = old_image_features / old_image_features.norm(dim=-1, keepdim=True)
+                    new_image_features = classifier.new_adapter(embeddings)
+                    new_image_features = new_image_features / new_image_features.norm(dim=-1, keepdim=True)
+                    image_features = classifier.ebd_weight * old_image_features + (1 - classifier.ebd_weight) * new_image_features
+                text_features_normalized = classifier.text_features / classifier.text_features.norm(dim=0, keepdim=True)
+                logits = image_features @ text_features_normalized / classifier.temperature
+                tsn = classifier.text_spurious_features / classifier.text_spurious_features.norm(dim=0, keepdim=True)
+                logits_spurious = image_features @ tsn / classifier.temperature
+                out[f"{name}/{tag}/features"] = image_features.numpy().copy()
+                out[f"{name}/{tag}/logits"] = logits.numpy().copy()
+                out[f"{name}/{tag}/logits_spurious"] = logits_spurious.numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, "export_cases.npz"), **out)
+    print("export_cases.npz:", len(out), "arrays")
+
+
 def gen_checkpoint_layout(fm, ru):
     path = [p for p in os.listdir("/root/reference/trained_model") if p.endswith(".pth")][0]
     sd = torch.load(os.path.join("/root/reference/trained_model", path), map_location="cpu")
@@ -392,7 +438,7 @@ def main():
     fm, ru = import_reference()
     torch.set_num_threads(8)
     todo = dict(kernels=gen_kernels, metrics=gen_metrics, schedule=gen_schedule, sampling=gen_sampling,
-                supcon=gen_supcon, layout=gen_checkpoint_layout, e2e=gen_e2e)
+                supcon=gen_supcon, layout=gen_checkpoint_layout, e2e=gen_e2e, export=gen_export)
     for k, fn in todo.items():
         if a.only in ("all", k):
             fn(fm, ru)

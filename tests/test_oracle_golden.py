@@ -183,3 +183,23 @@ def test_supcon_vectorised_matches_loop_and_autograd():
         losses.append((-lp).mean())
     torch.stack(losses).mean().backward()
     np.testing.assert_allclose(r["dZ"], Zt.grad.numpy(), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["tiny_b33", "vitl_b256"])
+def test_export_features_match_reference_modules(golden_dir, name):
+    """validate_adapter_with_return's feature / logit lines (demo/demo_visualization.ipynb:1117-1215) executed on the
+    reference's modules (oracle/make_golden.py::gen_export) vs the oracle restatement."""
+    gold = np.load(os.path.join(golden_dir, "export_cases.npz"))
+    c = cases.make_case(name)
+    run = gold[f"{name}/running"]
+    p_old, p_new = am.copy_params(c["p_old"]), am.copy_params(c["p_new"])
+    p_old["running_mean"], p_old["running_var"], p_new["running_mean"], p_new["running_var"] = run[0], run[1], run[2], run[3]
+    X = c["Xe"][:96]
+    Tc, Ts = am.normalize_text(c["T_class"]), am.normalize_text(c["T_spurious"])
+    for tag, feats in (("adapter", am.export_features(X, p_old)), ("multi", am.export_features(X, p_old, p_new, 0.5))):
+        ref = gold[f"{name}/{tag}/features"]
+        assert np.abs(feats - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-6
+        for key, T in (("logits", Tc), ("logits_spurious", Ts)):
+            rl = gold[f"{name}/{tag}/{key}"]
+            ol = feats @ T / np.float32(0.01)
+            assert np.abs(ol - rl).max() <= 1e-3 * np.abs(rl).max() + 1e-3
