@@ -30,7 +30,10 @@ void set_error(const char* fmt, ...) {
 }
 
 constexpr int64_t EVAL_CHUNK = 16384;
-constexpr int64_t EVAL_TC_CHUNK = 32768;       // rows per pass of the tensor-core eval path: its h tiles (32 MB) stay in L2
+// rows per pass of the tensor-core eval path: whole waves of 128-row tiles on 148 SMs, as many as keep the pass's h tiles
+// (1 KB per row and adapter) inside the 126 MB L2: 5 waves (97 MB) for one adapter, 2 waves (2 x 39 MB) for two.
+// Measured, 162,770 rows, one adapter: 32,768-row passes 0.597 ms, 2 waves 0.554, 3 waves 0.509, 5 waves 0.486.
+constexpr int64_t EVAL_TC_CHUNK = 148 * 640, EVAL_TC_CHUNK2 = 148 * 256;
 constexpr int EVAL_TAIL_LD = 32;
 
 struct EvalTcWs { float *gram, *whi, *wlo, *hhi, *hlo, *rowdot, *tail, *bthi, *btlo, *bias; int64_t chunk; size_t total; };
@@ -38,7 +41,9 @@ static EvalTcWs carve_eval_tc_ws(void* base, int64_t N, int D, int H, int C, int
     EvalTcWs w; char* p = (char*)base; size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
     const int ldg = H + 1 + C;
-    w.chunk = N < EVAL_TC_CHUNK ? N : EVAL_TC_CHUNK;
+    static const int64_t chunk_env = getenv("DBMM_EVAL_CHUNK") ? atoll(getenv("DBMM_EVAL_CHUNK")) : 0;     // timing experiments
+    const int64_t chunk_max = chunk_env >= 128 ? chunk_env : (nad == 1 ? EVAL_TC_CHUNK : EVAL_TC_CHUNK2);
+    w.chunk = N < chunk_max ? N : chunk_max;
     const size_t o1 = take(sizeof(float) * (size_t)nad * (H + 1) * ldg), o2 = take(sizeof(float) * (size_t)nad * H * D),
                  o3 = take(sizeof(float) * (size_t)nad * H * D), o4 = take(sizeof(float) * (size_t)nad * w.chunk * H),
                  o5 = take(sizeof(float) * (size_t)nad * w.chunk * H), o6 = take(sizeof(float) * (size_t)nad * w.chunk),
