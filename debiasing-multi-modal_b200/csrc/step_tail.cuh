@@ -1,19 +1,19 @@
-// Fused tail of a single-GPU training step: gradient finalisation AND optimizer step in one kernel, split into two
-// roles that the epoch graph launches on two streams so that the W2 half overlaps the tensor-core dW1 GEMM.
+// Fused tail of a training step: gradient finalisation AND optimizer step AND the next step's operands, as two kernels
+// that the epoch graph launches on two branches so that the W2 half leaves the critical path.
 //
-//   role bit 0 (after k_wgrad_tc):  dW1 = sum of the batch-chunk partial tiles -> SGD on W1 -> tf32 split of the new W1
-//                                   (everything elementwise: one pass, 16 partial loads + p + v in flight per thread)
-//   role bit 1 (after k_rows_train, concurrent with k_wgrad_tc):
-//       W2 CTAs (32 embedding rows each, 512 threads, 104 KB of shared memory: they fit on an SM BESIDE a CTA of the
-//       main branch's tensor-core kernels, whose training launches ask for a 2-deep / 1-deep stage ring = 97 KB): dW2a = [W2 | b2 | That] S -> SGD on W2 / b2 -> the slice's share of NEXT step's
-//       Gram matrix G = [W2 | b2]^T [W2 | b2 | That] (coalesced fp32 reds into the other half of a double buffer; this
-//       step's half, consumed by k_rows_train, is re-zeroed here).
-//   One more CTA of role bit 0 (k_wgrad_tc reads gamma): dgamma / dbeta / db1 -> SGD on b1 / gamma / beta, BatchNorm
+//   k_tail_w1 (main branch, after k_wgrad_tc):  dW1 = sum of the batch-chunk partial tiles -> SGD on W1 -> tf32 split of
+//       the new W1 (everything elementwise: one pass, 16 partial loads + p + v in flight per thread).  One more CTA
+//       ("chores": k_wgrad_tc reads gamma, so not earlier): dgamma / dbeta / db1 -> SGD on b1 / gamma / beta, BatchNorm
 //       running statistics (final_main.py:122,574: the frozen adapter drifts too).
+//   k_tail_w2 (second branch: forked after k_rows_train, joined before the NEXT step's k_rows_train):
+//       per CTA 64 / 32 / 16 embedding rows: dW2a = [W2 | b2 | That] S -> SGD on W2 / b2 -> the rows' share of the next
+//       Gram matrix G = [W2 | b2]^T [W2 | b2 | That] (fp32 reds into the other half of a double buffer; this step's half,
+//       consumed by k_rows_train, is re-zeroed here).
 // The per-step accumulators are re-zeroed by the NEXT step's head kernels (column sums: k_gemm1_tc; dgamma / dbeta and S:
-// k_reduce_stats), never here: k_wgrad_tc reads them concurrently.  SGD as torch.optim.SGD (demo/util.py:118-136):
-// g += wd*p; v = momentum*v + g; p -= lr*v (the caller zeroes v before the optimizer's first step, which makes v = g).
-// Data-parallel epochs keep k_finalize_grads + k_update (the gradient all-reduce sits between them).
+// k_reduce_stats), never here: k_wgrad_tc reads them while the W2 branch runs.  SGD as torch.optim.SGD
+// (demo/util.py:118-136): g += wd*p; v = momentum*v + g; p -= lr*v (the caller zeroes v before the optimizer's first
+// step, which makes v = g).  Data parallel (template P2P): the dW1 quads and S are summed over the ranks through peer
+// memory inside these kernels (p2p.cuh) -- there is no gradient all-reduce kernel.
 #pragma once
 #include "common.cuh"
 #include "ptx_sm100.cuh"
