@@ -152,3 +152,53 @@ class DataParallelTrainer:
         if self.world > 1:
             self._all_reduce(stats.loss_sum)
             self._all_reduce(stats.counts)
+
+
+def supcon_distributed(Z_local: torch.Tensor, labels_local: torch.Tensor, *, tau_cl=0.1, group=None, compute=None):
+    """Contrastive regulariser with GLOBAL negatives (BASELINE config 3): every rank holds B / world
+    L2-normalised rows; the rows and labels are all-gathered, each rank scores ITS anchors against the whole batch
+    (dbmm_supcon_fwd on the tcgen05 GEMM), loss sum and valid-anchor count are all-reduced, the backward produces the
+    anchor-role gradient of the local rows and the contrast-role gradient of ALL rows, and the latter is reduce-scattered
+    back to the owners.  Returns (mean loss over the global batch, dZ_local [B_local, d]).
+
+    Equal shard sizes are required (all_gather_into_tensor); `compute` = (fwd, bwd) is the injection point for the gloo
+    test, where the oracle stands in for the kernels (the product has no CPU path):
+        fwd(Z_all, labels_all, row0, n_local) -> (loss_sum: float, n_valid: int, ctx)
+        bwd(Z_all, ctx, row0, n_local, n_valid_global) -> (dZ_local [n_local, d], dZ_all [B, d])"""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    Bl, d = Z_local.shape
+    if world > 1:
+        Z_all = torch.empty((world * Bl, d), dtype=Z_local.dtype, device=Z_local.device)
+        labels_all = torch.empty((world * Bl,), dtype=labels_local.dtype, device=labels_local.device)
+        dist.all_gather_into_tensor(Z_all, Z_local.contiguous(), group=group)
+        dist.all_gather_into_tensor(labels_all, labels_local.contiguous(), group=group)
+    else:
+        Z_all, labels_all = Z_local.contiguous(), labels_local.contiguous()
+    row0 = rank * Bl
+    if compute is None:
+        state = ops.SupconState(device=Z_local.device)
+
+        def fwd(Za, la, r0, nl):
+            ops.supcon_fwd(Za, la, state, row0=r0, n_local=nl, tau_cl=tau_cl)
+            return state.loss_sum, state.n_valid, None
+
+        def bwd(Za, ctx, r0, nl, n_valid_global):
+            state.n_valid.copy_(n_valid_global)
+            return ops.supcon_bwd(Za, state, row0=r0, n_local=nl, tau_cl=tau_cl)
+    else:
+        fwd, bwd = compute
+    loss_sum, n_valid, ctx = fwd(Z_all, labels_all, row0, Bl)
+    red = torch.stack([torch.as_tensor(loss_sum, dtype=torch.float64, device=Z_local.device).reshape(()),
+                       torch.as_tensor(n_valid, device=Z_local.device).to(torch.float64).reshape(())])
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.SUM, group=group)
+    n_valid_global = red[1].to(torch.int32).reshape(1)
+    dZ_local, dZ_all = bwd(Z_all, ctx, row0, Bl, n_valid_global)
+    if world > 1:
+        mine = torch.empty_like(dZ_local)
+        dist.reduce_scatter_tensor(mine, dZ_all.contiguous(), op=dist.ReduceOp.SUM, group=group)
+        dZ_local = dZ_local + mine
+    else:
+        dZ_local = dZ_local + dZ_all
+    return float(red[0].item() / max(float(red[1].item()), 1.0)), dZ_local

@@ -173,3 +173,78 @@ def test_two_rank_gloo_epoch_equals_single_process_oracle():
     assert int(res["p"]["num_batches_tracked"]) == 3
     np.testing.assert_allclose(res["loss"], loss, rtol=1e-10)
     assert np.array_equal(res["counts"], np.stack(counts))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# contrastive regulariser with all-gathered negatives (BASELINE config 3): gather / all-reduce / reduce-scatter protocol
+# ---------------------------------------------------------------------------------------------------------------------
+def _supcon_problem():
+    rng = np.random.default_rng(4)
+    B, d = 48, 16
+    Z = rng.standard_normal((B, d))
+    Z /= np.linalg.norm(Z, axis=1, keepdims=True)
+    return Z, rng.integers(0, 3, B)
+
+
+def _oracle_supcon_compute():
+    """(fwd, bwd) with the oracle's arithmetic: this rank's anchors against the gathered batch."""
+    def parts(Z, labels, r0, nl):
+        Z = Z.numpy().astype(np.float64); labels = labels.numpy()
+        B = len(Z)
+        S = Z[r0:r0 + nl] @ Z.T / 0.1
+        rows = np.arange(r0, r0 + nl)
+        self_mask = rows[:, None] == np.arange(B)[None, :]
+        same = (labels[rows][:, None] == labels[None, :]) & ~self_mask
+        valid = (same.sum(1) > 0) & ((labels[rows][:, None] != labels[None, :]).sum(1) > 0)
+        Sm = np.where(self_mask, -np.inf, S)
+        mx = Sm.max(1, keepdims=True)
+        E = np.exp(Sm - mx)
+        lse = np.log(E.sum(1)) + mx[:, 0]
+        loss = lse - (np.where(same, S, 0).sum(1) / np.maximum(same.sum(1), 1))
+        Gm = E / E.sum(1, keepdims=True) - same / np.maximum(same.sum(1), 1)[:, None]
+        Gm[~valid] = 0
+        return float(loss[valid].sum()), int(valid.sum()), (Z, Gm)
+
+    def fwd(Z_all, labels_all, r0, nl):
+        return parts(Z_all, labels_all, r0, nl)
+
+    def bwd(Z_all, ctx, r0, nl, n_valid_global):
+        Z, Gm = ctx
+        scale = 1.0 / (0.1 * float(n_valid_global.item()))
+        return torch.from_numpy(Gm @ Z * scale), torch.from_numpy(Gm.T @ Z[r0:r0 + nl] * scale)
+    return fwd, bwd
+
+
+def _supcon_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import dbmm
+    from dbmm import parallel
+    Z, labels = _supcon_problem()
+    Bl = len(Z) // world
+    loss, dZ = parallel.supcon_distributed(torch.from_numpy(Z[rank * Bl:(rank + 1) * Bl]), torch.from_numpy(labels[rank * Bl:(rank + 1) * Bl]),
+                                           compute=_oracle_supcon_compute())
+    out.put((rank, loss, dZ.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_supcon_equals_single_process_oracle():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_supcon_worker, args=(r, 2, port, out)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    got = dict()
+    for _ in range(2):
+        r, loss, dZ = out.get(timeout=240)
+        got[r] = (loss, dZ)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    Z, labels = _supcon_problem()
+    ref = am.supcon_all_anchors_grad(Z, labels, 0.1)
+    assert got[0][0] == pytest.approx(ref["loss"], rel=1e-10) and got[1][0] == pytest.approx(ref["loss"], rel=1e-10)
+    np.testing.assert_allclose(np.concatenate([got[0][1], got[1][1]]), ref["dZ"], rtol=1e-9, atol=1e-12)
