@@ -546,7 +546,7 @@ static int train_step_impl(int phases, bool fresh,
         ua.whi = tc1 ? w.whi + (size_t)(nad - 1) * H * D : nullptr; ua.wlo = tc1 ? w.wlo + (size_t)(nad - 1) * H * D : nullptr;
         ua.That = That; ua.gram = gram_t;
         ua.D = D; ua.H = H; ua.C = C; ua.nad = nad; ua.Bg = B_global;
-        ua.colsum = w.colsum; ua.dgb = w.dgb; ua.S = w.S; ua.zero_accum = 3;
+        ua.colsum = w.colsum; ua.dgb = w.dgb; ua.S = w.S; ua.zero_accum = 1;
         const dbmm_adapter* a0 = old_ad ? old_ad : ad;
         ua.rm[0] = a0->running_mean; ua.rv[0] = a0->running_var; ua.nbt[0] = (long long*)a0->num_batches_tracked;
         ua.rm[1] = ad->running_mean; ua.rv[1] = ad->running_var; ua.nbt[1] = (long long*)ad->num_batches_tracked;

@@ -26,7 +26,6 @@ struct UpdateArgs {
     int zero_accum;
     float* rm[2]; float* rv[2]; long long* nbt[2];
     int n_w1_ctas, n_w2_ctas;
-    int roles;                                // bit 0: W1 (+ tf32 split); bit 1: W2 / b2 (+ Gram), b1 / gamma / beta, running stats, resets
 };
 
 static inline size_t update_smem_bytes(int H, int C) { return sizeof(float) * (size_t)UP_ROWS * ((H + 1 + C + 3) & ~3) + 16; }
@@ -37,7 +36,7 @@ __global__ void __launch_bounds__(UP_THREADS) k_update(UpdateArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float lr = a.lr_dev ? __ldg(a.lr_dev) : a.lr;
     const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
-    const int bid = (int)blockIdx.x + ((a.roles & 1) ? 0 : a.n_w1_ctas);          // W2-only launch: skip the W1 CTAs
+    const int bid = blockIdx.x;
     ptx::pdl_wait();                // the flat gradient comes from k_finalize_grads
     ptx::pdl_launch();
 
@@ -184,14 +183,11 @@ __global__ void __launch_bounds__(UP_THREADS) k_update(UpdateArgs a) {
         }
         if (tid < a.nad) *a.nbt[tid] += 1;
     }
-    if (a.zero_accum) {                      // bit 0: S; bit 1: column sums and (dgamma, dbeta) (not when dW1 runs concurrently)
+    if (a.zero_accum) {
         __syncthreads();
-        if (a.zero_accum & 2) {
-            for (int e = tid; e < a.nad * 2 * H; e += UP_THREADS) a.colsum[e] = 0.0;
-            for (int e = tid; e < 2 * H; e += UP_THREADS) a.dgb[e] = 0.0;
-        }
-        if (a.zero_accum & 1)
-            for (int e = tid; e < (H + 1 + C) * s_stride(H); e += UP_THREADS) a.S[e] = 0.f;
+        for (int e = tid; e < a.nad * 2 * H; e += UP_THREADS) a.colsum[e] = 0.0;
+        for (int e = tid; e < 2 * H; e += UP_THREADS) a.dgb[e] = 0.0;
+        for (int e = tid; e < (H + 1 + C) * s_stride(H); e += UP_THREADS) a.S[e] = 0.f;
     }
 }
 
@@ -201,9 +197,7 @@ static int launch_update(UpdateArgs a, cudaStream_t st) {
     DBMM_CUDA(set_smem(k_update, smem));
     a.n_w1_ctas = 64;
     a.n_w2_ctas = ceil_div(a.D, UP_ROWS);
-    if (!a.roles) a.roles = 3;
-    const int grid = ((a.roles & 1) ? a.n_w1_ctas : 0) + ((a.roles & 2) ? a.n_w2_ctas + 1 : 0);
-    DBMM_CUDA(launch_pdl(k_update, dim3(grid), dim3(UP_THREADS), smem, st, a));
+    DBMM_CUDA(launch_pdl(k_update, dim3(a.n_w1_ctas + a.n_w2_ctas + 1), dim3(UP_THREADS), smem, st, a));
     return DBMM_OK;
 }
 

@@ -267,7 +267,6 @@ struct FinalizeArgs {
     float* gW1; float* gb1; float* ggamma; float* gbeta; float* gW2; float* gb2;
     int D, H, C;
     int n_w1_ctas;
-    int roles;             // bit 0: dW1 chunk sums; bit 1: dW2a tiles, dgamma / dbeta / db1, Gram reset (two launches on two streams overlap them)
     float gb_scale;        // B_local / B_global: dgb holds GLOBAL sums under data parallelism, the flat gradient is summed over ranks
     float* gram_zero; int gram_floats;     // Gram matrix of the trainable adapter: consumed by the row kernel, re-accumulated by k_update
 };
@@ -284,15 +283,14 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) 
     extern __shared__ __align__(16) float fin_smem[];
     const int H = a.H, C = a.C, D = a.D, K = H + 1 + C, N = H + 1;
     const int tid = threadIdx.x;
-    const int bid = (int)blockIdx.x + ((a.roles & 1) ? 0 : a.n_w1_ctas);        // W2-only launch: skip the dW1 CTAs
-    if (bid < a.n_w1_ctas) {
+    if ((int)blockIdx.x < a.n_w1_ctas) {
         ptx::pdl_wait();            // the chunk partials come from k_wgrad_tc
         ptx::pdl_launch();
         // ---- dW1 = sum of the batch-chunk partial tiles (16-byte accesses; H * D is a multiple of 4)
         if (a.part) {
             const int64_t n4 = (int64_t)H * D / 4;
             const size_t plane4 = (size_t)H * D / 4;
-            for (int64_t i = (int64_t)bid * FIN_THREADS + tid; i < n4; i += (int64_t)a.n_w1_ctas * FIN_THREADS) {
+            for (int64_t i = (int64_t)blockIdx.x * FIN_THREADS + tid; i < n4; i += (int64_t)a.n_w1_ctas * FIN_THREADS) {
                 float4 v[16];                                   // all chunk partials of this quad in flight together
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
@@ -303,14 +301,9 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) 
                 reinterpret_cast<float4*>(a.gW1)[i] = acc;
             }
         }
-        return;
-    }
-    {   // W2 role, shared chores: reset the Gram accumulator (consumed by the row kernel, refilled by k_update) and emit
-        // dgamma / dbeta / db1
-        const int w2 = bid - a.n_w1_ctas, n_w2 = (int)gridDim.x - ((a.roles & 1) ? a.n_w1_ctas : 0);
         if (a.gram_zero)
-            for (int e = w2 * FIN_THREADS + tid; e < a.gram_floats; e += n_w2 * FIN_THREADS) a.gram_zero[e] = 0.f;
-        if (w2 == 0) {
+            for (int e = blockIdx.x * FIN_THREADS + tid; e < a.gram_floats; e += a.n_w1_ctas * FIN_THREADS) a.gram_zero[e] = 0.f;
+        if (blockIdx.x == 0) {
             for (int j = tid; j < H; j += FIN_THREADS) {
                 a.ggamma[j] = (float)(a.dgb[j] * (double)a.gb_scale);
                 a.gbeta[j] = (float)(a.dgb[H + j] * (double)a.gb_scale);
@@ -319,13 +312,14 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) 
                 a.gb1[j] = 0.f;
             }
         }
+        return;
     }
     // ---- dW2a rows [d0, d0 + FIN_ROWS):  out[d][n] = sum_k L[d][k] S[k][n],  L = [W2 | b2 | That]
     // 4 x 4 register tiles, operands read as 16-byte vectors (k padded to KP, n padded to NP with zeros)
     const int KP = (K + 3) & ~3, NP = (N + 3) & ~3;
     float* sS = fin_smem;                       // [KP][NP]
     float* sL = sS + (size_t)KP * NP;           // [FIN_ROWS][KP]
-    const int d0 = (bid - a.n_w1_ctas) * FIN_ROWS;
+    const int d0 = ((int)blockIdx.x - a.n_w1_ctas) * FIN_ROWS;
     {   // S is stored with row stride NP: whole 16-byte chunks, everything in flight at once
         const int n4 = K * NP / 4;
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sS);
@@ -385,11 +379,9 @@ static int launch_finalize(FinalizeArgs a, cudaStream_t st) {
     DBMM_CHECK_SHAPE(smem <= 227 * 1024 && (FIN_ROWS / 4) * ((a.H + 4) / 4) <= FIN_THREADS, "finalize kernel: H=%d C=%d too large", a.H, a.C);
     DBMM_CUDA(set_smem(k_finalize_grads, smem));
     a.n_w1_ctas = a.part ? 64 : 1;
-    if (!a.roles) a.roles = 3;
     DBMM_CHECK_ARG(a.nchunk <= 16, "at most 16 batch chunks (got %d)", a.nchunk);
     const int n_w2 = ceil_div(a.D, FIN_ROWS);
-    const int grid = ((a.roles & 1) ? a.n_w1_ctas : 0) + ((a.roles & 2) ? n_w2 : 0);
-    DBMM_CUDA(launch_pdl(k_finalize_grads, dim3(grid), dim3(FIN_THREADS), (a.roles & 2) ? smem : 0, st, a));
+    DBMM_CUDA(launch_pdl(k_finalize_grads, dim3(a.n_w1_ctas + n_w2), dim3(FIN_THREADS), smem, st, a));
     return DBMM_OK;
 }
 
