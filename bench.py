@@ -303,6 +303,16 @@ def main():
         kus = ops.train_epoch_profile(X, order_buf, BATCH, y, g, ad, That, 100.0, buf, lrs, stats, G=G)
     else:
         kus = None
+        if rank == 0:
+            # N > 1: the per-kernel intervals are measured at N = 1 only (dbmm_train_epoch_profile is single-GPU); the line
+            # carries the whole step of ONE rank against the roofs, like roofline.step of the N = 1 line
+            t_step = ms_per_step * 1e-3 / steps_per_epoch
+            gbs = ALG_BYTES_PER_EMB * BATCH / t_step / 1e9
+            out["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": P["hbm"], "unit": "GB/s", "frac": gbs / P["hbm"],
+                               "traffic": None, "kernel": "whole data-parallel step of one rank (per-kernel figures: N = 1 line)",
+                               "peak_source": P["src"], "algorithmic_bytes_per_launch": ALG_BYTES_PER_EMB * BATCH,
+                               "step": {"bound": "tensor", "achieved_tflops": ALG_FLOP_TRAIN * BATCH / t_step / 1e12,
+                                        "frac": ALG_FLOP_TRAIN * BATCH / t_step / 1e12 / P["tc_sustained"]}}
     if rank == 0 and kus is not None:
         np_ = 2 * D * H + 3 * H + D
         alg = {"gemm1_tc": (ALG_BYTES_PER_EMB * BATCH, 2.0 * D * H * BATCH), "wgrad_tc": (ALG_BYTES_PER_EMB * BATCH, 2.0 * D * H * BATCH),
