@@ -40,6 +40,13 @@ class BatchStats(C.Structure):
     _fields_ = [("loss_sum", C.c_void_p), ("counts", C.c_void_p)]
 
 
+class Member(C.Structure):
+    """struct dbmm_member (one member of a batched sweep epoch)"""
+    _fields_ = [("order", C.c_void_p), ("old_ad", C.POINTER(AdapterPtrs)), ("ad", C.POINTER(AdapterPtrs)),
+                ("grads", C.c_void_p), ("momentum_buf", C.c_void_p), ("stats", BatchStats),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
 def sources_newer_than_lib() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -82,10 +89,16 @@ SIGNATURES = {
     "dbmm_train_epoch": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _AP, _AP, _f32,
                                    _vp, _f32, _vp, _vp, C.POINTER(C.c_float), _f32, _f32, _i32, BatchStats,
                                    _vp, _sz, _vp]),
+    "dbmm_train_forward": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _AP, _AP, _f32, _vp, _f32, _vp, _i32, _vp, _sz, _vp]),
+    "dbmm_train_backward": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _AP, _AP, _f32, _vp, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "dbmm_batched_workspace_bytes": (_sz, [_i32, _i64]),
+    "dbmm_train_epoch_batched": (C.c_int, [_i32, C.POINTER(Member), _vp, _i64, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _i32,
+                                           _f32, _vp, _f32, C.POINTER(C.c_float), _f32, _f32, _i32, _vp, _sz, _vp]),
     "dbmm_comm_unique_id": (C.c_int, [_vp]),
     "dbmm_comm_init": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
     "dbmm_comm_destroy": (C.c_int, [_vp]),
     "dbmm_comm_has_p2p": (C.c_int, [_vp]),
+    "dbmm_comm_check": (C.c_int, [_vp]),
     "dbmm_train_epoch_dp": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _AP, _AP,
                                       _f32, _vp, _f32, _vp, _vp, C.POINTER(C.c_float), _f32, _f32, _i32, BatchStats, _i32,
                                       _vp, _sz, _vp]),

@@ -92,6 +92,10 @@ def finalize_options(opt):
     if opt.dataset not in ("celeba", "waterbirds"):
         raise ValueError("dataset not supported: {}".format(opt.dataset))
     opt.n_cls = 2
+    if opt.tl_method != "linear_probing" and not (4 <= opt.adapter_feat_dim <= 128 and opt.adapter_feat_dim % 4 == 0):
+        # the reference accepts any width (final_main.py:241); the fused kernels hold one hidden vector per warp slot set
+        raise ValueError(f"--adapter_feat_dim {opt.adapter_feat_dim}: the B200 kernels support multiples of 4 up to 128 "
+                         "(DBMM_MAX_H, include/dbmm.h); the reference's default is 128")
     if opt.tl_method == "adapter":
         assert not opt.add_adapter
         assert not opt.balance_val
@@ -170,6 +174,13 @@ def _to_jsonable(d):
 
 
 def train_all_epochs(opt, loaders=None):
+    """final_main.train_all_epochs (805-1128): same arguments, prints, artefacts and return value."""
+    return E.drive(train_all_epochs_gen(opt, loaders))
+
+
+def train_all_epochs_gen(opt, loaders=None):
+    """train_all_epochs as a generator over its training epochs: every epoch's prepared TrainJob is yielded instead of run,
+    so that the sweep driver can run the jobs of many members in lock step (sweep.py); `train_all_epochs` drives it alone."""
     best_acc, best_epoch, best_model = 0, 0, None
     print(f"> Start Transfer Learning using [{opt.tl_method}]")
     print("========================================================================")
@@ -202,15 +213,15 @@ def train_all_epochs(opt, loaders=None):
 
         if opt.tl_method == "adapter_reg":
             gp = not opt.use_cls_prompt_in_reg
-            _, _, group_acc = E.train_reg_one_epoch(
+            _, _, group_acc = yield from E.train_reg_one_epoch_gen(
                 opt, train_loader, reg_loader, classifier, criterion, optimizer, epoch, get_yp_func,
                 target=opt.train_target, group_prompt=gp,
                 print_label="Train (Alternative Learning)(" + ("Group" if gp else "Class") + " prompt)")
         elif opt.tl_method in ("adapter_reg_seq", "adapter_reg_seq_alter"):
             if epoch <= FL:
-                _, _, group_acc = E.train_one_epoch(opt, train_loader, classifier, criterion, optimizer, epoch,
-                                                    get_yp_func, target=opt.train_target,
-                                                    print_label="Train-1 (Feature Learning)")
+                _, _, group_acc = yield from E.train_one_epoch_gen(opt, train_loader, classifier, criterion, optimizer, epoch,
+                                                                   get_yp_func, target=opt.train_target,
+                                                                   print_label="Train-1 (Feature Learning)")
             else:
                 if epoch == FL + 1:
                     if opt.continue_from_best:
@@ -229,12 +240,12 @@ def train_all_epochs(opt, loaders=None):
                 model = multiple_adapter if opt.add_adapter else classifier
                 label = "Train-2 (Balanced Learning)" + ("(new adapter)" if opt.add_adapter else "") + \
                         ("(Group prompt)" if use_group else "(Class prompt)")
-                _, _, group_acc = E.train_reg_seq_one_epoch(opt, reg_loader, model, criterion, optimizer_reg, epoch,
-                                                            get_yp_func, target=opt.train_target, print_label=label,
-                                                            use_group=use_group)
+                _, _, group_acc = yield from E.train_reg_seq_one_epoch_gen(opt, reg_loader, model, criterion, optimizer_reg, epoch,
+                                                                           get_yp_func, target=opt.train_target, print_label=label,
+                                                                           use_group=use_group)
         else:
-            _, _, group_acc = E.train_one_epoch(opt, train_loader, classifier, criterion, optimizer, epoch, get_yp_func,
-                                                target=opt.train_target, print_label=f"Train({opt.train_target})")
+            _, _, group_acc = yield from E.train_one_epoch_gen(opt, train_loader, classifier, criterion, optimizer, epoch, get_yp_func,
+                                                               target=opt.train_target, print_label=f"Train({opt.train_target})")
         train_group_accs.append(group_acc)
 
         stage2_ma = bool(opt.add_adapter and FL is not None and epoch > FL)

@@ -92,7 +92,25 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-__host__ __device__ static inline int s_stride(int H) { return (H + 1 + 3) & ~3; }     // row stride of the S matrix
+__host__ __device__ static inline int s_stride(int H) { return (H + 1 + 3) & ~3; }     // row stride of the S matrix and of the [h | 1] rows
+__host__ __device__ static inline int l_stride(int H, int C) { return (H + 1 + C + 3) & ~3; }     // row stride of the [c*h | c | ds] rows
+
+// ---- deterministic cross-CTA accumulators.  The small per-step batch reductions that several CTAs add into (BatchNorm
+// column sums, dgamma / dbeta) are 64-bit FIXED-POINT integers: integer atomics commute, so the sum does not depend on the
+// order in which the CTAs arrive and a training run is bit-reproducible (fp32 / fp64 atomics are not: the last bit follows
+// the arrival order).  The large ones (S, the Gram matrix) are atomics-free GEMMs (tn_gemm.cuh).  The wrapper type keeps
+// plain floating-point arithmetic on a slot from compiling.  LOG2 = binary point: resolution 2^-LOG2, range +-2^(63-LOG2).
+struct fx64 { long long v; };
+constexpr int FX_COLSUM = 20;     // sum a, sum a^2 over the global batch: range 8.8e12, resolution 9.5e-7 (fp32 partials carry more error)
+constexpr int FX_DGB = 40;        // dgamma, dbeta: range 8.4e6, resolution 9.1e-13
+template <int LOG2>
+__device__ __forceinline__ unsigned long long fx_bits(double x) { return (unsigned long long)__double2ll_rn(x * (double)(1ll << LOG2)); }
+template <int LOG2>
+__device__ __forceinline__ void fx_add(fx64* p, double x) { atomicAdd(reinterpret_cast<unsigned long long*>(&p->v), fx_bits<LOG2>(x)); }
+template <int LOG2>
+__device__ __forceinline__ double fx_val(long long bits) { return (double)bits * (1.0 / (double)(1ll << LOG2)); }
+template <int LOG2>
+__device__ __forceinline__ double fx_get(const fx64* p) { return fx_val<LOG2>(__ldcg(&p->v)); }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -130,12 +148,16 @@ constexpr int DBMM_LR_TABLE = 65536;          // learning rates (one per step) a
 constexpr int DBMM_G1_PART_ROWS = 16384;      // ksplit * nad * ceil128(B) never exceeds this (see gemm1_ksplit)
 
 struct TrainWs {
-    double* colsum;   // [nad][2][H]   sum a, sum a^2         (zero at the start of every step)
-    double* dgb;      // [2][H]        dgamma, dbeta          (zero at the start of every step)
-    float* S;         // [H+1+C][SP]   batch reduction for dW2, SP = H+1 rounded up to 4 (zero at the start of every step)
+    fx64* colsum;     // [nad][2][H]   sum a, sum a^2         (fixed point; zero at the start of every step)
+    fx64* dgb;        // [2][H]        dgamma, dbeta          (fixed point; zero at the start of every step)
+    float* S;         // [H+1+C][SP]   batch reduction for dW2 = L^T [h | 1] (k_tn_gemm), SP = H+1 rounded up to 4
     float* gram;      // [nad][H+1][H+1+C]
     float* S2;        // second half of the S double buffer (fused step tail)
     float* gram2;     // second half of the Gram double buffer (fused step tail: step s reads half s & 1, fills the other)
+    int* tn_ticket;   // [16]          tile tickets of the K-sliced TN GEMMs (zero between launches)
+    float* tn_part;   // K-slice tiles of the TN GEMMs (S and the Gram matrix run one after the other and share it)
+    float* Lrows;     // [B][l_stride]  rows [c*h | c | ds] of the trainable adapter (operand of S)
+    float* Hrows;     // [B][s_stride]  rows [h | 1]
     float* A;         // [nad][B][H]   pre-BatchNorm activations
     float* dahat;     // [B][H]        dL/d(normalised activation)
     float* whi;       // [nad][H][D]   tf32-exact part of W1 (tensor-core GEMM-1 operand)
@@ -152,13 +174,17 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     char* p = (char*)base;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_colsum = take(sizeof(double) * nad * 2 * H);
-    size_t o_dgb = take(sizeof(double) * 2 * H);
+    size_t o_colsum = take(sizeof(fx64) * nad * 2 * H);
+    size_t o_dgb = take(sizeof(fx64) * 2 * H);
     size_t o_S = take(sizeof(float) * (size_t)(H + 1 + C) * s_stride(H));
-    size_t o_gram = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));     // split-K target: zeroed with the sums
+    size_t o_gram = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));
     size_t o_S2 = take(sizeof(float) * (size_t)(H + 1 + C) * s_stride(H));
     size_t o_gram2 = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C));
+    size_t o_tk = take(sizeof(int) * 32);
     w.accum_bytes = off;
+    size_t o_tp = take(sizeof(float) * (size_t)8 * 16 * 32 * 48);       // TNG_MAX_KSPLIT * TNG_MAX_TILES * TNG_TM * TNG_TN
+    size_t o_L = take(sizeof(float) * (size_t)B * l_stride(H, C));
+    size_t o_Hr = take(sizeof(float) * (size_t)B * s_stride(H));
     size_t o_A = take(sizeof(float) * (size_t)nad * B * H);
     size_t o_da = take(sizeof(float) * (size_t)B * H);
     size_t o_whi = take(sizeof(float) * (size_t)nad * H * D);
@@ -167,7 +193,9 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     size_t o_g1 = take(sizeof(float) * (size_t)(DBMM_G1_PART_ROWS + 2 * 128) * H);
     size_t o_lr = take(sizeof(float) * DBMM_LR_TABLE);
     w.total = off;
-    w.colsum = (double*)(p + o_colsum); w.dgb = (double*)(p + o_dgb);
+    w.colsum = (fx64*)(p + o_colsum); w.dgb = (fx64*)(p + o_dgb);
+    w.Lrows = (float*)(p + o_L); w.Hrows = (float*)(p + o_Hr);
+    w.tn_ticket = (int*)(p + o_tk); w.tn_part = (float*)(p + o_tp);
     w.A = (float*)(p + o_A); w.dahat = (float*)(p + o_da);
     w.gram = (float*)(p + o_gram); w.gram2 = (float*)(p + o_gram2); w.S = (float*)(p + o_S); w.S2 = (float*)(p + o_S2);
     w.whi = (float*)(p + o_whi); w.wlo = (float*)(p + o_wlo); w.part = (float*)(p + o_part);

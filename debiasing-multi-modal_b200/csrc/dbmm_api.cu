@@ -8,8 +8,10 @@
 #include "kernels_simt.cuh"
 #include "rows_train.cuh"
 #include "wgrad_tc.cuh"
+#include "tn_gemm.cuh"
 #include "update.cuh"
 #include "step_tail.cuh"
+#include "batched.cuh"
 #include "export_rows.cuh"
 #include "head_supcon.cuh"
 #include "nccl_dyn.cuh"
@@ -101,22 +103,41 @@ static int launch_rows(const RowsArgs& ra, int nad, int H, int C, cudaStream_t s
     return DBMM_OK;
 }
 
+// Gram matrix of one adapter, G = [W2 | b2]^T [W2 | b2 | That]  ((H+1) x (H+1+C), K = D): atomics-free TN GEMM.
+struct TnSplit { float* part; int* ticket; };       // K-slice scratch of the training workspace (nullptr: one CTA per tile walks all of K)
+static inline int tn_ksplit(int K) { int k = K / 128; return k < 1 ? 1 : (k > TNG_MAX_KSPLIT ? TNG_MAX_KSPLIT : k); }
+static int launch_gram_gemm(const dbmm_adapter* ad, const float* That, float* gram, int D, int H, int C, cudaStream_t st,
+                            const TnSplit* sp = nullptr, bool pdl = false) {
+    TnGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    if (sp) { g.ksplit = tn_ksplit(D); g.part = sp->part; g.ticket = sp->ticket; }
+    g.A = cat_mat(ad->W2, H, H, ad->b2, 1, 1);
+    g.B = cat_mat(ad->W2, H, H, ad->b2, 1, 1, That, C, C);
+    g.M = H + 1; g.N = H + 1 + C; g.K = D; g.C = gram; g.ldc = H + 1 + C; g.n_store = H + 1 + C;
+    g.no_early_trigger = 1;          // k_rows_train copies the Gram matrix before its dependency wait
+    return launch_tn_gemm(g, st, pdl);
+}
 static int launch_gram(const dbmm_adapter* old_ad, const dbmm_adapter* ad, const float* That, float* gram,
-                       int D, int H, int C, cudaStream_t st) {
-    GramArgs ga;
-    const int nad = old_ad ? 2 : 1;
-    ga.W2[0] = old_ad ? old_ad->W2 : ad->W2; ga.b2[0] = old_ad ? old_ad->b2 : ad->b2;
-    ga.W2[1] = ad->W2; ga.b2[1] = ad->b2;
-    ga.That = That; ga.gram = gram; ga.D = D; ga.H = H; ga.C = C; ga.nad = nad;
-    ga.ksplit = D >= 256 ? 16 : 1;           // the caller zeroes `gram` when ksplit > 1 (see gram_needs_zero)
-    dim3 grid(ceil_div(H + 1, GT_BM), ceil_div(H + 1 + C, GT_BN), nad * ga.ksplit);
-    k_gram<<<grid, GT_THREADS, 0, st>>>(ga);
-    DBMM_LAUNCH_CHECK();
-    return DBMM_OK;
+                       int D, int H, int C, cudaStream_t st, const TnSplit* sp = nullptr) {
+    const size_t gf = (size_t)(H + 1) * (H + 1 + C);
+    if (old_ad) if (int rc = launch_gram_gemm(old_ad, That, gram, D, H, C, st, sp)) return rc;
+    return launch_gram_gemm(ad, That, gram + (old_ad ? gf : 0), D, H, C, st, sp);
+}
+// S = [c*h | c | ds]^T [h | 1] over the batch rows the row kernel has just written ((H+1+C) x (H+1), K = B).
+static int launch_s_gemm(const float* Lrows, const float* Hrows, float* S, int B, int H, int C, cudaStream_t st,
+                         const TnSplit* sp = nullptr) {
+    TnGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    if (sp) { g.ksplit = tn_ksplit(B); g.part = sp->part; g.ticket = sp->ticket; }
+    g.A = cat_mat(Lrows, l_stride(H, C), H + 1 + C);
+    g.B = cat_mat(Hrows, s_stride(H), H + 1);
+    g.M = H + 1 + C; g.N = H + 1; g.K = B; g.C = S; g.ldc = s_stride(H); g.n_store = s_stride(H);
+    g.no_early_trigger = 0;
+    return launch_tn_gemm(g, st, false);
 }
 
 static void fill_gemm1(Gemm1Args& g, const float* X, int64_t ldx, const int32_t* idx, int64_t pos0, int B, int D, int H,
-                       const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, double* colsum) {
+                       const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, fx64* colsum) {
     g.X = X; g.ldx = ldx; g.idx = idx; g.pos0 = pos0; g.B = B; g.D = D; g.H = H;
     g.nad = old_ad ? 2 : 1;
     g.W1[0] = old_ad ? old_ad->W1 : ad->W1; g.b1[0] = old_ad ? old_ad->b1 : ad->b1;
@@ -148,7 +169,7 @@ static int gemm1_ksplit(int B, int nad, int D) {
 }
 
 // Fused step tail: the per-step accumulators are re-zeroed by the NEXT step's head kernels (see step_tail.cuh).
-struct StepZero { double* dgb; int dgb_n; float* S; int S_n; };
+struct StepZero { fx64* dgb; int dgb_n; };
 
 // How the tail of a training step runs.  nullptr / !fused: k_finalize_grads + k_update (stepwise API, data parallel).
 // fused: k_step_tail; with a side stream its W2 role is forked off after the row kernel and joined only before the NEXT
@@ -159,7 +180,7 @@ struct TailPlan { bool fused; int parity; cudaStream_t side; cudaEvent_t ev_fork
 // a = x W1^T + b1 for one or two adapters (+ fp64 column sums).  whi/wlo: scratch [nad][H][D] each.
 // ksplit > 1 (training): D-sliced partial tiles into `g1part`, finished by k_reduce_stats.
 static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t pos0, int B, int D, int H,
-                        const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, double* colsum,
+                        const dbmm_adapter* old_ad, const dbmm_adapter* ad, float* A, fx64* colsum,
                         float* whi, float* wlo, bool split_weights, int ksplit, float* g1part, cudaStream_t st,
                         cudaEvent_t* ev = nullptr, const P2pArgs* p2p = nullptr, const StepZero* zero = nullptr) {
     const int nad = old_ad ? 2 : 1;
@@ -199,7 +220,7 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
         memset(&r.p2p, 0, sizeof(r.p2p));
         if (p2p) r.p2p = *p2p;
         r.zero_dgb = nullptr; r.zero_dgb_n = 0; r.zero_S = nullptr; r.zero_S_n = 0;
-        if (zero) { r.zero_dgb = zero->dgb; r.zero_dgb_n = zero->dgb_n; r.zero_S = zero->S; r.zero_S_n = zero->S_n; }
+        if (zero) { r.zero_dgb = zero->dgb; r.zero_dgb_n = zero->dgb_n; }
         DBMM_CUDA(set_smem(k_reduce_stats, 0));
         DBMM_CUDA(launch_pdl(k_reduce_stats, dim3(ceil_div(B, RS_ROWS), nad), dim3(RS_THREADS), 0, st, r));
     }
@@ -223,7 +244,6 @@ static int eval_fwd_tc(const float* X, int64_t ldx, const int32_t* idx, const in
     const int nad = old_ad ? 2 : 1, ldg = H + 1 + C;
     EvalTcWs w = carve_eval_tc_ws(ws, N, D, H, C, nad);
     const dbmm_adapter* ads[2] = {old_ad ? old_ad : ad, ad};
-    DBMM_CUDA(cudaMemsetAsync(w.gram, 0, sizeof(float) * (size_t)nad * (H + 1) * ldg, st));
     if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
     for (int i = 0; i < nad; ++i) {
         k_split_tf32<<<148, 256, 0, st>>>(ads[i]->W1, w.whi + (size_t)i * H * D, w.wlo + (size_t)i * H * D, (int64_t)H * D);
@@ -349,7 +369,6 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
     const int64_t chunk_rows = N < EVAL_CHUNK ? N : EVAL_CHUNK;
     float* whi = (float*)((char*)A + align_up(sizeof(float) * (size_t)nad * chunk_rows * H, 256));
     float* wlo = (float*)((char*)whi + align_up(sizeof(float) * (size_t)nad * H * D, 256));
-    DBMM_CUDA(cudaMemsetAsync(gram, 0, sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C), st));
     if (int rc = launch_gram(old_ad, ad, That, gram, D, H, C, st)) return rc;
     for (int64_t pos0 = 0; pos0 < N; pos0 += EVAL_CHUNK) {
         const int B = (int)((N - pos0) < EVAL_CHUNK ? (N - pos0) : EVAL_CHUNK);
@@ -404,6 +423,9 @@ int dbmm_export_embeddings(const float* X, int64_t ldx, const int32_t* idx, int6
     return DBMM_OK;
 }
 
+// nn.Module boundary (dbmm_train_forward / dbmm_train_backward): logits out, upstream logit gradient in
+struct StepExtras { float* logits_out; const float* dlogits_in; };
+
 // One training step.  fresh: first step of an API call -- the accumulators are zeroed, the Gram matrices and the tf32
 // weight splits are computed from scratch; otherwise the previous step's k_finalize_grads / k_update left them ready.
 // lr_dev != nullptr: the learning rate is read from device memory by the update kernel (CUDA-graph replay).
@@ -416,7 +438,7 @@ static int train_step_impl(int phases, bool fresh,
                            dbmm_batch_stats stats, int64_t slot, const TrainWs& w, cudaStream_t st,
                            cudaEvent_t* ev = nullptr /* 7 events: before each of the 6 step kernels + after the last */,
                            const P2pArgs* p2p = nullptr /* fused peer-memory all-reduce of the column sums / (dgamma, dbeta) */,
-                           TailPlan* tail = nullptr) {
+                           TailPlan* tail = nullptr, const StepExtras* ex = nullptr) {
     const int nad = old_ad ? 2 : 1;
     const bool fused = tail && tail->fused;
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
@@ -425,21 +447,27 @@ static int train_step_impl(int phases, bool fresh,
     float* gram_cur = fused && tail->parity ? w.gram2 : w.gram;         // read by this step's row kernel
     float* gram_nxt = fused && !tail->parity ? w.gram2 : w.gram;        // fused tail: filled for the next step
     float* gram_t = gram_cur + (size_t)(nad - 1) * gram_floats;
+    float* gram_next_t = gram_nxt + (size_t)(nad - 1) * gram_floats;
     float* S_cur = fused && tail->parity ? w.S2 : w.S;
     const bool tc1 = use_tc_gemm1(D, H);
+    const TnSplit tsp = {w.tn_part, w.tn_ticket};
+#ifdef DBMM_EXPERIMENTS
     static const int skip = getenv("DBMM_SKIP") ? atoi(getenv("DBMM_SKIP")) : 0;   // timing experiments only: drop kernels by bit mask
     if (skip) phases &= ~skip;
+#else
+    constexpr int skip = 0;        // the "results are wrong on purpose" switches exist only in -DDBMM_EXPERIMENTS builds
+#endif
 
     if (phases & DBMM_PHASE_GEMM1) {
         if (fresh) {
             DBMM_CUDA(cudaMemsetAsync(w.colsum, 0, w.accum_bytes, st));
-            if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st)) return rc;
+            if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st, &tsp)) return rc;
             if (fused && nad == 2)            // the frozen adapter's Gram matrix is constant: present in both halves
                 DBMM_CUDA(cudaMemcpyAsync(w.gram2, w.gram, sizeof(float) * gram_floats, cudaMemcpyDeviceToDevice, st));
         }
         const int ks = tc1 ? gemm1_ksplit(B, nad, D) : 1;
         StepZero sz;
-        sz.dgb = w.dgb; sz.dgb_n = 2 * H; sz.S = S_cur; sz.S_n = (H + 1 + C) * s_stride(H);
+        sz.dgb = w.dgb; sz.dgb_n = 2 * H;
         DBMM_CHECK_ARG(!fused || (tc1 && ks > 1), "fused step tail needs the D-sliced tensor-core GEMM-1");
         if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, old_ad, ad, w.A, w.colsum, w.whi, w.wlo, fresh, ks, w.g1part, st, ev, p2p,
                                   fused && !fresh ? &sz : nullptr)) return rc;
@@ -457,8 +485,10 @@ static int train_step_impl(int phases, bool fresh,
         ra.ad[0] = view_of(old_ad ? old_ad : ad); ra.ad[1] = view_of(ad);
         ra.w_old = ebd_weight; ra.inv_tau = inv_tau; ra.inv_B = 1.0f / (float)B_global;
         ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.slot = slot;
-        ra.dahat = w.dahat; ra.dgb = w.dgb; ra.S = S_cur;
+        ra.dahat = w.dahat; ra.dgb = w.dgb; ra.Lrows = w.Lrows; ra.Hrows = w.Hrows;
+        if (ex) { ra.logits_out = ex->logits_out; ra.dlogits_in = ex->dlogits_in; }
         if (int rc = launch_rows_train(ra, nad, st)) return rc;
+        if (!fused) if (int rc = launch_s_gemm(w.Lrows, w.Hrows, w.S, B, H, C, st, &tsp)) return rc;
     }
     StepTailArgs ta;
     if (fused) {
@@ -469,7 +499,6 @@ static int train_step_impl(int phases, bool fresh,
         ta.g = grads; ta.v = momentum_buf; ta.lr_dev = lr_dev; ta.lr = lr; ta.momentum = momentum; ta.wd = weight_decay;
         ta.part = w.part; ta.whi = w.whi + (size_t)(nad - 1) * H * D; ta.wlo = w.wlo + (size_t)(nad - 1) * H * D;
         ta.That = That; ta.S = S_cur;
-        ta.gram_next = gram_nxt + (size_t)(nad - 1) * gram_floats; ta.gram_zero = gram_t;
         ta.dgb = w.dgb; ta.colsum = w.colsum; ta.D = D; ta.H = H; ta.C = C; ta.nad = nad; ta.Bg = B_global;
         const dbmm_adapter* a0 = old_ad ? old_ad : ad;
         ta.rm[0] = a0->running_mean; ta.rv[0] = a0->running_var; ta.nbt[0] = (long long*)a0->num_batches_tracked;
@@ -479,7 +508,9 @@ static int train_step_impl(int phases, bool fresh,
             DBMM_CUDA(cudaEventRecord(tail->ev_fork, st));
             DBMM_CUDA(cudaStreamWaitEvent(tail->side, tail->ev_fork, 0));
             ta.roles = 2;
+            if (int rc = launch_s_gemm(w.Lrows, w.Hrows, S_cur, B, H, C, tail->side, &tsp)) return rc;
             if (int rc = launch_step_tail(ta, tail->side)) return rc;
+            if (int rc = launch_gram_gemm(ad, That, gram_next_t, D, H, C, tail->side, &tsp, true)) return rc;
             DBMM_CUDA(cudaEventRecord(tail->ev_join, tail->side));
             tail->join_pending = true;
         }
@@ -489,7 +520,7 @@ static int train_step_impl(int phases, bool fresh,
         mark(3);
         int nchunk = 0;
         const float* A_t = w.A + (size_t)(nad - 1) * B * H;
-        const double* colsum_t = w.colsum + (size_t)(nad - 1) * 2 * H;
+        const fx64* colsum_t = w.colsum + (size_t)(nad - 1) * 2 * H;
         if (tc && !(skip & 32)) {
             WgradTcArgs t;
             memset(&t, 0, sizeof(t));
@@ -521,7 +552,9 @@ static int train_step_impl(int phases, bool fresh,
                 mark(5);
                 if (!tail->side) {                               // no fork (stream launches, profiling): W2 role in line
                     ta.roles = 2;
+                    if (int rc = launch_s_gemm(w.Lrows, w.Hrows, S_cur, B, H, C, st, &tsp)) return rc;
                     if (int rc = launch_step_tail(ta, st)) return rc;
+                    if (int rc = launch_gram_gemm(ad, That, gram_next_t, D, H, C, st, &tsp, true)) return rc;
                 }
             }
             mark(6);
@@ -534,7 +567,7 @@ static int train_step_impl(int phases, bool fresh,
         fa.gW1 = grads + oW1; fa.gb1 = grads + ob1; fa.ggamma = grads + og; fa.gbeta = grads + obeta;
         fa.gW2 = grads + oW2; fa.gb2 = grads + ob2; fa.D = D; fa.H = H; fa.C = C; fa.n_w1_ctas = 0;
         fa.gb_scale = (float)((double)B / (double)B_global);
-        fa.gram_zero = gram_t; fa.gram_floats = (int)gram_floats;
+        fa.gram_zero = nullptr; fa.gram_floats = 0;
         if (!(skip & 16)) if (int rc = launch_finalize(fa, st)) return rc;
     }
     if (phases & DBMM_PHASE_UPDATE) {
@@ -544,13 +577,14 @@ static int train_step_impl(int phases, bool fresh,
         ua.W1 = ad->W1; ua.b1 = ad->b1; ua.gamma = ad->gamma; ua.beta = ad->beta; ua.W2 = ad->W2; ua.b2 = ad->b2;
         ua.g = grads; ua.v = momentum_buf; ua.lr_dev = lr_dev; ua.lr = lr; ua.momentum = momentum; ua.wd = weight_decay;
         ua.whi = tc1 ? w.whi + (size_t)(nad - 1) * H * D : nullptr; ua.wlo = tc1 ? w.wlo + (size_t)(nad - 1) * H * D : nullptr;
-        ua.That = That; ua.gram = gram_t;
+        ua.That = That;
         ua.D = D; ua.H = H; ua.C = C; ua.nad = nad; ua.Bg = B_global;
-        ua.colsum = w.colsum; ua.dgb = w.dgb; ua.S = w.S; ua.zero_accum = 1;
+        ua.colsum = w.colsum; ua.dgb = w.dgb; ua.zero_accum = 1;
         const dbmm_adapter* a0 = old_ad ? old_ad : ad;
         ua.rm[0] = a0->running_mean; ua.rv[0] = a0->running_var; ua.nbt[0] = (long long*)a0->num_batches_tracked;
         ua.rm[1] = ad->running_mean; ua.rv[1] = ad->running_var; ua.nbt[1] = (long long*)ad->num_batches_tracked;
         if (int rc = launch_update(ua, st)) return rc;
+        if (int rc = launch_gram_gemm(ad, That, gram_t, D, H, C, st, &tsp)) return rc;      // next step's Gram matrix from the new W2 / b2
         mark(6);
     }
     return DBMM_OK;
@@ -591,6 +625,63 @@ int dbmm_train_step_ex(int phases, int fresh,
     }
     return train_step_impl(phases, fresh != 0, X, ldx, idx, y, grp, B_local, B_global, D, H, C, G, old_ad, ad, ebd_weight, That,
                            inv_tau, grads, momentum_buf, lr, lr_dev, momentum, weight_decay, stats, slot, w, st);
+}
+
+// ---- nn.Module boundary: train-mode forward (logits) and backward (parameter gradients from dL/dlogits) as two calls, so
+// that the reference's own loop -- output = classifier(x); loss = criterion(output, y); loss.backward(); optimizer.step()
+// (final_main.py:455-466) -- runs unchanged on modules whose arithmetic is these kernels (modules.py).
+static int check_fb_args(const float* X, int64_t ldx, int B, int D, int H, int C, const dbmm_adapter* old_ad, const dbmm_adapter* ad,
+                         const float* That, void* ws) {
+    if (int rc = check_dims(D, H, C, 1)) return rc;
+    DBMM_CHECK_SHAPE(H % 4 == 0, "H=%d must be a multiple of 4", H);
+    if (int rc = check_adapter(ad, "trainable")) return rc;
+    if (old_ad) if (int rc = check_adapter(old_ad, "old")) return rc;
+    DBMM_CHECK_ARG(X && That && ws && ldx >= D, "NULL X / That / workspace");
+    DBMM_CHECK_ARG(B > 1, "BatchNorm needs more than 1 row per batch in training (got %d)", B);
+    return DBMM_OK;
+}
+
+int dbmm_train_forward(const float* X, int64_t ldx, const int32_t* idx, int B, int D, int H, int C,
+                       const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight, const float* That, float inv_tau,
+                       float* logits_out, int update_running_stats, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_fb_args(X, ldx, B, D, H, C, old_ad, ad, That, ws)) return rc;
+    DBMM_CHECK_ARG(logits_out != nullptr, "NULL logits output");
+    const int nad = old_ad ? 2 : 1;
+    TrainWs w = carve_train_ws(ws, B, D, H, C, nad);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    StepExtras ex = {logits_out, nullptr};
+    dbmm_batch_stats none = {nullptr, nullptr};
+    if (int rc = train_step_impl(DBMM_PHASE_GEMM1 | DBMM_PHASE_ROWS, true, X, ldx, idx, nullptr, nullptr, B, B, D, H, C, 1, old_ad, ad,
+                                 ebd_weight, That, inv_tau, nullptr, nullptr, 0.f, nullptr, 0.f, 0.f, none, 0, w, st, nullptr, nullptr,
+                                 nullptr, &ex)) return rc;
+    if (update_running_stats) {
+        BnRunningArgs b;
+        const dbmm_adapter* a0 = old_ad ? old_ad : ad;
+        b.colsum = w.colsum; b.nad = nad; b.H = H; b.Bg = B;
+        b.rm[0] = a0->running_mean; b.rv[0] = a0->running_var; b.nbt[0] = (long long*)a0->num_batches_tracked;
+        b.rm[1] = ad->running_mean; b.rv[1] = ad->running_var; b.nbt[1] = (long long*)ad->num_batches_tracked;
+        k_bn_running<<<1, 256, 0, st>>>(b);
+        DBMM_LAUNCH_CHECK();
+    }
+    return DBMM_OK;
+}
+
+int dbmm_train_backward(const float* X, int64_t ldx, const int32_t* idx, int B, int D, int H, int C,
+                        const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight, const float* That, float inv_tau,
+                        const float* dlogits, float* grads, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_fb_args(X, ldx, B, D, H, C, old_ad, ad, That, ws)) return rc;
+    DBMM_CHECK_ARG(dlogits && grads, "NULL logit gradient / gradient output");
+    const int nad = old_ad ? 2 : 1;
+    TrainWs w = carve_train_ws(ws, B, D, H, C, nad);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    StepExtras ex = {nullptr, dlogits};
+    dbmm_batch_stats none = {nullptr, nullptr};
+    // the forward is recomputed from X (4 MB per 1024 rows): nothing has to survive between the two calls
+    return train_step_impl(DBMM_PHASE_GEMM1 | DBMM_PHASE_ROWS | DBMM_PHASE_WGRAD, true, X, ldx, idx, nullptr, nullptr, B, B, D, H, C, 1,
+                           old_ad, ad, ebd_weight, That, inv_tau, grads, nullptr, 0.f, nullptr, 0.f, 0.f, none, 0, w, st, nullptr, nullptr,
+                           nullptr, &ex);
 }
 
 int dbmm_train_step(int phases,
@@ -646,10 +737,17 @@ struct DbmmComm {
 static int tail_mode(int B0, int last_B, int nad, int D, int H, int C) {
     const char* e = getenv("DBMM_TAIL");
     if (e && strcmp(e, "split") == 0) return 0;
+#ifdef DBMM_EXPERIMENTS
     if (getenv("DBMM_SKIP")) return 0;
+#endif
     if (!(use_tc_gemm1(D, H) && use_tc_wgrad(D, H) && step_tail_supported(D, H, C))) return 0;
     if (gemm1_ksplit(B0, nad, D) <= 1 || gemm1_ksplit(last_B, nad, D) <= 1) return 0;
     return (e && strcmp(e, "serial") == 0) ? 1 : 2;
+}
+
+static unsigned long long p2p_timeout_ns() {       // wall-clock bound of the peer-memory waits (p2p.cuh); default 300 s
+    static const double s = getenv("DBMM_P2P_TIMEOUT_S") ? atof(getenv("DBMM_P2P_TIMEOUT_S")) : 300.0;
+    return (unsigned long long)((s > 0.001 ? s : 300.0) * 1e9);
 }
 
 static bool p2p_enabled() {
@@ -718,8 +816,11 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
             memset(&pa, 0, sizeof(pa));
             if (use_p2p) {
                 pa.world = world; pa.rank = rank; pa.step = (int)s;
+#ifdef DBMM_EXPERIMENTS
                 static const int dp_skip = getenv("DBMM_DP_SKIP") ? atoi(getenv("DBMM_DP_SKIP")) : 0;      // timing experiments only
                 pa.skip = dp_skip;
+#endif
+                pa.timeout_ns = p2p_timeout_ns();
                 for (int r = 0; r < world; ++r) pa.peer[r] = dcomm->p2p_peer[r];
             }
             tplan.parity = (int)(s & 1);
@@ -730,11 +831,15 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
             };
             if (!dp || tplan.fused) { if (int rc = phase(DBMM_PHASE_ALL)) return rc; continue; }
             if (int rc = phase(DBMM_PHASE_GEMM1)) return rc;
-            if (!use_p2p) DBMM_NCCL(nc->AllReduce(w.colsum, w.colsum, (size_t)nad * 2 * H, ncclFloat64, ncclSum, comm, s_));
+            if (!use_p2p) DBMM_NCCL(nc->AllReduce(w.colsum, w.colsum, (size_t)nad * 2 * H, ncclInt64, ncclSum, comm, s_));      // fixed point
             if (int rc = phase(DBMM_PHASE_ROWS)) return rc;
-            if (!use_p2p) DBMM_NCCL(nc->AllReduce(w.dgb, w.dgb, (size_t)2 * H, ncclFloat64, ncclSum, comm, s_));
+            if (!use_p2p) DBMM_NCCL(nc->AllReduce(w.dgb, w.dgb, (size_t)2 * H, ncclInt64, ncclSum, comm, s_));
             if (int rc = phase(DBMM_PHASE_WGRAD)) return rc;
+#ifdef DBMM_EXPERIMENTS
             static const bool skip_grad_ar = getenv("DBMM_SKIP_GRAD_AR") != nullptr;      // timing experiments only
+#else
+            constexpr bool skip_grad_ar = false;
+#endif
             if (!skip_grad_ar) DBMM_NCCL(nc->AllReduce(grads, grads, np, ncclFloat32, ncclSum, comm, s_));
             if (int rc = phase(DBMM_PHASE_UPDATE)) return rc;
         }
@@ -814,6 +919,115 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
                             (cudaStream_t)stream);
 }
 
+// ---- batched-adapter training: M sweep members in lock step (BASELINE config 5; csrc/batched.cuh)
+size_t dbmm_batched_workspace_bytes(int n_members, int64_t steps) {
+    if (n_members < 1 || steps < 1) return 0;
+    return align_up(sizeof(MemberDev) * (size_t)n_members, 256) + align_up(sizeof(float) * (size_t)n_members * (size_t)steps, 256);
+}
+
+int dbmm_train_epoch_batched(int n_members, const dbmm_member* members,
+                             const float* X, int64_t ldx, int64_t n_rows, int batch_size, const int32_t* y, const int32_t* grp,
+                             int D, int H, int C, int G, float ebd_weight, const float* That, float inv_tau,
+                             const float* lr_host, float momentum, float weight_decay, int first_step,
+                             void* bws, size_t bws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DBMM_CHECK_ARG(n_members >= 1 && members && lr_host && bws, "NULL members / lr table / batched workspace");
+    DBMM_CHECK_ARG(n_rows >= 1 && batch_size >= 1, "bad n_rows=%lld batch_size=%d", (long long)n_rows, batch_size);
+    const int64_t steps = (n_rows + batch_size - 1) / batch_size;
+    const int B0 = (int)(n_rows < batch_size ? n_rows : batch_size);
+    const int64_t last_B = n_rows - (steps - 1) * batch_size;
+    DBMM_CHECK_ARG(last_B > 1, "BatchNorm needs more than 1 row per batch in training (trailing batch of %lld)", (long long)last_B);
+    DBMM_CHECK_ARG(dbmm_batched_workspace_bytes(n_members, steps) <= bws_bytes, "batched workspace too small");
+    const bool has_old = members[0].old_ad != nullptr;
+    const int nad = has_old ? 2 : 1;
+    DBMM_CHECK_SHAPE(batched_supported(D, H, C), "batched training needs D %% 128 == 0 and H == 128 (D=%d H=%d C=%d): run the members one by one", D, H, C);
+    std::vector<MemberDev> host((size_t)n_members);
+    const size_t np = dbmm_param_count(D, H);
+    for (int m = 0; m < n_members; ++m) {
+        const dbmm_member& mb = members[m];
+        DBMM_CHECK_ARG((mb.old_ad != nullptr) == has_old, "member %d: all members must be in the same stage (old_ad NULL or not)", m);
+        DBMM_CHECK_ARG(mb.order && mb.grads && mb.momentum_buf && mb.ws, "member %d: NULL order / grads / momentum / workspace", m);
+        if (int rc = check_train_args(X, ldx, y, B0, B0, D, H, C, G, mb.old_ad, mb.ad, That, mb.ws, mb.grads)) return rc;
+        TrainWs w = carve_train_ws(mb.ws, B0, D, H, C, nad);
+        DBMM_CHECK_ARG(w.total <= mb.ws_bytes, "member %d: workspace too small: need %zu, have %zu", m, w.total, mb.ws_bytes);
+        MemberDev& d = host[(size_t)m];
+        memset(&d, 0, sizeof(d));
+        d.order = mb.order; d.ad[0] = view_of(has_old ? mb.old_ad : mb.ad); d.ad[1] = view_of(mb.ad);
+        d.grads = mb.grads; d.mom = mb.momentum_buf;
+        d.lr = (const float*)((char*)bws + align_up(sizeof(MemberDev) * (size_t)n_members, 256)) + (size_t)m * steps;
+        d.loss_sum = mb.stats.loss_sum; d.counts = mb.stats.counts; d.w = w;
+        DBMM_CHECK_ARG(d.loss_sum && d.counts, "member %d: NULL statistics buffers", m);
+    }
+    MemberDev* dmem = (MemberDev*)bws;
+    DBMM_CUDA(cudaMemcpyAsync(dmem, host.data(), sizeof(MemberDev) * (size_t)n_members, cudaMemcpyHostToDevice, st));
+    DBMM_CUDA(cudaMemcpyAsync((char*)bws + align_up(sizeof(MemberDev) * (size_t)n_members, 256), lr_host,
+                              sizeof(float) * (size_t)n_members * (size_t)steps, cudaMemcpyHostToDevice, st));
+
+    auto enqueue = [&](cudaStream_t s_) -> int {
+        for (int m = 0; m < n_members; ++m) {        // epoch prologue per member: accumulators, Gram matrices, tf32 weight splits
+            const dbmm_member& mb = members[m];
+            const MemberDev& d = host[(size_t)m];
+            if (first_step) DBMM_CUDA(cudaMemsetAsync(mb.momentum_buf, 0, sizeof(float) * np, s_));
+            DBMM_CUDA(cudaMemsetAsync(d.w.colsum, 0, d.w.accum_bytes, s_));
+            if (int rc = launch_gram(mb.old_ad, mb.ad, That, d.w.gram, D, H, C, s_)) return rc;
+            const dbmm_adapter* ads[2] = {has_old ? mb.old_ad : mb.ad, mb.ad};
+            for (int i = 0; i < nad; ++i) {
+                k_split_tf32<<<148, 256, 0, s_>>>(ads[i]->W1, d.w.whi + (size_t)i * H * D, d.w.wlo + (size_t)i * H * D, (int64_t)H * D);
+                DBMM_LAUNCH_CHECK();
+            }
+        }
+        for (int64_t s = 0; s < steps; ++s) {
+            const int64_t p0 = s * batch_size;
+            const int B = (int)((n_rows - p0) < batch_size ? (n_rows - p0) : batch_size);
+            if (int rc = batched_step(dmem, n_members, (int)s, p0, B, X, ldx, y, grp, D, H, C, G, nad, ebd_weight, That, inv_tau,
+                                      momentum, weight_decay, s_)) return rc;
+        }
+        return DBMM_OK;
+    };
+    if (!graphs_enabled() || steps < 2) return enqueue(st);
+
+    // one graph per distinct argument set, keyed by a hash of everything that is baked into the kernel arguments
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) { const unsigned char* c = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; } };
+    mix(host.data(), sizeof(MemberDev) * host.size());
+    for (int m = 0; m < n_members; ++m) { mix(&members[m].momentum_buf, sizeof(void*)); }
+    struct { const void* X; int64_t ldx, n_rows; int bs; const void* y; const void* grp; int D, H, C, G; float w; const void* T; float it, mo, wd; int first; const void* bws; } k =
+        {X, ldx, n_rows, batch_size, y, grp, D, H, C, G, ebd_weight, That, inv_tau, momentum, weight_decay, first_step, bws};
+    mix(&k, sizeof(k));
+    int device = 0;
+    DBMM_CUDA(cudaGetDevice(&device));
+    EpochKey key;
+    memset(&key, 0, sizeof(key));
+    key.X = (const void*)(uintptr_t)h; key.n_rows = -(int64_t)n_members; key.device = device; key.ws = bws;      // batched entries: negative n_rows
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : g_graphs)
+        if (memcmp(&g.key, &key, sizeof(key)) == 0) { exec = g.exec; g.stamp = ++g_graph_clock; break; }
+    if (!exec) {
+        DBMM_CHECK_ARG(device >= 0 && device < 64, "device index %d out of range", device);
+        if (!g_capture_stream[device]) DBMM_CUDA(cudaStreamCreateWithFlags(&g_capture_stream[device], cudaStreamNonBlocking));
+        cudaStream_t cs = g_capture_stream[device];
+        DBMM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue(cs);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) { set_error("stream capture of the batched epoch failed: %s", cudaGetErrorString(ce)); return DBMM_ERR_CUDA; }
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); return DBMM_ERR_CUDA; }
+        if (g_graphs.size() >= MAX_EPOCH_GRAPHS) {
+            size_t victim = 0;
+            for (size_t i = 1; i < g_graphs.size(); ++i) if (g_graphs[i].stamp < g_graphs[victim].stamp) victim = i;
+            cudaGraphExecDestroy(g_graphs[victim].exec);
+            g_graphs.erase(g_graphs.begin() + victim);
+        }
+        g_graphs.push_back(EpochGraph{key, exec, ++g_graph_clock});
+    }
+    DBMM_CUDA(cudaGraphLaunch(exec, st));
+    return DBMM_OK;
+}
+
 // ---- data parallel over one NVSwitch box: own NCCL communicator (rank 0 creates the id, the host broadcasts its 128 bytes)
 int dbmm_comm_unique_id(void* id_out_128_bytes) {
     DBMM_CHECK_ARG(id_out_128_bytes != nullptr, "NULL id buffer");
@@ -837,41 +1051,82 @@ int dbmm_comm_init(const void* id_128_bytes, int world, int rank, void** comm_ou
     if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", nc->GetErrorString(r)); delete c; return DBMM_ERR_CUDA; }
     *comm_out = c;
     // Symmetric buffers for the fused one-shot all-reduces: cudaMalloc + CUDA IPC, handles exchanged with ncclAllGather.
-    // Any failure leaves p2p_ok = false and the epoch falls back to NCCL all-reduces (same results).
+    // EVERY rank runs EVERY collective below whatever happened to it locally (a rank that skipped one would leave its peers
+    // blocked inside it), and the outcome is agreed with an all-reduce(min) of the local flags: either all ranks use the
+    // peer-memory exchange or all fall back to NCCL all-reduces (same results).  `world` and DBMM_P2P are the same everywhere.
     if (world > P2P_MAX_WORLD || world < 2 || !p2p_enabled()) return DBMM_OK;
-    do {
-        if (cudaMalloc((void**)&c->p2p_local, P2P_BYTES) != cudaSuccess) break;
-        if (cudaMemset(c->p2p_local, 0, P2P_BYTES) != cudaSuccess) break;
-        cudaIpcMemHandle_t mine;
-        if (cudaIpcGetMemHandle(&mine, c->p2p_local) != cudaSuccess) break;
-        char* dev_handles = nullptr;
-        if (cudaMalloc((void**)&dev_handles, sizeof(mine) * (size_t)world) != cudaSuccess) break;
-        bool ok = cudaMemcpy(dev_handles + sizeof(mine) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess;
-        ok = ok && nc->AllGather(dev_handles + sizeof(mine) * (size_t)rank, dev_handles, sizeof(mine), ncclUint8, c->nccl, 0) == ncclSuccess;
-        ok = ok && cudaStreamSynchronize(0) == cudaSuccess;
+    bool ok = cudaMalloc((void**)&c->p2p_local, P2P_BYTES) == cudaSuccess;
+    if (!ok) c->p2p_local = nullptr;
+    ok = ok && cudaMemset(c->p2p_local, 0, P2P_BYTES) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    ok = ok && cudaIpcGetMemHandle(&mine, c->p2p_local) == cudaSuccess;
+    char* dev_buf = nullptr;                     // [world handles][2 ints: agreement flags]
+    const size_t hb = sizeof(mine) * (size_t)world;
+    bool have_buf = cudaMalloc((void**)&dev_buf, hb + 2 * sizeof(int)) == cudaSuccess;
+    if (!have_buf) {                             // without a device buffer no collective can run at all: ranks may disagree only here,
+        cudaGetLastError();                      // and then the peers' collectives fail on this rank's absence rather than hang forever
+        set_error("dbmm_comm_init: cudaMalloc of the %zu-byte exchange buffer failed", hb + 2 * sizeof(int));
+        return DBMM_ERR_CUDA;
+    }
+    ok = ok && cudaMemcpy(dev_buf + sizeof(mine) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess;
+    bool coll = nc->AllGather(dev_buf + sizeof(mine) * (size_t)rank, dev_buf, sizeof(mine), ncclUint8, c->nccl, 0) == ncclSuccess;
+    coll = coll && cudaStreamSynchronize(0) == cudaSuccess;
+    // first agreement: did every rank publish a valid handle?
+    int flag = ok && coll ? 1 : 0;
+    cudaMemcpy(dev_buf + hb, &flag, sizeof(int), cudaMemcpyHostToDevice);
+    coll = nc->AllReduce(dev_buf + hb, dev_buf + hb, 1, ncclInt32, ncclMin, c->nccl, 0) == ncclSuccess && cudaStreamSynchronize(0) == cudaSuccess && coll;
+    int all_published = 0;
+    cudaMemcpy(&all_published, dev_buf + hb, sizeof(int), cudaMemcpyDeviceToHost);
+    ok = ok && coll && all_published == 1;
+    if (ok) {
         std::vector<cudaIpcMemHandle_t> all((size_t)world);
-        ok = ok && cudaMemcpy(all.data(), dev_handles, sizeof(mine) * (size_t)world, cudaMemcpyDeviceToHost) == cudaSuccess;
-        cudaFree(dev_handles);
-        if (!ok) break;
+        ok = cudaMemcpy(all.data(), dev_buf, hb, cudaMemcpyDeviceToHost) == cudaSuccess;
         for (int p = 0; p < world && ok; ++p) {
             if (p == rank) { c->p2p_peer[p] = c->p2p_local; continue; }
             void* ptr = nullptr;
             ok = cudaIpcOpenMemHandle(&ptr, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-            c->p2p_peer[p] = (char*)ptr;
+            c->p2p_peer[p] = ok ? (char*)ptr : nullptr;
         }
-        if (!ok) break;
-        // nobody may start pushing before every rank has mapped every buffer and zeroed its own
-        float* dummy = nullptr;
-        if (cudaMalloc((void**)&dummy, sizeof(float)) != cudaSuccess) break;
-        ok = nc->AllReduce(dummy, dummy, 1, ncclFloat32, ncclSum, c->nccl, 0) == ncclSuccess && cudaStreamSynchronize(0) == cudaSuccess;
-        cudaFree(dummy);
-        c->p2p_ok = ok;
-    } while (0);
-    if (!c->p2p_ok) cudaGetLastError();          // clear the sticky-free error state of the failed optional set-up
+    }
+    // second agreement (also the barrier: nobody may start pushing before every rank has mapped every buffer and zeroed its own)
+    flag = ok ? 1 : 0;
+    cudaMemcpy(dev_buf + hb + sizeof(int), &flag, sizeof(int), cudaMemcpyHostToDevice);
+    coll = nc->AllReduce(dev_buf + hb + sizeof(int), dev_buf + hb + sizeof(int), 1, ncclInt32, ncclMin, c->nccl, 0) == ncclSuccess &&
+           cudaStreamSynchronize(0) == cudaSuccess;
+    int all_mapped = 0;
+    cudaMemcpy(&all_mapped, dev_buf + hb + sizeof(int), sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(dev_buf);
+    c->p2p_ok = coll && all_mapped == 1;
+    if (!c->p2p_ok) {                            // agreed fallback: release whatever this rank had set up
+        for (int p = 0; p < world; ++p) {
+            if (p != rank && c->p2p_peer[p]) cudaIpcCloseMemHandle(c->p2p_peer[p]);
+            c->p2p_peer[p] = nullptr;
+        }
+        if (c->p2p_local) { cudaFree(c->p2p_local); c->p2p_local = nullptr; }
+        cudaGetLastError();                      // clear the error state of the failed optional set-up
+    }
     return DBMM_OK;
 }
 
 int dbmm_comm_has_p2p(void* comm) { return comm && ((DbmmComm*)comm)->p2p_ok ? 1 : 0; }
+
+// Synchronises the device and reports whether a peer-memory wait of an earlier epoch ran out of time (a rank never arrived,
+// see p2p.cuh): 0 = fine.  The training state after a timeout is undefined; the context stays usable.
+int dbmm_comm_check(void* comm) {
+    if (!comm) return DBMM_OK;
+    DbmmComm* c = (DbmmComm*)comm;
+    DBMM_CUDA(cudaDeviceSynchronize());
+    if (!c->p2p_ok || !c->p2p_local) return DBMM_OK;
+    unsigned err = 0;
+    DBMM_CUDA(cudaMemcpy(&err, c->p2p_local + sizeof(unsigned) * (size_t)(P2P_CHANNELS + 1) * 32, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (err) {
+        DBMM_CUDA(cudaMemset(c->p2p_local + sizeof(unsigned) * (size_t)(P2P_CHANNELS + 1) * 32, 0, sizeof(unsigned)));
+        set_error("a peer-memory wait timed out on rank %d (a rank did not reach the same epoch call within DBMM_P2P_TIMEOUT_S)", c->rank);
+        return DBMM_ERR_CUDA;
+    }
+    return DBMM_OK;
+}
 
 int dbmm_comm_destroy(void* comm) {
     if (!comm) return DBMM_OK;

@@ -23,7 +23,7 @@ struct Gemm1TcArgs {
     int B, D, H, nad;
     const float* Whi[2]; const float* Wlo[2]; const float* b1[2];   // per adapter, [H][D] / [H]
     float* A;          // [nad][B][H]
-    double* colsum;    // [nad][2][H] or nullptr
+    fx64* colsum;      // [nad][2][H] or nullptr (fixed point, FX_COLSUM)
     // eval epilogue (hhi != nullptr): h = relu(BN_running(a)) split into tf32 hi + lo, [nad][B][H] each, instead of A
     float* hhi; float* hlo;
     const float* bn_mean[2]; const float* bn_var[2]; const float* bn_gamma[2]; const float* bn_beta[2];
@@ -31,7 +31,7 @@ struct Gemm1TcArgs {
     float* part;       //      part[kpart][nad][B][H]; k_reduce_stats finishes the job
     int pack;          // data parallel: request only the used part of the stage ring (two CTAs may share an SM)
     int stages;        // set by the launcher: min(ring depth of the configuration, k-blocks per CTA)
-    double* zero_colsum; int zero_colsum_n;     // ksplit > 1 only: CTA 0 resets the column sums k_reduce_stats will accumulate
+    fx64* zero_colsum; int zero_colsum_n;       // ksplit > 1 only: CTA 0 resets the column sums k_reduce_stats will accumulate
 };
 
 __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ w, float* __restrict__ hi,
@@ -54,8 +54,9 @@ struct G1Cfg {
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// kz: D-slice of this CTA (blockIdx.z of the single-run launch; the batched launch keeps the member index there)
 template <int BN, int TERMS>
-__global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
+__device__ __forceinline__ void gemm1_tc_body(const Gemm1TcArgs& a, const int kz) {
     using Cfg = G1Cfg<BN, TERMS>;
     const int S = a.stages;                             // stage ring depth: the launch sizes the shared memory for it
     extern __shared__ uint8_t g1_smem_raw[];
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
     uint64_t* tmem_full = empty + S;
     uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
     __shared__ int64_t sRowOff[G1_BM];
-    __shared__ double sCol[2][BN];
+    __shared__ unsigned long long sCol[2][BN];          // fixed-point column sums of this CTA (integer adds commute)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * G1_BM;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
     const int n0 = (blockIdx.y - ad * slices) * BN;     // first hidden unit of this CTA
     const int KB_all = a.D / G1_BK;
     const int kb_per = (KB_all + a.ksplit - 1) / a.ksplit;
-    const int kb_lo = blockIdx.z * kb_per;
+    const int kb_lo = kz * kb_per;
     const int KB = max(0, min(KB_all, kb_lo + kb_per) - kb_lo);      // k-blocks of this CTA (host guarantees >= 1)
 
     if (tid < G1_BM) {
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
         // hit L2 instead of opening a DRAM page per slice (measured: 1.4 -> see profiles/ TB/s on the eval stream)
         if (blockIdx.y == 0 && m0 + tid < a.B) ptx::prefetch_l2_bulk(a.X + r * a.ldx + (size_t)kb_lo * G1_BK, (uint32_t)KB * G1_BK * 4);
     }
-    if (tid < BN) { sCol[0][tid] = 0.0; sCol[1][tid] = 0.0; }
+    if (tid < BN) { sCol[0][tid] = 0ull; sCol[1][tid] = 0ull; }
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { ptx::mbar_init(&full[s], G1_PRODUCERS); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(tmem_full, 1);
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
         }
     }
     ptx::pdl_wait();                // W1 hi / lo come from the previous step's update kernel
-    if (a.zero_colsum && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)       // (its chores CTA read the column sums)
-        for (int e = tid; e < a.zero_colsum_n; e += G1_THREADS) a.zero_colsum[e] = 0.0;
+    if (a.zero_colsum && blockIdx.x == 0 && blockIdx.y == 0 && kz == 0)       // (its chores CTA read the column sums)
+        for (int e = tid; e < a.zero_colsum_n; e += G1_THREADS) a.zero_colsum[e].v = 0;
     ptx::pdl_launch();
 
     if (warp < 4) {
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
             float v[32];
             if (a.ksplit > 1) {
                 if (row_ok) {
-                    float* prow = a.part + (((size_t)blockIdx.z * a.nad + ad) * a.B + m) * a.H + n0 + ch * 32;
+                    float* prow = a.part + (((size_t)kz * a.nad + ad) * a.B + m) * a.H + n0 + ch * 32;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<float4*>(prow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
@@ -215,15 +216,15 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
                 float s1 = 0.f, s2 = 0.f;
                 for (int rr = 0; rr < rows_here; ++rr) { const float x = scr[rr * 33 + lane]; s1 += x; s2 = fmaf(x, x, s2); }
                 __syncwarp();
-                atomicAdd(&sCol[0][ch * 32 + lane], (double)s1);
-                atomicAdd(&sCol[1][ch * 32 + lane], (double)s2);
+                atomicAdd(&sCol[0][ch * 32 + lane], fx_bits<FX_COLSUM>((double)s1));
+                atomicAdd(&sCol[1][ch * 32 + lane], fx_bits<FX_COLSUM>((double)s2));
             }
         }
         ptx::tc_fence_before_sync();
         asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
         if (a.ksplit == 1 && a.colsum && tid < BN) {
-            atomicAdd(&a.colsum[((size_t)ad * 2 + 0) * a.H + n0 + tid], sCol[0][tid]);
-            atomicAdd(&a.colsum[((size_t)ad * 2 + 1) * a.H + n0 + tid], sCol[1][tid]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&a.colsum[((size_t)ad * 2 + 0) * a.H + n0 + tid].v), sCol[0][tid]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&a.colsum[((size_t)ad * 2 + 1) * a.H + n0 + tid].v), sCol[1][tid]);
         }
     } else {
         // ===================== MMA issuer: one thread =====================
@@ -252,6 +253,9 @@ __global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) {
     __syncthreads();
     if (warp == 4) ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
+
+template <int BN, int TERMS>
+__global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) { gemm1_tc_body<BN, TERMS>(a, (int)blockIdx.z); }
 
 template <int BN, int TERMS>
 static int launch_gemm1_tc_impl(const Gemm1TcArgs& a, cudaStream_t st) {
@@ -291,16 +295,17 @@ struct ReduceStatsArgs {
     const float* part; int ksplit, nad, B, H;
     const float* b1[2];
     float* A;          // [nad][B][H]
-    double* colsum;    // [nad][2][H] or nullptr
+    fx64* colsum;      // [nad][2][H] or nullptr (fixed point, FX_COLSUM)
     P2pArgs p2p;       // data parallel over peer memory: the last CTA all-reduces the column sums in place (channel 0)
-    double* zero_dgb; int zero_dgb_n;           // fused step tail: CTA 0 resets (dgamma, dbeta) and all CTAs share the reset of
+    fx64* zero_dgb; int zero_dgb_n;             // fused step tail: CTA 0 resets (dgamma, dbeta), which the row kernel
     float* zero_S; int zero_S_n;                //                  S -- the row kernel accumulates both next
 };
 constexpr int RS_ROWS = 16, RS_MAXK = 16, RS_THREADS = 256;
 
 // 256 threads = 8 row lanes x 32 column quads (H <= 128), two rows per thread; the D-slice partials of one element are
 // fetched together (RS_MAXK independent 16-byte loads in flight) before they are summed.  Few, fat CTAs on purpose:
-// the fp64 column-sum atomics of all CTAs hit the same 2H addresses and the L2 serialises them (~40 cycles each).
+// the column-sum atomics (64-bit fixed point, see fx64) of all CTAs hit the same 2H addresses and the L2 serialises them
+// (~40 cycles each).
 __global__ void __launch_bounds__(RS_THREADS) k_reduce_stats(ReduceStatsArgs a) {
     __shared__ float sS[2][8][DBMM_MAX_H];
     const int H = a.H, H4 = H >> 2;
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_reduce_stats(ReduceStatsArgs a) 
     ptx::pdl_wait();
     ptx::pdl_launch();
     if (a.zero_dgb && blockIdx.x == 0 && blockIdx.y == 0)
-        for (int e = tid; e < a.zero_dgb_n; e += RS_THREADS) a.zero_dgb[e] = 0.0;
+        for (int e = tid; e < a.zero_dgb_n; e += RS_THREADS) a.zero_dgb[e].v = 0;
     if (a.zero_S) {
         const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
         for (int e = cta * RS_THREADS + tid; e < a.zero_S_n; e += ncta * RS_THREADS) a.zero_S[e] = 0.f;
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_reduce_stats(ReduceStatsArgs a) 
         double v = 0.0;
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) v += (double)sS[which][rr][j];
-        atomicAdd(&a.colsum[((size_t)ad * 2 + which) * H + j], v);
+        fx_add<FX_COLSUM>(&a.colsum[((size_t)ad * 2 + which) * H + j], v);
     }
     if (a.p2p.world) p2p_allreduce_when_last(a.p2p, 0, a.colsum, a.nad * 2 * H, gridDim.x * gridDim.y);
 }

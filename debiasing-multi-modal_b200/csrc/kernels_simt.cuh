@@ -42,13 +42,13 @@ struct Gemm1Args {
     int B, D, H, nad;
     const float* W1[2]; const float* b1[2];
     float* A;          // [nad][B][H]
-    double* colsum;    // [nad][2][H] or nullptr
+    fx64* colsum;      // [nad][2][H] or nullptr (fixed point, FX_COLSUM)
 };
 
 __global__ void __launch_bounds__(GT_THREADS) k_gemm1(Gemm1Args a) {
     __shared__ __align__(16) float smem[GT_SMEM_FLOATS];
     __shared__ int64_t sRow[GT_BM];
-    __shared__ double sCol[2][GT_BN];
+    __shared__ unsigned long long sCol[2][GT_BN];      // fixed-point column sums (integer adds commute: deterministic)
     const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * GT_BN;
     const int NT = a.nad * a.H;
     for (int i = threadIdx.x; i < GT_BM; i += GT_THREADS) {
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm1(Gemm1Args a) {
         int64_t r = -1;
         if (m < a.B) r = a.idx ? (int64_t)a.idx[a.pos0 + m] : (a.pos0 + m);
         sRow[i] = r;
-        if (i < GT_BN) { sCol[0][i] = 0.0; sCol[1][i] = 0.0; }
+        if (i < GT_BN) { sCol[0][i] = 0ull; sCol[1][i] = 0ull; }
     }
     __syncthreads();
     auto fa = [&](int m, int k) -> float {
@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm1(Gemm1Args a) {
             float v2 = s2[j] + __shfl_xor_sync(0xffffffffu, s2[j], 16);
             if ((threadIdx.x & 16) == 0) {
                 const int cl = (threadIdx.x % (GT_BN / GT_TN)) * GT_TN + j;
-                atomicAdd(&sCol[0][cl], (double)v1);
-                atomicAdd(&sCol[1][cl], (double)v2);
+                atomicAdd(&sCol[0][cl], fx_bits<FX_COLSUM>((double)v1));
+                atomicAdd(&sCol[1][cl], fx_bits<FX_COLSUM>((double)v2));
             }
         }
         __syncthreads();
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(GT_THREADS) k_gemm1(Gemm1Args a) {
             const int n = n0 + i;
             if (n < NT) {
                 const int ad = n / a.H, jj = n - ad * a.H;
-                atomicAdd(&a.colsum[((size_t)ad * 2 + 0) * a.H + jj], sCol[0][i]);
-                atomicAdd(&a.colsum[((size_t)ad * 2 + 1) * a.H + jj], sCol[1][i]);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&a.colsum[((size_t)ad * 2 + 0) * a.H + jj].v), sCol[0][i]);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&a.colsum[((size_t)ad * 2 + 1) * a.H + jj].v), sCol[1][i]);
             }
         }
     }
@@ -476,7 +476,7 @@ struct WgradArgs {
     const float* X; int64_t ldx; const int32_t* idx;
     int B; int64_t Bg; int D, H;
     const float* A; const float* dahat;
-    const double* colsum; const double* dgb; const float* gamma;
+    const fx64* colsum; const fx64* dgb; const float* gamma;      // fixed point (FX_COLSUM / FX_DGB)
     float* gW1;
     int tiles_m, tiles_n, ksplit;
 };
@@ -494,13 +494,13 @@ __global__ void __launch_bounds__(GT_THREADS) k_wgrad(WgradArgs a) {
         const int j = m0 + i;
         float mu = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
         if (j < H) {
-            const double m = a.colsum[j] / (double)a.Bg;
-            double v = a.colsum[H + j] / (double)a.Bg - m * m;
+            const double m = fx_get<FX_COLSUM>(&a.colsum[j]) / (double)a.Bg;
+            double v = fx_get<FX_COLSUM>(&a.colsum[H + j]) / (double)a.Bg - m * m;
             if (v < 0.0) v = 0.0;
             mu = (float)m; rstd = 1.0f / sqrtf((float)v + DBMM_BN_EPS);
             const double gm = (double)a.gamma[j];
-            m1 = (float)(gm * a.dgb[H + j] / (double)a.Bg);     // mean_B(dahat)       = gamma * dbeta  / B
-            m2 = (float)(gm * a.dgb[j] / (double)a.Bg);         // mean_B(dahat*ahat)  = gamma * dgamma / B
+            m1 = (float)(gm * fx_get<FX_DGB>(&a.dgb[H + j]) / (double)a.Bg);     // mean_B(dahat)       = gamma * dbeta  / B
+            m2 = (float)(gm * fx_get<FX_DGB>(&a.dgb[j]) / (double)a.Bg);         // mean_B(dahat*ahat)  = gamma * dgamma / B
         }
         sCst[0][i] = mu; sCst[1][i] = rstd; sCst[2][i] = m1; sCst[3][i] = m2;
     }

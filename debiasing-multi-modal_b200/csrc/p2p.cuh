@@ -1,9 +1,9 @@
 // Data-parallel exchanges of the training step over NVLink peer memory, fused into the kernels that produce and consume
 // the data: no collective launch, no kernel boundary, no NCCL inside the step.
 //
-//   channel 0  BatchNorm column sums [nad][2][H] fp64   k_reduce_stats: the LAST CTA to finish (atomic ticket) pushes the
+//   channel 0  BatchNorm column sums [nad][2][H] fx64   k_reduce_stats: the LAST CTA to finish (atomic ticket) pushes the
 //              rank's vector to the other ranks, polls theirs, adds in rank order, writes the global sums back in place
-//   channel 1  (dgamma, dbeta) [2][H] fp64              k_wgrad_tc: CTA (0, 0) pushes in its prologue, every CTA polls
+//   channel 1  (dgamma, dbeta) [2][H] fx64              k_wgrad_tc: CTA (0, 0) pushes in its prologue, every CTA polls
 //   dW1        [H][D] fp32                              k_tail_w1: every thread pushes its chunk-summed quad and polls the
 //              same quad of its peers; own quad from registers; no cross-CTA synchronisation at all
 //   S          [H+1+C][H+1] fp32                        k_tail_w2: CTA c stores slice c to every rank and raises flag
@@ -15,7 +15,10 @@
 // order, so the replicas stay bit-identical.  Slots are double-buffered by instance parity: a rank can run at most one
 // instance ahead of the slowest rank, because completing instance i needs every rank's data of instance i.  `base`
 // (device counter, bumped by k_p2p_bump after every epoch) makes instance numbers unique across replays of an epoch graph.
-// Bounded spins __trap() instead of hanging the GPU when a rank never arrives.
+// Waits are bounded by WALL CLOCK (%globaltimer; P2pArgs::timeout_ns, default 300 s, DBMM_P2P_TIMEOUT_S overrides): ordinary
+// rank skew (one rank writing a checkpoint, a first-time graph capture, a longer validation) just waits; a rank that never
+// arrives makes the waiter raise the error word of its own buffer and carry on, and the host reports it from
+// dbmm_comm_check() (the CUDA context stays usable).  Ranks must otherwise run in lock step: one epoch call per rank.
 // Buffers come from cudaMalloc + CUDA IPC (handles exchanged through the library's own NCCL communicator, dbmm_comm_init).
 #pragma once
 #include "common.cuh"
@@ -34,6 +37,7 @@ constexpr size_t P2P_LL_OFF = P2P_SF_OFF + (size_t)P2P_S_CTAS * 128;            
 constexpr size_t P2P_BYTES = P2P_LL_OFF + (size_t)P2P_CHANNELS * 2 * P2P_MAX_WORLD * P2P_VEC * 16;
 
 struct P2pArgs {
+    unsigned long long timeout_ns;   // wall-clock bound of every wait
     int world, rank;          // world == 0: disabled (single GPU, or NCCL all-reduces between the kernels)
     int step;                 // instance = *base + step
     int skip;                 // timing experiments only (DBMM_DP_SKIP): bit 0/1 sum only the own value of channel 0/1, bit 2 no
@@ -43,6 +47,21 @@ struct P2pArgs {
 
 __device__ __forceinline__ unsigned* p2p_ticket(char* buf, int ch) { return reinterpret_cast<unsigned*>(buf) + (size_t)ch * 32; }
 __device__ __forceinline__ unsigned* p2p_base(char* buf) { return reinterpret_cast<unsigned*>(buf) + (size_t)P2P_CHANNELS * 32; }
+__device__ __forceinline__ unsigned* p2p_error(char* buf) { return reinterpret_cast<unsigned*>(buf) + (size_t)(P2P_CHANNELS + 1) * 32; }
+__device__ __forceinline__ unsigned long long p2p_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// true when the wait that started at t0 has run out of time (raises the error word; checked every 1024 polls)
+__device__ __forceinline__ bool p2p_expired(const P2pArgs& p, unsigned long long& t0, unsigned spin) {
+    if ((spin & 1023u) != 1023u) return false;
+    const unsigned long long now = p2p_now();
+    if (t0 == 0) { t0 = now; return false; }
+    if (now - t0 < p.timeout_ns) return false;
+    atomicExch(p2p_error(p.peer[p.rank]), 1u);
+    return true;
+}
 __device__ __forceinline__ unsigned p2p_instance(const P2pArgs& p) { return __ldcg(p2p_base(p.peer[p.rank])) + (unsigned)p.step; }
 __global__ void k_p2p_bump(char* buf, unsigned steps) { *p2p_base(buf) += steps; }
 
@@ -50,20 +69,20 @@ __global__ void k_p2p_bump(char* buf, unsigned steps) { *p2p_base(buf) += steps;
 __device__ __forceinline__ unsigned long long* p2p_ll_slot(char* buf, int ch, int parity, int src) {
     return reinterpret_cast<unsigned long long*>(buf + P2P_LL_OFF) + ((((size_t)ch * 2 + parity) * P2P_MAX_WORLD + src) * P2P_VEC) * 2;
 }
-__device__ __forceinline__ void p2p_ll_store(unsigned long long* slot, int e, double v, unsigned tag) {
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+__device__ __forceinline__ void p2p_ll_store(unsigned long long* slot, int e, long long v, unsigned tag) {
+    const unsigned long long bits = (unsigned long long)v;
     const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)tag << 32);
     const unsigned long long w1 = (bits >> 32) | ((unsigned long long)tag << 32);
     asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 2 * (size_t)e), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ double p2p_ll_load(const unsigned long long* slot, int e, unsigned tag) {
-    unsigned long long w0 = 0, w1 = 0;
-    for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+__device__ __forceinline__ long long p2p_ll_load(const P2pArgs& p, const unsigned long long* slot, int e, unsigned tag) {
+    unsigned long long w0 = 0, w1 = 0, t0 = 0;
+    for (unsigned spin = 0;; ++spin) {
         asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot + 2 * (size_t)e) : "memory");
         if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
+        if (p2p_expired(p, t0, spin)) break;           // a rank never arrived: error word raised, the host reports it
     }
-    if ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) __trap();      // a rank never arrived: fail loudly, do not hang
-    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    return (long long)((w0 & 0xffffffffull) | (w1 << 32));
 }
 
 // Consumer side: the token (instance number) to pass to p2p_sum; the waiting happens per element there.
@@ -71,14 +90,14 @@ __device__ __forceinline__ int p2p_wait(const P2pArgs& p, int ch) {
     (void)ch;
     return (int)p2p_instance(p);
 }
-// Element e of the global vector: polls every rank's LL word pair until it carries this instance, sums in rank order
-// (every rank adds the same numbers in the same order: the replicas stay bit-identical).
-__device__ __forceinline__ double p2p_sum(const P2pArgs& p, int ch, int token, int e) {
+// Element e of the global vector: polls every rank's LL word pair until it carries this instance and adds the fixed-point
+// values (integer sums: every rank gets the same bits whatever the order; the replicas stay bit-identical).
+__device__ __forceinline__ long long p2p_sum(const P2pArgs& p, int ch, int token, int e) {
     char* me = p.peer[p.rank];
     const unsigned inst = (unsigned)token;
-    double s = 0.0;
-    if (p.skip & (1 << ch)) return p2p_ll_load(p2p_ll_slot(me, ch, inst & 1u, p.rank), e, inst + 1u);
-    for (int r = 0; r < p.world; ++r) s += p2p_ll_load(p2p_ll_slot(me, ch, inst & 1u, r), e, inst + 1u);
+    long long s = 0;
+    if (p.skip & (1 << ch)) return p2p_ll_load(p, p2p_ll_slot(me, ch, inst & 1u, p.rank), e, inst + 1u);
+    for (int r = 0; r < p.world; ++r) s += p2p_ll_load(p, p2p_ll_slot(me, ch, inst & 1u, r), e, inst + 1u);
     return s;
 }
 
@@ -86,7 +105,7 @@ __device__ __forceinline__ double p2p_sum(const P2pArgs& p, int ch, int token, i
 // CTA to finish (atomic ticket) pushes the rank's vector to every OTHER rank as LL words, polls theirs, adds everything
 // in rank order (own values from registers) and writes the global vector back over `local` -- the consumer kernels
 // read plain memory and need no peer-memory code at all.
-__device__ __forceinline__ void p2p_allreduce_when_last(const P2pArgs& p, int ch, double* local, int n, unsigned total_ctas) {
+__device__ __forceinline__ void p2p_allreduce_when_last(const P2pArgs& p, int ch, fx64* local, int n, unsigned total_ctas) {
     __shared__ unsigned s_last3;
     __threadfence();
     __syncthreads();
@@ -98,23 +117,23 @@ __device__ __forceinline__ void p2p_allreduce_when_last(const P2pArgs& p, int ch
     const unsigned inst = p2p_instance(p);
     const int parity = inst & 1u;
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        const double v = __ldcg(local + e);
+        const long long v = __ldcg(&local[e].v);
         for (int r = 0; r < p.world; ++r)
             if (r != p.rank) p2p_ll_store(p2p_ll_slot(p.peer[r], ch, parity, p.rank), e, v, inst + 1u);
-        double s = 0.0;
+        long long s = 0;
         for (int r = 0; r < p.world; ++r)
-            s += (r == p.rank || (p.skip & (1 << ch))) ? (r == p.rank ? v : 0.0) : p2p_ll_load(p2p_ll_slot(me, ch, parity, r), e, inst + 1u);
-        local[e] = s;
+            s += (r == p.rank || (p.skip & (1 << ch))) ? (r == p.rank ? v : 0ll) : p2p_ll_load(p, p2p_ll_slot(me, ch, parity, r), e, inst + 1u);
+        local[e].v = s;
     }
     if (threadIdx.x == 0) *p2p_ticket(me, ch) = 0u;
 }
 
 // k_wgrad_tc prologue: CTA (0, 0) pushes the rank's (dgamma, dbeta) to every rank INCLUDING itself; every CTA then sums
 // all ranks' LL slots with p2p_sum (the row kernel stays free of peer-memory code).
-__device__ __forceinline__ void p2p_push_now(const P2pArgs& p, int ch, const double* local, int n) {
+__device__ __forceinline__ void p2p_push_now(const P2pArgs& p, int ch, const fx64* local, int n) {
     const unsigned inst = p2p_instance(p);
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        const double v = __ldcg(local + e);
+        const long long v = __ldcg(&local[e].v);
         for (int r = 0; r < p.world; ++r) p2p_ll_store(p2p_ll_slot(p.peer[r], ch, inst & 1u, p.rank), e, v, inst + 1u);
     }
 }
@@ -129,16 +148,15 @@ __device__ __forceinline__ void p2p_g_store(unsigned long long* slot, int64_t i,
     asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 4 * i), "l"(w0), "l"(w1) : "memory");
     asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 4 * i + 2), "l"(w2), "l"(w3) : "memory");
 }
-__device__ __forceinline__ float4 p2p_g_load(const unsigned long long* slot, int64_t i, unsigned tag, bool no_wait) {
-    unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+__device__ __forceinline__ float4 p2p_g_load(const P2pArgs& p, const unsigned long long* slot, int64_t i, unsigned tag, bool no_wait) {
+    unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, t0 = 0;
     bool ok = false;
-    for (unsigned spin = 0; spin < (no_wait ? 1u : (1u << 26)); ++spin) {
+    for (unsigned spin = 0;; ++spin) {
         asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot + 4 * i) : "memory");
         asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(slot + 4 * i + 2) : "memory");
         ok = (unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag && (unsigned)(w2 >> 32) == tag && (unsigned)(w3 >> 32) == tag;
-        if (ok) break;
+        if (ok || no_wait || p2p_expired(p, t0, spin)) break;
     }
-    if (!ok && !no_wait) __trap();                    // a rank never arrived: fail loudly, do not hang
     return make_float4(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1), __uint_as_float((unsigned)w2), __uint_as_float((unsigned)w3));
 }
 __device__ __forceinline__ float* p2p_s_slot(char* buf, int parity, int src) {

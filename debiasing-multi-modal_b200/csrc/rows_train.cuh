@@ -1,10 +1,10 @@
 // Training row kernel (H-space, see kernels_simt.cuh header):  BatchNorm -> ReLU -> t = [h,1] G -> logits -> CE ->
-// row backward (dL/d ahat) -> per-batch reductions (dgamma, dbeta, S = [c*h | c | ds]^T [h | 1]) in ONE launch.
+// row backward (dL/d ahat) -> per-batch reductions (dgamma, dbeta) and the operand rows of S = [c*h | c | ds]^T [h | 1] in ONE launch.
 //
 // A CTA owns RT_ROWS = 8 batch rows and 16 warps.  The (H+1)-long contraction t = [h,1] G is split over the WARPS
 // (9 Gram rows each, all 8 batch rows at once, 40 accumulators per lane) and combined through shared memory, so the
 // dependent-FMA chain per warp is 9 long instead of 129.  Afterwards warp w < 8 finishes row w (softmax-CE, argmax,
-// group counters, dh, BatchNorm-backward inputs), and all warps add the CTA's 8-row share of S with coalesced reds.
+// group counters, dh, BatchNorm-backward inputs), and all warps store the CTA's 8 operand rows of S.
 #pragma once
 #include "kernels_simt.cuh"
 #include "ptx_sm100.cuh"
@@ -19,11 +19,15 @@ struct RowsTrainArgs {
     int H, C, G;
     const float* A; int64_t strideA;      // [nad][B][H]
     const float* gram;                    // [nad][H+1][H+1+C]
-    const double* colsum;                 // [nad][2][H]
+    const fx64* colsum;                   // [nad][2][H] (fixed point, FX_COLSUM)
     AdapterView ad[2];
     float w_old, inv_tau, inv_B;
     double* loss_sum; int64_t* counts; int64_t slot;
-    float* dahat; double* dgb; float* S;  // outputs: [B][H], [2][H] (+=), [H+1+C][H+1] (+=)
+    float* dahat; fx64* dgb;              // outputs: [B][H], [2][H] (+=, FX_DGB)
+    float* logits_out;                    // optional [B][C]: the batch's logits (train-mode nn.Module forward, modules.py)
+    const float* dlogits_in;              // optional [B][C]: upstream dL/dlogits replaces the fused CE gradient (autograd backward)
+    float* Lrows; float* Hrows;           // outputs: [B][l_stride] rows [c*h | c | ds] and [B][s_stride] rows [h | 1]: the operands
+                                          // of S = L^T [h | 1] (k_tn_gemm on the second graph branch)
 };
 
 static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT, int RT_WARPS) {
@@ -35,7 +39,7 @@ static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT, int RT
 }
 
 template <int NAD, int CT, int NW>
-__global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
+__device__ __forceinline__ void rows_train_body(const RowsTrainArgs& a) {
     constexpr int RT_WARPS = NW, RT_THREADS = NW * 32;
     extern __shared__ __align__(16) float dyn_smem[];
     const int H = a.H, C = a.C, ldg = H + 1 + C, HP = H + 1;
@@ -49,7 +53,6 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
     int* sRowG = reinterpret_cast<int*>(sRowNll + 32);
     int* sRowCorr = sRowG + 32;
     float* sLo = reinterpret_cast<float*>(sRowCorr + 32);                // [RT_ROWS][CT]
-    float* sDgb = sLo + (size_t)RT_ROWS * CT;                            // [2][H]
     constexpr int TSTR = RK_NSLOT * 32;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
     if (warp < RT_ROWS && blockIdx.x * RT_ROWS + warp < a.B) {
         const int r = blockIdx.x * RT_ROWS + warp;
         const int64_t dsrow = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
-        y_pre = a.y[dsrow];
+        y_pre = a.y ? a.y[dsrow] : -1;
         g_pre = a.grp ? a.grp[dsrow] : 0;
     }
     ptx::pdl_wait();                // A / column sums come from k_reduce_stats; the Gram matrix is two kernels upstream
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
     }
     for (int e = tid; e < NAD * H; e += RT_THREADS) {
         const int ad = e / H, j = e - ad * H;
-        const double s1 = a.colsum[((size_t)ad * 2 + 0) * H + j], s2 = a.colsum[((size_t)ad * 2 + 1) * H + j];
+        const double s1 = fx_get<FX_COLSUM>(&a.colsum[((size_t)ad * 2 + 0) * H + j]), s2 = fx_get<FX_COLSUM>(&a.colsum[((size_t)ad * 2 + 1) * H + j]);
         const double m = s1 / (double)a.Bg;
         double v = s2 / (double)a.Bg - m * m;
         if (v < 0.0) v = 0.0;
@@ -93,7 +96,6 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
         bn[j] = (float)m; bn[H + j] = 1.0f / sqrtf((float)v + DBMM_BN_EPS);
         bn[2 * H + j] = a.ad[ad].gamma[j]; bn[3 * H + j] = a.ad[ad].beta[j];
     }
-    for (int e = tid; e < 2 * H; e += RT_THREADS) sDgb[e] = 0.f;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
             if (base == (int)blockIdx.x * RT_ROWS) { yv = y_pre; gval = g_pre; }
             else {
                 const int64_t dsrow = a.idx ? (int64_t)a.idx[r] : (int64_t)r;
-                yv = a.y[dsrow];
+                yv = a.y ? a.y[dsrow] : -1;
                 gval = a.grp ? a.grp[dsrow] : 0;
             }
         }
@@ -245,10 +247,17 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
             corr = (am == yv) ? 1 : 0;
             const float inv_se = 1.0f / se;
             float dot = 0.f;
+            if (a.logits_out && lane < C) {
+                float v = 0.f;
+#pragma unroll
+                for (int c = 0; c < CT; ++c) if (c == lane) v = l[c];
+                a.logits_out[(size_t)r * C + lane] = v;
+            }
 #pragma unroll
             for (int c = 0; c < CT; ++c) {
                 if (c < C) {
-                    const float dl = (p[c] * inv_se - (c == yv ? 1.f : 0.f)) * a.inv_B;
+                    const float dl = a.dlogits_in ? __ldg(a.dlogits_in + (size_t)r * C + c)
+                                                  : (p[c] * inv_se - (c == yv ? 1.f : 0.f)) * a.inv_B;
                     dot = fmaf(dl, lnew[c], dot);
                     dsv[c] = coef * dl * a.inv_tau * inv_n;
                 }
@@ -308,45 +317,39 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) {
                 }
             }
         }
-        // ---- phase 4: S[m][n] += sum_rows L[row][m] * [h | 1][row][n]   (warp w owns MR rows m; lanes own n)
+        // ---- phase 4: the rows' operands of S = L^T [h | 1] go to global memory, coalesced (the batch reduction itself is a
+        // small tensor-core GEMM off the critical path; round 1 issued 17 K fp32 atomics per CTA here)
         {
-            float Rr[RT_ROWS][RK_NSLOT];
-#pragma unroll
-            for (int rr = 0; rr < RT_ROWS; ++rr)
-#pragma unroll
-                for (int s = 0; s < RK_NSLOT; ++s) {
-                    const int n = lane + 32 * s;
-                    Rr[rr][s] = (n < HP) ? sH[(size_t)rr * HP + n] : 0.f;
-                }
-            const int m0 = warp * MR, m1 = min(ldg, m0 + MR), SP = s_stride(H);
-            for (int m = m0; m < m1; ++m) {
-                float v[RK_NSLOT];
-#pragma unroll
-                for (int s = 0; s < RK_NSLOT; ++s) v[s] = 0.f;
-#pragma unroll
-                for (int rr = 0; rr < RT_ROWS; ++rr) {
-                    const float l = sL[(size_t)rr * ldg + m];
-#pragma unroll
-                    for (int s = 0; s < RK_NSLOT; ++s) v[s] = fmaf(l, Rr[rr][s], v[s]);
-                }
-#pragma unroll
-                for (int s = 0; s < RK_NSLOT; ++s) {
-                    const int n = lane + 32 * s;
-                    if (n < HP) atomicAdd(&a.S[(size_t)m * SP + n], v[s]);
-                }
+            const int LDL = l_stride(H, C), LDH = s_stride(H);
+            for (int e = tid; e < RT_ROWS * ldg; e += RT_THREADS) {
+                const int rr = e / ldg, c = e - rr * ldg;
+                if (base + rr < a.B) a.Lrows[(size_t)(base + rr) * LDL + c] = sL[(size_t)rr * ldg + c];
+            }
+            for (int e = tid; e < RT_ROWS * HP; e += RT_THREADS) {
+                const int rr = e / HP, c = e - rr * HP;
+                if (base + rr < a.B) a.Hrows[(size_t)(base + rr) * LDH + c] = sH[(size_t)rr * HP + c];
             }
         }
         __syncthreads();
     }
 
+    // (dgamma, dbeta): one slot per warp (sT is free now), summed over the warps in a fixed order, then one fixed-point
+    // atomic per element and CTA -- nothing here depends on the order in which warps or CTAs arrive
 #pragma unroll
     for (int s = 0; s < RK_HSLOT; ++s) {
         const int j = lane + 32 * s;
-        if (s < HS && j < H) { atomicAdd(&sDgb[j], dg_acc[s]); atomicAdd(&sDgb[H + j], db_acc[s]); }
+        if (s < HS && j < H) { sT[(size_t)warp * 2 * H + j] = dg_acc[s]; sT[(size_t)warp * 2 * H + H + j] = db_acc[s]; }
     }
     __syncthreads();
-    for (int e = tid; e < 2 * H; e += RT_THREADS) atomicAdd(&a.dgb[e], (double)sDgb[e]);
+    for (int e = tid; e < 2 * H; e += RT_THREADS) {
+        float v = 0.f;
+        for (int w2 = 0; w2 < RT_WARPS; ++w2) v += sT[(size_t)w2 * 2 * H + e];
+        fx_add<FX_DGB>(&a.dgb[e], (double)v);
+    }
 }
+
+template <int NAD, int CT, int NW>
+__global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) { rows_train_body<NAD, CT, NW>(a); }
 
 static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) {
     const int CT = ra.C <= 4 ? 4 : 16;

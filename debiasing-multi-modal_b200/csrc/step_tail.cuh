@@ -6,9 +6,9 @@
 //       ("chores": k_wgrad_tc reads gamma, so not earlier): dgamma / dbeta / db1 -> SGD on b1 / gamma / beta, BatchNorm
 //       running statistics (final_main.py:122,574: the frozen adapter drifts too).
 //   k_tail_w2 (second branch: forked after k_rows_train, joined before the NEXT step's k_rows_train):
-//       per CTA 64 / 32 / 16 embedding rows: dW2a = [W2 | b2 | That] S -> SGD on W2 / b2 -> the rows' share of the next
-//       Gram matrix G = [W2 | b2]^T [W2 | b2 | That] (fp32 reds into the other half of a double buffer; this step's half,
-//       consumed by k_rows_train, is re-zeroed here).
+//       per CTA 64 / 32 / 16 embedding rows: dW2a = [W2 | b2 | That] S -> SGD on W2 / b2.  The same branch computes S before
+//       it and the next step's Gram matrix G = [W2 | b2]^T [W2 | b2 | That] after it (k_tn_gemm: one CTA per output tile,
+//       no atomics, bit-reproducible).
 // The per-step accumulators are re-zeroed by the NEXT step's head kernels (column sums: k_gemm1_tc; dgamma / dbeta and S:
 // k_reduce_stats), never here: k_wgrad_tc reads them while the W2 branch runs.  SGD as torch.optim.SGD
 // (demo/util.py:118-136): g += wd*p; v = momentum*v + g; p -= lr*v (the caller zeroes v before the optimizer's first
@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "p2p.cuh"
+#include "tn_gemm.cuh"
 
 namespace dbmm {
 
@@ -33,9 +34,8 @@ struct StepTailArgs {
     const float* lr_dev; float lr; float momentum, wd;
     const float* part; int nchunk;            // [nchunk][H][D] batch-chunk partials of dW1
     float* whi; float* wlo;                   // tf32 split of the new W1
-    const float* That; const float* S;        // [D][C]; [H+1+C][s_stride(H)]
-    float* gram_next; float* gram_zero;       // trainable adapter's Gram matrix: next step's (+=) and this step's (reset)
-    const double* dgb; const double* colsum;  // [2][H]; [nad][2][H]
+    const float* That; const float* S;        // [D][C]; [H+1+C][s_stride(H)] (k_tn_gemm's output)
+    const fx64* dgb; const fx64* colsum;      // [2][H] (FX_DGB); [nad][2][H] (FX_COLSUM)
     int D, H, C, nad; int64_t Bg;
     float* rm[2]; float* rv[2]; long long* nbt[2];
     int n_w1_ctas, n_w2_ctas;
@@ -50,7 +50,7 @@ static inline size_t step_tail_smem_bytes(int H, int C) {
 
 // ---- role bit 0: W1 CTAs + one chores CTA
 template <bool P2P>
-__global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
+__device__ __forceinline__ void tail_w1_body(const StepTailArgs& a) {
     const int H = a.H, D = a.D;
     const int tid = threadIdx.x;
     const float lr = a.lr_dev ? __ldg(a.lr_dev) : a.lr;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
                 for (int c = 0; c < ST_MAXCHUNK; ++c) pt[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int c = 0; c < P2P_MAX_WORLD; ++c)
-                    if (c < a.p2p.world) pt[c] = c == a.p2p.rank ? mine : p2p_g_load(p2p_g_ll(me, parity, c), i, inst + 1u, (a.p2p.skip & 4) != 0);
+                    if (c < a.p2p.world) pt[c] = c == a.p2p.rank ? mine : p2p_g_load(a.p2p, p2p_g_ll(me, parity, c), i, inst + 1u, (a.p2p.skip & 4) != 0);
             }
             const float4 pv = i == i0 ? pv0 : reinterpret_cast<const float4*>(a.W1)[i];
             const float4 vv = i == i0 ? vv0 : reinterpret_cast<const float4*>(a.v + oW1)[i];
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
         const int seg = e / H, j = e - seg * H;
         float* pp = (seg == 0 ? a.b1 : (seg == 1 ? a.gamma : a.beta)) + j;
         const size_t fo = ob1 + e;
-        const float graw = seg == 0 ? 0.f : (float)a.dgb[(size_t)(seg - 1) * H + j];
+        const float graw = seg == 0 ? 0.f : (float)fx_get<FX_DGB>(&a.dgb[(size_t)(seg - 1) * H + j]);
         const float pv = *pp;
         const float g = graw + a.wd * pv;
         const float vn = a.momentum * a.v[fo] + g;
@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
     }
     for (int e = tid; e < a.nad * H; e += ST_THREADS) {
         const int ad = e / H, j = e - ad * H;
-        const double m = a.colsum[((size_t)ad * 2 + 0) * H + j] / (double)a.Bg;
-        double var = a.colsum[((size_t)ad * 2 + 1) * H + j] / (double)a.Bg - m * m;
+        const double m = fx_get<FX_COLSUM>(&a.colsum[((size_t)ad * 2 + 0) * H + j]) / (double)a.Bg;
+        double var = fx_get<FX_COLSUM>(&a.colsum[((size_t)ad * 2 + 1) * H + j]) / (double)a.Bg - m * m;
         if (var < 0.0) var = 0.0;
         const float unbiased = (float)(var * (double)a.Bg / (double)(a.Bg - 1));
         a.rm[ad][j] = (1.0f - DBMM_BN_MOMENTUM) * a.rm[ad][j] + DBMM_BN_MOMENTUM * (float)m;
@@ -141,26 +141,13 @@ __global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) {
     if (tid < a.nad) *a.nbt[tid] += 1;
 }
 
-// ---- role bit 1: W2 / b2 rows [d0, d0 + ST2_ROWS):  dW2a[d][n] = sum_k L[d][k] S[k][n],  L = [W2 | b2 | That], then the
-// rows' share of the next Gram matrix.  Both small contractions run on the tensor cores as warp-level mma.sync m16n8k8
-// with 3xTF32 split operands (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~2^-20 relative, the policy of DESIGN.md 3.2);
-// 64-row tiles off the critical path do not warrant a tcgen05 / TMEM pipeline.
-__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(x) & 0xffffe000u;                 // tf32-exact head; the tensor core ignores the 13 low bits of lo
-    lo = __float_as_uint(x - __uint_as_float(hi));         // (|lo| < 2^-10 |x|, truncated at 2^-21 |x|)
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
-                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
-    mma_tf32(c, al, bh);
-    mma_tf32(c, ah, bl);
-    mma_tf32(c, ah, bh);
-}
+template <bool P2P>
+__global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) { tail_w1_body<P2P>(a); }
 
+// ---- role bit 1: W2 / b2 rows [d0, d0 + ST2_ROWS):  dW2a[d][n] = sum_k L[d][k] S[k][n],  L = [W2 | b2 | That], then SGD on
+// those rows.  The contraction runs on the tensor cores as warp-level mma.sync m16n8k8 with 3xTF32 split operands
+// (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~2^-20 relative, the policy of DESIGN.md 3.2); 64-row tiles off the critical
+// path do not warrant a tcgen05 / TMEM pipeline.
 static inline size_t step_tail_w2_smem(int rows) { return sizeof(float) * ((size_t)ST2_K8MAX * ST2_SP + (size_t)rows * ST2_LP) + 16; }
 // Embedding rows per W2-role CTA.  Measured on B200 (scripts/dp_time.py, scripts/train_only.py): one GPU runs best with 16
 // fat CTAs on the ~20 SMs the 128-CTA kernels of the main branch leave free (41 us/step); under data parallelism the role
@@ -173,7 +160,7 @@ static inline int step_tail_w2_rows(bool dp) {
 }
 
 template <bool P2P, int ST2_ROWS>
-__global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
+__device__ __forceinline__ void tail_w2_body(const StepTailArgs& a) {
     extern __shared__ __align__(16) float st_smem[];
     const int H = a.H, D = a.D, C = a.C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -183,14 +170,12 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
     const int KT = (K + 7) >> 3, K8 = KT * 8;                          // k-steps of the dW2a contraction
     constexpr int LP = ST2_LP, SP = ST2_SP;
     const int w2 = blockIdx.x;
-    {   // this step's Gram matrix has been consumed by k_rows_train: reset it for the step after next
-        const int nz = N * K;
-        for (int e = w2 * ST2_THREADS + tid; e < nz; e += (int)gridDim.x * ST2_THREADS) a.gram_zero[e] = 0.f;
-    }
     float* sS = st_smem;                        // [K8][SP], zero padded
-    float* sL = sS + (size_t)ST2_K8MAX * SP;    // [ST2_ROWS][LP], zero padded; after the update: the NEW [W2 | b2 | That] rows
+    float* sL = sS + (size_t)ST2_K8MAX * SP;    // [ST2_ROWS][LP], zero padded: the rows' [W2 | b2 | That]
     const int d0 = w2 * ST2_ROWS;
     const int n4row = NPg >> 2;                 // 16-byte chunks per row of S
+    ptx::pdl_wait();        // S comes from k_tn_gemm, the kernel in front of this one on its stream (programmatic launch)
+    ptx::pdl_launch();
     if constexpr (P2P) {
         // Data parallel: this CTA pushes its slice of the rank's S to every rank (off the critical path), raises S flag
         // [cta][rank] everywhere, then waits for every slice of every rank and sums the slots in rank order.
@@ -211,11 +196,11 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
         if (tid < (int)gridDim.x * a.p2p.world) {
             const unsigned* f = p2p_s_flag(a.p2p.peer[a.p2p.rank], tid / a.p2p.world, tid % a.p2p.world);
             unsigned v = 0;
-            for (unsigned spin = 0; spin < ((a.p2p.skip & 8) ? 1u : (1u << 28)); ++spin) {
+            unsigned long long t0 = 0;
+            for (unsigned spin = 0;; ++spin) {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                if ((int)(v - (inst + 1u)) >= 0) break;
+                if ((int)(v - (inst + 1u)) >= 0 || (a.p2p.skip & 8) || p2p_expired(a.p2p, t0, spin)) break;
             }
-            if ((int)(v - (inst + 1u)) < 0 && !(a.p2p.skip & 8)) __trap();
         }
         __syncthreads();
         char* me = a.p2p.peer[a.p2p.rank];
@@ -301,7 +286,6 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
             }
         }
     }
-    __syncthreads();                             // every warp is done reading the OLD rows in sL
     // SGD on the owned elements (c fragment: rows r0 / r0 + 8, columns n, n + 1); the new values replace the old in sL
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
@@ -321,46 +305,18 @@ __global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) {
                 *reinterpret_cast<float2*>(a.W2 + fo) = make_float2(q0, q1);
                 *reinterpret_cast<float2*>(a.v + oW2 + fo) = make_float2(v0, v1);
                 *reinterpret_cast<float2*>(a.g + oW2 + fo) = make_float2(g0, g1);
-                lrow[n] = q0; lrow[n + 1] = q1;
             } else if (n == H) {
                 const float p0 = lrow[H];
                 const float v0 = a.momentum * vv[j][hh].x + (g0 + a.wd * p0);
                 const float q0 = p0 - lr * v0;
                 a.b2[d] = q0; a.v[ob2 + d] = v0; a.g[ob2 + d] = g0;
-                lrow[H] = q0;
-            }
-        }
-    }
-    __syncthreads();
-    // ---- Gram share of the new rows: G[m][n] += sum_r L[r][m] L[r][n]  (m < N, n < K), 16 x 8 tiles dealt round-robin
-    const int ldg = K, MT = (N + 15) >> 4, NT2 = (K + 7) >> 3;
-    for (int tile = warp; tile < MT * NT2; tile += ST2_THREADS / 32) {
-        const int gm = tile / NT2, gn = tile - gm * NT2;
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int ks = 0; ks < ST2_ROWS / 8; ++ks) {
-            const float* ra = sL + (size_t)(ks * 8 + t) * LP;
-            const float* rb = ra + 4 * LP;
-            uint32_t ah[4], al[4], bh[2], bl[2];
-            tf32_split(ra[gm * 16 + g], ah[0], al[0]);
-            tf32_split(ra[gm * 16 + g + 8], ah[1], al[1]);
-            tf32_split(rb[gm * 16 + g], ah[2], al[2]);
-            tf32_split(rb[gm * 16 + g + 8], ah[3], al[3]);
-            tf32_split(ra[gn * 8 + g], bh[0], bl[0]);
-            tf32_split(rb[gn * 8 + g], bh[1], bl[1]);
-            mma_3xtf32(c, ah, al, bh, bl);
-        }
-        const int n = gn * 8 + 2 * t;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int m = gm * 16 + g + 8 * hh;
-            if (m < N) {
-                if (n < ldg) atomicAdd(&a.gram_next[(size_t)m * ldg + n], c[2 * hh]);
-                if (n + 1 < ldg) atomicAdd(&a.gram_next[(size_t)m * ldg + n + 1], c[2 * hh + 1]);
             }
         }
     }
 }
+
+template <bool P2P, int ST2_ROWS>
+__global__ void __launch_bounds__(ST2_THREADS) k_tail_w2(StepTailArgs a) { tail_w2_body<P2P, ST2_ROWS>(a); }
 
 static inline bool step_tail_supported(int D, int H, int C) {
     return H % 4 == 0 && D % 4 == 0 && H <= 128 && (H + 1 + C) <= ST2_K8MAX - 7 && s_stride(H) <= ST2_SP &&
@@ -370,8 +326,10 @@ static inline bool step_tail_supported(int D, int H, int C) {
 static int launch_step_tail(StepTailArgs a, cudaStream_t st) {
     DBMM_CHECK_SHAPE(step_tail_supported(a.D, a.H, a.C), "step tail kernels: unsupported D=%d H=%d C=%d", a.D, a.H, a.C);
     DBMM_CHECK_ARG(a.nchunk <= ST_MAXCHUNK, "at most %d batch chunks (got %d)", ST_MAXCHUNK, a.nchunk);
+#ifdef DBMM_EXPERIMENTS
     static const int skip_roles = getenv("DBMM_TAIL_SKIP") ? atoi(getenv("DBMM_TAIL_SKIP")) : 0;      // timing experiments only
     a.roles &= ~skip_roles;
+#endif
     a.n_w1_ctas = ceil_div((int64_t)a.H * a.D / 4, ST_THREADS);
     if (a.n_w1_ctas > 128) a.n_w1_ctas = 128;
     const int w2_rows = step_tail_w2_rows(a.p2p.world > 1);
@@ -388,7 +346,7 @@ static int launch_step_tail(StepTailArgs a, cudaStream_t st) {
 #define DBMM_W2_LAUNCH(P2P_, ROWS_)                                                         \
         do {                                                                                \
             DBMM_CUDA(set_smem(k_tail_w2<P2P_, ROWS_>, smem));                              \
-            k_tail_w2<P2P_, ROWS_><<<a.n_w2_ctas, ST2_THREADS, smem, st>>>(a);              \
+            DBMM_CUDA(launch_pdl(k_tail_w2<P2P_, ROWS_>, dim3(a.n_w2_ctas), dim3(ST2_THREADS), smem, st, a));  \
         } while (0)
         if (p2p) { if (w2_rows == 64) DBMM_W2_LAUNCH(true, 64); else if (w2_rows == 32) DBMM_W2_LAUNCH(true, 32); else DBMM_W2_LAUNCH(true, 16); }
         else { if (w2_rows == 64) DBMM_W2_LAUNCH(false, 64); else if (w2_rows == 32) DBMM_W2_LAUNCH(false, 32); else DBMM_W2_LAUNCH(false, 16); }

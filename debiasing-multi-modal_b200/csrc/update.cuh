@@ -2,8 +2,7 @@
 // v = momentum*v + g; p -= lr*v -- the caller zeroes v before the optimizer's first step, which makes v = g) fused
 // with everything the NEXT training step needs from the new weights:
 //   * W1 CTAs also emit the tf32 split W1 = hi + lo consumed by the tensor-core GEMM-1,
-//   * W2 CTAs keep their updated rows in shared memory and add their share of the Gram matrix
-//     G = [W2 | b2]^T [W2 | b2 | That]  (zeroed by k_finalize_grads) with coalesced fp32 reds,
+//   * (the Gram matrix G = [W2 | b2]^T [W2 | b2 | That] of the new weights follows as a k_tn_gemm launch),
 //   * the last CTA updates b1 / gamma / beta, the BatchNorm running statistics of every adapter in the forward
 //     (the frozen one drifts too, final_main.py:122,574) and re-zeroes the per-step accumulators.
 #pragma once
@@ -20,9 +19,9 @@ struct UpdateArgs {
     const float* lr_dev; float lr;            // lr_dev != nullptr: learning rate read from device memory
     float momentum, wd;
     float* whi; float* wlo;                   // [H][D] tf32 split of the new W1, or nullptr
-    const float* That; float* gram;           // [D][C], [(H+1)][(H+1+C)] (+=), or gram == nullptr
+    const float* That;                        // [D][C]
     int D, H, C, nad; int64_t Bg;
-    double* colsum; double* dgb; float* S;    // per-step accumulators (read for the running stats, then zeroed)
+    fx64* colsum; fx64* dgb;                  // per-step fixed-point accumulators (read for the running stats, then zeroed)
     int zero_accum;
     float* rm[2]; float* rv[2]; long long* nbt[2];
     int n_w1_ctas, n_w2_ctas;
@@ -110,54 +109,6 @@ __global__ void __launch_bounds__(UP_THREADS) k_update(UpdateArgs a) {
                 sRow[e] = out;
             }
         }
-        if (!a.gram) return;
-        __syncthreads();
-        // Gram rows: warp w owns m in [16w, 16w + 16) (16-byte operand reads) and warp 7 also the last row m = H
-        constexpr int MW = 16;
-        float acc[MW][UP_NSLOT], accx[UP_NSLOT];
-#pragma unroll
-        for (int s = 0; s < UP_NSLOT; ++s) accx[s] = 0.f;
-#pragma unroll
-        for (int m = 0; m < MW; ++m)
-#pragma unroll
-            for (int s = 0; s < UP_NSLOT; ++s) acc[m][s] = 0.f;
-        const int m0 = warp * MW;
-        for (int r = 0; r < UP_ROWS; ++r) {
-            const float* row = sRow + (size_t)r * LP;
-            float bv[UP_NSLOT];
-#pragma unroll
-            for (int s = 0; s < UP_NSLOT; ++s) { const int n = lane + 32 * s; bv[s] = n < ldg ? row[n] : 0.f; }
-            const float ax = row[H];
-#pragma unroll
-            for (int s = 0; s < UP_NSLOT; ++s) accx[s] = fmaf(ax, bv[s], accx[s]);
-#pragma unroll
-            for (int m4 = 0; m4 < MW; m4 += 4) {
-                float4 am = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m0 + m4 < H) am = *reinterpret_cast<const float4*>(row + m0 + m4);      // H % 4 == 0
-                const float amx[4] = {am.x, am.y, am.z, am.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int s = 0; s < UP_NSLOT; ++s) acc[m4 + q][s] = fmaf(amx[q], bv[s], acc[m4 + q][s]);
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < MW; ++m) {
-            if (m0 + m >= H) break;
-#pragma unroll
-            for (int s = 0; s < UP_NSLOT; ++s) {
-                const int n = lane + 32 * s;
-                if (n < ldg) atomicAdd(&a.gram[(size_t)(m0 + m) * ldg + n], acc[m][s]);
-            }
-        }
-        if (warp == UP_THREADS / 32 - 1) {
-#pragma unroll
-            for (int s = 0; s < UP_NSLOT; ++s) {
-                const int n = lane + 32 * s;
-                if (n < ldg) atomicAdd(&a.gram[(size_t)H * ldg + n], accx[s]);
-            }
-        }
-        (void)HP;
         return;
     }
     // ---- last CTA: b1 / gamma / beta, BatchNorm running statistics, accumulator reset
@@ -174,8 +125,8 @@ __global__ void __launch_bounds__(UP_THREADS) k_update(UpdateArgs a) {
     if (a.colsum) {
         for (int e = tid; e < a.nad * H; e += UP_THREADS) {
             const int ad = e / H, j = e - ad * H;
-            const double m = a.colsum[((size_t)ad * 2 + 0) * H + j] / (double)a.Bg;
-            double var = a.colsum[((size_t)ad * 2 + 1) * H + j] / (double)a.Bg - m * m;
+            const double m = fx_get<FX_COLSUM>(&a.colsum[((size_t)ad * 2 + 0) * H + j]) / (double)a.Bg;
+            double var = fx_get<FX_COLSUM>(&a.colsum[((size_t)ad * 2 + 1) * H + j]) / (double)a.Bg - m * m;
             if (var < 0.0) var = 0.0;
             const float unbiased = (float)(var * (double)a.Bg / (double)(a.Bg - 1));
             a.rm[ad][j] = (1.0f - DBMM_BN_MOMENTUM) * a.rm[ad][j] + DBMM_BN_MOMENTUM * (float)m;
@@ -185,10 +136,26 @@ __global__ void __launch_bounds__(UP_THREADS) k_update(UpdateArgs a) {
     }
     if (a.zero_accum) {
         __syncthreads();
-        for (int e = tid; e < a.nad * 2 * H; e += UP_THREADS) a.colsum[e] = 0.0;
-        for (int e = tid; e < 2 * H; e += UP_THREADS) a.dgb[e] = 0.0;
-        for (int e = tid; e < (H + 1 + C) * s_stride(H); e += UP_THREADS) a.S[e] = 0.f;
+        for (int e = tid; e < a.nad * 2 * H; e += UP_THREADS) a.colsum[e].v = 0;
+        for (int e = tid; e < 2 * H; e += UP_THREADS) a.dgb[e].v = 0;
     }
+}
+
+// BatchNorm running statistics of a train-mode forward that is NOT followed by the fused update (nn.Module forward under
+// torch autograd, modules.py): running_mean / running_var (unbiased, momentum 0.1) and num_batches_tracked, as torch does.
+struct BnRunningArgs { const fx64* colsum; int nad, H; int64_t Bg; float* rm[2]; float* rv[2]; long long* nbt[2]; };
+__global__ void __launch_bounds__(256) k_bn_running(BnRunningArgs a) {
+    const int H = a.H;
+    for (int e = threadIdx.x; e < a.nad * H; e += 256) {
+        const int ad = e / H, j = e - ad * H;
+        const double m = fx_get<FX_COLSUM>(&a.colsum[((size_t)ad * 2 + 0) * H + j]) / (double)a.Bg;
+        double var = fx_get<FX_COLSUM>(&a.colsum[((size_t)ad * 2 + 1) * H + j]) / (double)a.Bg - m * m;
+        if (var < 0.0) var = 0.0;
+        const float unbiased = (float)(var * (double)a.Bg / (double)(a.Bg - 1));
+        a.rm[ad][j] = (1.0f - DBMM_BN_MOMENTUM) * a.rm[ad][j] + DBMM_BN_MOMENTUM * (float)m;
+        a.rv[ad][j] = (1.0f - DBMM_BN_MOMENTUM) * a.rv[ad][j] + DBMM_BN_MOMENTUM * unbiased;
+    }
+    if (threadIdx.x < a.nad) *a.nbt[threadIdx.x] += 1;
 }
 
 static int launch_update(UpdateArgs a, cudaStream_t st) {

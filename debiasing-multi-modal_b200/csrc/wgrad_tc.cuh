@@ -30,14 +30,14 @@ struct WgradTcArgs {
     int B; int64_t Bg; int D, H;
     const float* A;        // [B][H] pre-BatchNorm activations of the trainable adapter
     const float* dahat;    // [B][H]
-    const double* colsum;  // [2][H] sum a, sum a^2 (global batch)
-    const double* dgb;     // [2][H] dgamma, dbeta (global batch)
+    const fx64* colsum;    // [2][H] sum a, sum a^2 (global batch; fixed point, FX_COLSUM)
+    const fx64* dgb;       // [2][H] dgamma, dbeta (global batch; fixed point, FX_DGB)
     const float* gamma;
     float* part;           // [nchunk][H][D]
     int rows_per_chunk;    // multiple of WG_BK
     int pack;              // data parallel: request only the used part of the stage ring
     int stages;            // set by the launcher: min(WG_STAGES, 64-row sub-tiles per chunk)
-    P2pArgs p2p; double* dgb_wb;   // data parallel over peer memory: global dgamma / dbeta in (channel 1), written back by CTA (0, 0)
+    P2pArgs p2p; fx64* dgb_wb;     // data parallel over peer memory: global dgamma / dbeta in (channel 1), written back by CTA (0, 0)
 };
 
 // byte offset of the 16-byte chunk (4 floats) `c16` (0..31 along the 128-float MN extent) of K-row `row` (0..63)
@@ -59,7 +59,7 @@ __device__ __forceinline__ uint64_t wg_desc(uint32_t smem_addr) {
     return d;
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
+__device__ __forceinline__ void wgrad_tc_body(const WgradTcArgs& a) {
     extern __shared__ uint8_t wg_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)wg_smem_raw + 1023) & ~(uintptr_t)1023);
     const int NST = a.stages;                   // stage ring depth (1 when the chunk is a single 64-row sub-tile: 97 KB per CTA)
@@ -154,16 +154,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     if (tid < WG_TILE) {
         float mu = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
         if (tid < H) {
-            const double m = a.colsum[tid] / (double)a.Bg;
-            double v = a.colsum[H + tid] / (double)a.Bg - m * m;
+            const double m = fx_get<FX_COLSUM>(&a.colsum[tid]) / (double)a.Bg;
+            double v = fx_get<FX_COLSUM>(&a.colsum[H + tid]) / (double)a.Bg - m * m;
             if (v < 0.0) v = 0.0;
             mu = (float)m; rstd = 1.0f / sqrtf((float)v + DBMM_BN_EPS);
             const double gm = (double)a.gamma[tid];
             double dg, db;
             if (a.p2p.world) {
-                dg = p2p_sum(a.p2p, 1, dgb_parity, tid); db = p2p_sum(a.p2p, 1, dgb_parity, H + tid);
-                if (blockIdx.x == 0 && blockIdx.y == 0) { a.dgb_wb[tid] = dg; a.dgb_wb[H + tid] = db; }
-            } else { dg = a.dgb[tid]; db = a.dgb[H + tid]; }
+                const long long dgi = p2p_sum(a.p2p, 1, dgb_parity, tid), dbi = p2p_sum(a.p2p, 1, dgb_parity, H + tid);
+                if (blockIdx.x == 0 && blockIdx.y == 0) { a.dgb_wb[tid].v = dgi; a.dgb_wb[H + tid].v = dbi; }
+                dg = fx_val<FX_DGB>(dgi); db = fx_val<FX_DGB>(dbi);
+            } else { dg = fx_get<FX_DGB>(&a.dgb[tid]); db = fx_get<FX_DGB>(&a.dgb[H + tid]); }
             m1 = (float)(gm * db / (double)a.Bg);
             m2 = (float)(gm * dg / (double)a.Bg);
         }
@@ -237,6 +238,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) {
     if (warp == 4) ptx::tmem_dealloc<WG_TILE>(tmem_base);
 }
 
+__global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) { wgrad_tc_body(a); }
+
 static inline int wgrad_tc_chunks(int B, int* rows_per_chunk) {
     // ~16 batch chunks (128 CTAs at D = 1024), each a multiple of the 64-row stage
     int rpc = (B + 15) / 16;
@@ -263,7 +266,7 @@ static int launch_wgrad_tc(const WgradTcArgs& a, int nchunk, cudaStream_t st) {
 struct FinalizeArgs {
     const float* part; int nchunk;        // [nchunk][H][D], or nullptr when gW1 was produced directly
     const float* W2; const float* b2; const float* That; const float* S;   // S: [H+1+C][s_stride(H)]
-    const double* dgb;
+    const fx64* dgb;
     float* gW1; float* gb1; float* ggamma; float* gbeta; float* gW2; float* gb2;
     int D, H, C;
     int n_w1_ctas;
@@ -305,8 +308,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) 
             for (int e = blockIdx.x * FIN_THREADS + tid; e < a.gram_floats; e += a.n_w1_ctas * FIN_THREADS) a.gram_zero[e] = 0.f;
         if (blockIdx.x == 0) {
             for (int j = tid; j < H; j += FIN_THREADS) {
-                a.ggamma[j] = (float)(a.dgb[j] * (double)a.gb_scale);
-                a.gbeta[j] = (float)(a.dgb[H + j] * (double)a.gb_scale);
+                a.ggamma[j] = (float)(fx_get<FX_DGB>(&a.dgb[j]) * (double)a.gb_scale);
+                a.gbeta[j] = (float)(fx_get<FX_DGB>(&a.dgb[H + j]) * (double)a.gb_scale);
                 // db1 = sum_B da vanishes identically (BatchNorm removes the bias); the reference's value is autograd
                 // rounding noise (|db1| ~ 1e-9, tests/test_oracle_golden.py), so b1 moves by weight decay only.
                 a.gb1[j] = 0.f;
@@ -320,6 +323,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) 
     float* sS = fin_smem;                       // [KP][NP]
     float* sL = sS + (size_t)KP * NP;           // [FIN_ROWS][KP]
     const int d0 = ((int)blockIdx.x - a.n_w1_ctas) * FIN_ROWS;
+    ptx::pdl_wait();                // S comes from k_tn_gemm, which may directly precede this kernel
+    ptx::pdl_launch();
     {   // S is stored with row stride NP: whole 16-byte chunks, everything in flight at once
         const int n4 = K * NP / 4;
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sS);
@@ -334,8 +339,6 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_grads(FinalizeArgs a) 
         sL[e] = v;
     }
     ptx::cp_async_wait<0>();
-    ptx::pdl_wait();                // S, W2, b2, That are all at least two kernels upstream: nothing waited for so far
-    ptx::pdl_launch();
     __syncthreads();
     const int ncq = NP >> 2;                                // column quads
     if (tid >= (FIN_ROWS / 4) * ncq) return;

@@ -41,13 +41,14 @@ def _check_criterion(criterion):
 
 
 _persistent: dict = {}
+_member_tag = None          # set by the lock-step sweep driver (sweep.py): members keep separate order / statistics buffers
 
 
 def _order_to_device(base, rows):
     """Batch order on the device, in a per-(device, length) buffer that keeps its address from epoch to epoch: the
     epoch's CUDA graph inside libdbmm is cached by argument addresses."""
     n = len(rows)
-    key = ("order", str(base.device), n)
+    key = ("order", _member_tag, str(base.device), n)
     buf = _persistent.get(key)
     if buf is None:
         buf = _persistent[key] = torch.empty(n, dtype=torch.int32, device=base.device)
@@ -56,7 +57,7 @@ def _order_to_device(base, rows):
 
 
 def _stats_buffers(n_slots, n_groups, device, tag):
-    key = ("stats", tag, str(device), n_slots, n_groups)
+    key = ("stats", _member_tag, tag, str(device), n_slots, n_groups)
     st = _persistent.get(key)
     if st is None:
         st = _persistent[key] = ops.BatchStatsBuffers(n_slots, n_groups, device=device)
@@ -93,42 +94,93 @@ def _print_batches(opt, print_label, epoch, n_batches, losses_b, accs_b, elapsed
     sys.stdout.flush()
 
 
+class TrainJob:
+    """One training epoch of one model, prepared (batch order drawn, learning-rate table built, buffers chosen) but not yet
+    run.  The epoch functions below are generators that yield their job: `drive` runs it on the spot (the stand-alone
+    path, identical to calling dbmm_train_epoch directly); the lock-step sweep driver (sweep.py) collects the jobs of all
+    members and runs those with the same signature as ONE dbmm_train_epoch_batched call."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def signature(self):
+        """Jobs with equal signatures share data, shapes, prompts and hyper-parameters and can run in lock step."""
+        if self.linear:
+            return None
+        return (self.base.x.data_ptr(), self.labels.data_ptr(), self.n, self.bs, self.old is None, self.prompt_key,
+                float(self.inv_tau), float(self.w), float(self.optimizer.momentum), float(self.optimizer.weight_decay),
+                bool(self.optimizer.buffers.first_step), self.ad.D, self.ad.H)
+
+    def member(self):
+        return ops.SweepMember(order=self.order, ad=self.ad, buf=self.optimizer.buffers, stats=self.stats, lrs=self.lrs,
+                               old_ad=self.old, ws=getattr(self.optimizer, "_sweep_ws", None))
+
+    def run(self):
+        base = self.base
+        if self.linear:
+            c, o = self.classifier, self.optimizer
+            ops.linear_train_epoch(base.x, self.order, self.bs, self.labels, base.labels["group"], c.fc.weight.data, c.fc.bias.data,
+                                   o.grads, o.momentum_buf, self.lrs, self.stats, first_step=o.first_step, G=base.n_groups,
+                                   momentum=o.momentum, weight_decay=o.weight_decay)
+            o.first_step = False
+            return
+        ops.train_epoch(base.x, self.order, self.bs, self.labels, base.labels["group"], self.ad, self.That, self.inv_tau,
+                        self.optimizer.buffers, self.lrs, self.stats, old_ad=self.old, ebd_weight=self.w, G=base.n_groups,
+                        momentum=self.optimizer.momentum, weight_decay=self.optimizer.weight_decay)
+
+
+def run_jobs_batched(jobs):
+    """Jobs of equal signature() in one lock-step call; their statistics land in each job's own buffers."""
+    j0 = jobs[0]
+    members = [j.member() for j in jobs]
+    ops.train_epoch_batched(j0.base.x, members, j0.bs, j0.labels, j0.base.labels["group"], j0.That, j0.inv_tau, ebd_weight=j0.w,
+                            G=j0.base.n_groups, momentum=j0.optimizer.momentum, weight_decay=j0.optimizer.weight_decay)
+    for j, m in zip(jobs, members):
+        j.optimizer._sweep_ws = m.ws              # the member keeps its workspace (and so its epoch-graph key) across epochs
+
+
+def drive(gen):
+    """Run an epoch / training generator to completion, executing every TrainJob it yields immediately."""
+    try:
+        job = next(gen)
+        while True:
+            job.run()
+            job = gen.send(None)
+    except StopIteration as e:
+        return e.value
+
+
 def _run_train_epoch(opt, loader, classifier, optimizer, target, use_group, warm_fn, get_yp_func, print_label, epoch,
                      count_metrics=True):
+    """Generator: prepares the epoch, yields its TrainJob, then reads the statistics back."""
     classifier.train()
     base, rows = loader.base_rows(loader.draw_order())
     n = len(rows)
     bs = loader.batch_size
     sizes = _batch_sizes(n, bs)
     lrs = _lr_table(len(sizes), optimizer, warm_fn)
-    if hasattr(classifier, "fc"):                                 # linear probing (final_main.py:43-49)
-        stats = _stats_buffers(len(sizes), base.n_groups, base.device, "train")
-        t0 = time.time()
-        ops.linear_train_epoch(base.x, _order_to_device(base, rows), bs, base.labels[target], base.labels["group"],
-                               classifier.fc.weight.data, classifier.fc.bias.data, optimizer.grads, optimizer.momentum_buf,
-                               lrs, stats, first_step=optimizer.first_step, G=base.n_groups, momentum=optimizer.momentum,
-                               weight_decay=optimizer.weight_decay)
-        optimizer.first_step = False
-        loss_sum, counts = stats.host()
-        return loss_sum, counts, sizes, time.time() - t0
-    old, ad, w = classifier.kernel_adapters()
-    That = classifier.prompt_matrix(use_group=use_group)
-    labels = base.labels["group"] if use_group else base.labels[target]
     stats = _stats_buffers(len(sizes), base.n_groups, base.device, "train")
     t0 = time.time()
-    ops.train_epoch(base.x, _order_to_device(base, rows), bs, labels, base.labels["group"], ad, That,
-                    1.0 / classifier.temperature, optimizer.buffers, lrs, stats, old_ad=old, ebd_weight=w,
-                    G=base.n_groups, momentum=optimizer.momentum, weight_decay=optimizer.weight_decay)
+    if hasattr(classifier, "fc"):                                 # linear probing (final_main.py:43-49)
+        job = TrainJob(linear=True, base=base, order=_order_to_device(base, rows), n=n, bs=bs, lrs=lrs, stats=stats,
+                       labels=base.labels[target], classifier=classifier, optimizer=optimizer)
+    else:
+        old, ad, w = classifier.kernel_adapters()
+        job = TrainJob(linear=False, base=base, order=_order_to_device(base, rows), n=n, bs=bs, lrs=lrs, stats=stats,
+                       labels=base.labels["group"] if use_group else base.labels[target], classifier=classifier,
+                       optimizer=optimizer, old=old, ad=ad, w=w, That=classifier.prompt_matrix(use_group=use_group),
+                       prompt_key=(classifier.text_group_embedding_dir, "group") if use_group else (classifier.text_embedding_dir, "class"),
+                       inv_tau=1.0 / classifier.temperature)
+    yield job
     loss_sum, counts = stats.host()
-    elapsed = time.time() - t0
-    return loss_sum, counts, sizes, elapsed
+    return loss_sum, counts, sizes, time.time() - t0
 
 
-def train_one_epoch(opt, train_loader, classifier, criterion, optimizer, epoch, get_yp_func, target,
-                    print_label='Train', predict_group=True):
-    """Stage-1 / plain adapter epoch (final_main.py:426-496)."""
+def train_one_epoch_gen(opt, train_loader, classifier, criterion, optimizer, epoch, get_yp_func, target,
+                        print_label='Train', predict_group=True):
+    """Stage-1 / plain adapter epoch (final_main.py:426-496), as a generator that yields its TrainJob."""
     _check_criterion(criterion)
-    loss_sum, counts, sizes, elapsed = _run_train_epoch(
+    loss_sum, counts, sizes, elapsed = yield from _run_train_epoch(
         opt, train_loader, classifier, optimizer, target, False,
         lambda idx: warmup_learning_rate(opt, epoch, idx, len(train_loader), optimizer), get_yp_func, print_label, epoch)
     losses, acc, acc_groups = replay_epoch(loss_sum, counts, sizes, _n_groups(train_loader))
@@ -137,13 +189,18 @@ def train_one_epoch(opt, train_loader, classifier, criterion, optimizer, epoch, 
     return losses.avg, acc.avg, group_acc
 
 
-def train_reg_seq_one_epoch(opt, train_loader, classifier, criterion, optimizer, epoch, get_yp_func, target,
-                            print_label='Train', predict_group=True, use_group=False):
+def train_one_epoch(*a, **k):
+    """final_main.train_one_epoch (426-496): same arguments and return value."""
+    return drive(train_one_epoch_gen(*a, **k))
+
+
+def train_reg_seq_one_epoch_gen(opt, train_loader, classifier, criterion, optimizer, epoch, get_yp_func, target,
+                                print_label='Train', predict_group=True, use_group=False):
     """Stage-2 epoch on the held-out regularisation split (final_main.py:571-653): labels are the group ids when
     `use_group`, and the warm-up hook is the `_reg` one with the stage-relative epoch."""
     _check_criterion(criterion)
     rel_epoch = epoch - opt.epochs_feature_learning
-    loss_sum, counts, sizes, elapsed = _run_train_epoch(
+    loss_sum, counts, sizes, elapsed = yield from _run_train_epoch(
         opt, train_loader, classifier, optimizer, target, use_group,
         lambda idx: warmup_learning_rate_reg(opt, rel_epoch, idx, len(train_loader), optimizer),
         get_yp_func, print_label, epoch)
@@ -153,15 +210,20 @@ def train_reg_seq_one_epoch(opt, train_loader, classifier, criterion, optimizer,
     return losses.avg, acc.avg, group_acc
 
 
-def train_reg_one_epoch(opt, train_loader1, train_loader2, classifier, criterion, optimizer, epoch, get_yp_func, target,
-                        group_prompt=True, print_label='Train'):
+def train_reg_seq_one_epoch(*a, **k):
+    """final_main.train_reg_seq_one_epoch (571-653): same arguments and return value."""
+    return drive(train_reg_seq_one_epoch_gen(*a, **k))
+
+
+def train_reg_one_epoch_gen(opt, train_loader1, train_loader2, classifier, criterion, optimizer, epoch, get_yp_func, target,
+                            group_prompt=True, print_label='Train'):
     """`adapter_reg` epoch (final_main.py:498-569): a pass over the train loader with class prompts, then a pass
-    over the reg loader with group (or class) prompts, one optimizer; only the first pass feeds the meters."""
+    over the reg loader with group (or class) prompts, one optimizer; passes with class prompts feed the meters."""
     _check_criterion(criterion)
     n_groups = _n_groups(train_loader1)
     merged = None
     for loader, use_group in ((train_loader1, False), (train_loader2, group_prompt)):
-        loss_sum, counts, sizes, _ = _run_train_epoch(
+        loss_sum, counts, sizes, _ = yield from _run_train_epoch(
             opt, loader, classifier, optimizer, target, use_group is True,
             lambda idx, L=loader: warmup_learning_rate(opt, epoch, idx, len(L), optimizer), get_yp_func, print_label, epoch)
         if use_group is False:
@@ -172,6 +234,11 @@ def train_reg_one_epoch(opt, train_loader1, train_loader2, classifier, criterion
     group_acc = train_group_acc(acc_groups, get_yp_func)
     print(f"{print_label}:", str(group_acc))
     return losses.avg, acc.avg, group_acc
+
+
+def train_reg_one_epoch(*a, **k):
+    """final_main.train_reg_one_epoch (498-569): same arguments and return value."""
+    return drive(train_reg_one_epoch_gen(*a, **k))
 
 
 def _run_eval(loader, classifier, target, spurious_prompts=False):

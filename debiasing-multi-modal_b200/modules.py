@@ -8,8 +8,11 @@ and state_dict keys as the reference (final_main.py:43-174):
 
 The torch modules only OWN the tensors (so state_dict / load_state_dict / deepcopy / .cuda() behave as in
 the reference and a checkpoint written here loads into the reference's classes with strict=True).  All
-arithmetic goes through libdbmm.so: `forward` in eval mode runs the fused eval kernel, training runs through
-`engine.train_one_epoch` & co. which call the fused train-step kernels on the same storage.
+arithmetic goes through libdbmm.so: `forward` in eval mode runs the fused eval kernel; `forward` in train mode is a
+torch.autograd.Function over dbmm_train_forward / dbmm_train_backward, so the REFERENCE's own training loop
+(output = classifier(x); loss = criterion(output, y); loss.backward(); optimizer.step(), final_main.py:455-466) runs
+unchanged on these modules with a stock torch optimizer; the fast path is `engine.train_one_epoch` & co., which run the
+whole epoch (forward, CE, backward, SGD) in the fused kernels on the same storage.
 """
 from __future__ import annotations
 
@@ -64,8 +67,15 @@ class Adapter(nn.Module):
                                   lin2.weight.data, lin2.bias.data)
 
     def forward(self, features):
-        raise NotImplementedError("the un-normalised D-wide adapter output is never materialised on the B200 path; "
-                                  "call CustomCLIP / MultipleAdapter forward (logits) instead")
+        """The un-normalised adapter output [N, D] (final_main.py:173-174).  Eval mode: the export kernel (running-stat
+        BatchNorm), which is what the visualisation notebooks call (`classifier.adapter(embeddings)`,
+        demo/demo_visualization.ipynb:1146).  The training loops never need it: the D-wide activation is not
+        materialised on the fused path (CustomCLIP / MultipleAdapter .forward return logits straight from the kernels).
+        Train mode is kept for interface completeness as the plain torch composition of the four layers."""
+        if self.training:
+            return self.layers(features)
+        out, _, _ = ops.export_embeddings(features.contiguous(), self.tensors())
+        return out
 
 
 class _PromptMixin:
@@ -105,6 +115,34 @@ class _PromptMixin:
         return new
 
 
+class _TrainLogits(torch.autograd.Function):
+    """Train-mode forward of CustomCLIP / MultipleAdapter under torch autograd: logits from dbmm_train_forward (batch-stat
+    BatchNorm, running statistics moved), parameter gradients from dbmm_train_backward.  Only the trainable adapter's six
+    tensors get gradients (the frozen adapter of a MultipleAdapter and the embeddings do not, as in the reference:
+    final_main.py:128 `.detach()` on the old features, 455 `embeddings.detach()`)."""
+
+    @staticmethod
+    def forward(ctx, x, That, inv_tau, old_ad, w, ad, W1, b1, gamma, beta, W2, b2):
+        x = x.detach().contiguous()
+        logits = ops.train_forward(x, ad, That, inv_tau, old_ad=old_ad, ebd_weight=w)
+        ctx.x, ctx.That, ctx.inv_tau, ctx.old_ad, ctx.w, ctx.ad = x, That, inv_tau, old_ad, w, ad
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ad = ctx.ad
+        g = ops.train_backward(ctx.x, ad, ctx.That, ctx.inv_tau, dlogits.contiguous().float(), old_ad=ctx.old_ad, ebd_weight=ctx.w)
+        sl = ops.flat_param_slices(ad.D, ad.H)
+        return (None, None, None, None, None, None, g[sl["W1"]].view(ad.H, ad.D), g[sl["b1"]], g[sl["gamma"]], g[sl["beta"]],
+                g[sl["W2"]].view(ad.D, ad.H), g[sl["b2"]])
+
+
+def _train_logits(x, adapter_module, That, inv_tau, old_ad=None, w=0.5):
+    lin1, bn, lin2 = adapter_module.layers[0], adapter_module.layers[1], adapter_module.layers[3]
+    return _TrainLogits.apply(x, That, inv_tau, old_ad, w, adapter_module.tensors(), lin1.weight, lin1.bias, bn.weight, bn.bias,
+                              lin2.weight, lin2.bias)
+
+
 def _no_label_eval(x, ad, That, inv_tau, old_ad=None, w=0.5):
     x = x.contiguous()
     logits, _ = ops.eval_fwd(x, None, None, ad, That, inv_tau, None, max(1, x.shape[0]), old_ad=old_ad, ebd_weight=w,
@@ -136,13 +174,13 @@ class CustomCLIP(nn.Module, _PromptMixin):
         return None, self.adapter.tensors(), 0.5
 
     def forward(self, features, use_group=False):
-        if self.training:
-            raise NotImplementedError("train-mode forward goes through engine.train_one_epoch (fused step)")
+        if self.training:      # the reference's own loop (final_main.py:455-466) runs on this: autograd over the kernels
+            return _train_logits(features, self.adapter, self.prompt_matrix(use_group), 1.0 / self.temperature)
         return _no_label_eval(features, self.adapter.tensors(), self.prompt_matrix(use_group), 1.0 / self.temperature)
 
     def forward_spurious(self, features):
         if self.training:
-            raise NotImplementedError("train-mode forward goes through engine.train_one_epoch (fused step)")
+            return _train_logits(features, self.adapter, self.prompt_matrix(spurious=True), 1.0 / self.temperature)
         return _no_label_eval(features, self.adapter.tensors(), self.prompt_matrix(spurious=True), 1.0 / self.temperature)
 
 
@@ -174,13 +212,13 @@ class MultipleAdapter(nn.Module, _PromptMixin):
         return self.old_cls.adapter.tensors(), self.new_adapter.tensors(), float(self.ebd_weight)
 
     def forward(self, features, use_group=False):
-        if self.training:
-            raise NotImplementedError("train-mode forward goes through engine.train_reg_seq_one_epoch (fused step)")
         old, new, w = self.kernel_adapters()
+        if self.training:      # both adapters run batch-stat BatchNorm, only the new one gets gradients (final_main.py:121-140)
+            return _train_logits(features, self.new_adapter, self.prompt_matrix(use_group), 1.0 / self.temperature, old_ad=old, w=w)
         return _no_label_eval(features, new, self.prompt_matrix(use_group), 1.0 / self.temperature, old_ad=old, w=w)
 
     def forward_spurious(self, features):
-        if self.training:
-            raise NotImplementedError("train-mode forward goes through engine.train_reg_seq_one_epoch (fused step)")
         old, new, w = self.kernel_adapters()
+        if self.training:
+            return _train_logits(features, self.new_adapter, self.prompt_matrix(spurious=True), 1.0 / self.temperature, old_ad=old, w=w)
         return _no_label_eval(features, new, self.prompt_matrix(spurious=True), 1.0 / self.temperature, old_ad=old, w=w)

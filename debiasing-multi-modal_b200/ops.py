@@ -213,6 +213,40 @@ def train_step(X, y, grp, ad: AdapterTensors, That, inv_tau, buf: TrainBuffers, 
         buf.first_step = False
 
 
+def train_forward(X, ad: AdapterTensors, That, inv_tau, *, old_ad=None, ebd_weight=0.5, update_running_stats=True):
+    """Train-mode logits [B, C] (batch-statistics BatchNorm; running statistics moved as torch does): the forward half of
+    the nn.Module boundary, final_main.py:66-80 / 121-140 under classifier.train()."""
+    lib = _lib.load()
+    _check(X, torch.float32, "X", contiguous=False)
+    _check(That, torch.float32, "That")
+    if X.stride(1) != 1:
+        raise DbmmError("X rows must be contiguous")
+    B, D, H, Cn = X.shape[0], X.shape[1], ad.H, That.shape[1]
+    nad = 2 if old_ad is not None else 1
+    ws = workspace(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, B, D, H, Cn, nad), X.device)
+    logits = torch.empty((B, Cn), dtype=torch.float32, device=X.device)
+    old_p = old_ad.ptrs() if old_ad is not None else None
+    _lib.check(lib.dbmm_train_forward(X.data_ptr(), X.stride(0), None, B, D, H, Cn, C.byref(old_p) if old_p is not None else None,
+                                      C.byref(ad.ptrs()), ebd_weight, That.data_ptr(), inv_tau, logits.data_ptr(),
+                                      1 if update_running_stats else 0, ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return logits
+
+
+def train_backward(X, ad: AdapterTensors, That, inv_tau, dlogits, *, old_ad=None, ebd_weight=0.5):
+    """Flat gradient (W1 | b1 | gamma | beta | W2 | b2) of the trainable adapter from dL/dlogits [B, C]."""
+    lib = _lib.load()
+    _check(dlogits, torch.float32, "dlogits")
+    B, D, H, Cn = X.shape[0], X.shape[1], ad.H, That.shape[1]
+    nad = 2 if old_ad is not None else 1
+    ws = workspace(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, B, D, H, Cn, nad), X.device)
+    grads = torch.empty(param_count(D, H), dtype=torch.float32, device=X.device)
+    old_p = old_ad.ptrs() if old_ad is not None else None
+    _lib.check(lib.dbmm_train_backward(X.data_ptr(), X.stride(0), None, B, D, H, Cn, C.byref(old_p) if old_p is not None else None,
+                                       C.byref(ad.ptrs()), ebd_weight, That.data_ptr(), inv_tau, dlogits.data_ptr(), grads.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return grads
+
+
 def train_workspace_bytes(batch_size: int, D: int, H: int, Cn: int, nad: int = 1) -> int:
     return int(_lib.load().dbmm_workspace_bytes(_lib.OP_TRAIN, batch_size, D, H, Cn, nad))
 
@@ -243,6 +277,74 @@ def train_epoch(X, order: torch.Tensor, batch_size: int, y, grp, ad: AdapterTens
                                     lrs.ctypes.data_as(C.POINTER(C.c_float)), momentum, weight_decay,
                                     1 if buf.first_step else 0, stats.c(), ws.data_ptr(), ws.numel(), _stream_ptr()))
     buf.first_step = False
+    return steps
+
+
+@dataclass
+class SweepMember:
+    """One member of a batched sweep epoch (dbmm_member): its own batch order, adapters, optimizer state, statistics slots
+    and workspace; the data, batch size and prompts are shared with the other members."""
+    order: torch.Tensor                     # int32 [n_rows] on the device
+    ad: AdapterTensors
+    buf: "TrainBuffers"
+    stats: "BatchStatsBuffers"
+    lrs: np.ndarray                         # [steps]
+    old_ad: AdapterTensors | None = None
+    ws: torch.Tensor | None = None          # uint8 workspace (allocated on first use, kept by the member)
+
+
+_batched_ws: dict = {}
+
+
+def train_epoch_batched(X, members, batch_size: int, y, grp, That, inv_tau, *, ebd_weight=0.5, G=4, momentum=0.9, weight_decay=5e-5):
+    """One epoch of every member in lock step (dbmm_train_epoch_batched; the reference runs its sweep members one after
+    another, run_multiple/final_main_iteration_wb.py:1129-1197).  All members must share n_rows, the stage (old_ad or not)
+    and `first_step`."""
+    lib = _lib.load()
+    _check(X, torch.float32, "X", contiguous=False)
+    _check(That, torch.float32, "That")
+    M = len(members)
+    if M < 1:
+        raise DbmmError("train_epoch_batched: no members")
+    D, H, Cn = X.shape[1], members[0].ad.H, That.shape[1]
+    G = _label_args(y, grp, G)
+    n = members[0].order.numel()
+    steps = (n + batch_size - 1) // batch_size
+    nad = 2 if members[0].old_ad is not None else 1
+    first = members[0].buf.first_step
+    need = int(lib.dbmm_workspace_bytes(_lib.OP_TRAIN, min(batch_size, n), D, H, Cn, nad))
+    arr = (_lib.Member * M)()
+    keep = []
+    lr_all = np.empty((M, steps), dtype=np.float32)
+    for i, mb in enumerate(members):
+        _check(mb.order, torch.int32, "order")
+        if mb.order.numel() != n or (mb.old_ad is not None) != (nad == 2) or mb.buf.first_step != first or mb.stats.n_slots < steps:
+            raise DbmmError("train_epoch_batched: members differ in n_rows / stage / first_step, or too few stat slots")
+        if mb.ws is None or mb.ws.numel() < need:
+            mb.ws = torch.empty(need, dtype=torch.uint8, device=X.device)
+        lr = np.asarray(mb.lrs, dtype=np.float32)
+        if len(lr) != steps:
+            raise DbmmError(f"member {i}: need {steps} learning rates, got {len(lr)}")
+        lr_all[i] = lr
+        ap = mb.ad.ptrs()
+        op = mb.old_ad.ptrs() if mb.old_ad is not None else None
+        keep += [ap, op]
+        arr[i].order = mb.order.data_ptr()
+        arr[i].old_ad = C.pointer(op) if op is not None else None
+        arr[i].ad = C.pointer(ap)
+        arr[i].grads = mb.buf.grads.data_ptr(); arr[i].momentum_buf = mb.buf.momentum.data_ptr()
+        arr[i].stats = mb.stats.c()
+        arr[i].ws = mb.ws.data_ptr(); arr[i].ws_bytes = mb.ws.numel()
+    bbytes = int(lib.dbmm_batched_workspace_bytes(M, steps))
+    key = (torch.device(X.device).index or 0, M, steps)
+    bws = _batched_ws.get(key)
+    if bws is None or bws.numel() < bbytes:
+        bws = _batched_ws[key] = torch.empty(bbytes, dtype=torch.uint8, device=X.device)
+    _lib.check(lib.dbmm_train_epoch_batched(M, arr, X.data_ptr(), X.stride(0), n, batch_size, y.data_ptr(), _ptr(grp), D, H, Cn, G,
+                                            ebd_weight, That.data_ptr(), inv_tau, lr_all.ctypes.data_as(C.POINTER(C.c_float)),
+                                            momentum, weight_decay, 1 if first else 0, bws.data_ptr(), bws.numel(), _stream_ptr()))
+    for mb in members:
+        mb.buf.first_step = False
     return steps
 
 

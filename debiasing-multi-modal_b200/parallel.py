@@ -27,12 +27,15 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def accum_views(ws: torch.Tensor, H: int, nad: int):
+def accum_views(ws: torch.Tensor, H: int, nad: int, dtype=torch.int64):
+    """The two per-step accumulator blocks of a DBMM_OP_TRAIN workspace that a data-parallel caller all-reduces between
+    the phases.  The kernels keep them as int64 fixed-point sums (include/dbmm.h: dbmm_train_accum_layout), so they are
+    reduced as int64; an injected step function (CPU protocol test) may treat the same 8-byte slots as float64."""
     lib = _lib.load(require_gpu=False)
     co, cc, do, dc = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
     _lib.check(lib.dbmm_train_accum_layout(H, nad, C.byref(co), C.byref(cc), C.byref(do), C.byref(dc)))
-    colsum = ws[co.value: co.value + 8 * cc.value].view(torch.float64)
-    dgb = ws[do.value: do.value + 8 * dc.value].view(torch.float64)
+    colsum = ws[co.value: co.value + 8 * cc.value].view(dtype)
+    dgb = ws[do.value: do.value + 8 * dc.value].view(dtype)
     return colsum, dgb
 
 
@@ -74,6 +77,11 @@ class DataParallelTrainer:
             self._comm = comm
         return self._comm
 
+    def check(self):
+        """Synchronise and raise if a peer-memory wait timed out (a rank never reached the same epoch call)."""
+        if self._comm is not None:
+            _lib.check(_lib.load().dbmm_comm_check(self._comm))
+
     def close(self):
         if self._comm is not None:
             _lib.check(_lib.load().dbmm_comm_destroy(self._comm))
@@ -94,7 +102,7 @@ class DataParallelTrainer:
         nad = 2 if old_ad is not None else 1
         self._step(X, y, grp, ad, That, inv_tau, buf, lr, stats, slot, phases=_lib.PHASE_GEMM1, **kw)
         ws = ops.workspace(0, X.device)
-        colsum, dgb = accum_views(ws, ad.H, nad)
+        colsum, dgb = accum_views(ws, ad.H, nad, torch.float64 if self._custom_step else torch.int64)
         if self.world > 1:
             self._all_reduce(colsum)
         self._step(X, y, grp, ad, That, inv_tau, buf, lr, stats, slot, phases=_lib.PHASE_ROWS, **kw)

@@ -2,11 +2,17 @@
 (run_multiple/final_main_iteration_wb.py:248-262, 1129-1197; run_multiple/final_main_iteration_ca.py:249-255, 1179-1256).
 
 Every member of the sweep (one seed of one (lr, bs, bsr) grid point) is an independent `train_all_epochs` run over the
-same GPU-resident embeddings.  The reference runs them one after another in nested Python loops; here the members are
-dealt round-robin to the ranks of a `torchrun` job (replicated data, no data-path collective -- SURVEY.md section 8e) and
-rank 0 gathers the result dictionaries and writes the CSVs.  Per member the result equals the sequential run with that
-seed, so the mean +- std rows are those of the reference's protocol -- including its quirk that the `*_std` row is
-computed after the `*_mean` row was appended (std over seeds + their mean, ddof = 1).
+same GPU-resident embeddings.  The reference runs them one after another in nested Python loops; here
+  * the members are dealt round-robin to the ranks of a `torchrun` job (replicated data, no data-path collective --
+    SURVEY.md section 8e) and rank 0 gathers the result dictionaries and writes the CSVs;
+  * the members of one rank train in LOCK STEP (BASELINE config 5): every member is a `train_all_epochs_gen` generator that
+    yields its prepared training epochs; the epochs that share data, batch size, stage and prompts run as ONE
+    `dbmm_train_epoch_batched` call (every kernel of the step launched once for all members), the rest one by one.
+    Each member keeps its own torch / numpy RNG streams (swapped in around its turns), so it draws the batch orders and
+    initial weights of its stand-alone run.  `--sequential_members` restores one-after-another execution.
+Per member the result equals the sequential run with that seed, so the mean +- std rows are those of the reference's
+protocol -- including its quirk that the `*_std` row is computed after the `*_mean` row was appended (std over seeds +
+their mean, ddof = 1).
 """
 from __future__ import annotations
 
@@ -14,6 +20,7 @@ import copy
 import os
 
 import numpy as np
+import torch
 
 from . import cli
 from . import engine as E
@@ -29,6 +36,8 @@ def add_sweep_arguments(parser):
     parser.add_argument("--bs_list", type=str, default=None, help="grid of batch sizes")
     parser.add_argument("--bsr_list", type=str, default=None, help="grid of stage-2 batch sizes")
     parser.add_argument("--results_root", type=str, default="results_iterative")
+    parser.add_argument("--sequential_members", action="store_true", help="run the members one after another (reference order) "
+                                                                         "instead of in lock step")
     return parser
 
 
@@ -64,6 +73,18 @@ def member_options(opt, point, seed):
     return cli.finalize_options(o)                            # re-derives the warm-up constants and seeds the RNGs
 
 
+def _member_loaders(loaders, point):
+    """Loaders over the shared datasets with this grid point's batch sizes (the datasets themselves are not copied)."""
+    from .data import EmbeddingLoader
+    _, bs, bsr = point
+    trainset, train_loader, reg_loader, val_loader, test_loader = loaders
+
+    def clone(ld, batch_size):
+        return None if ld is None else EmbeddingLoader(ld.dataset, batch_size=batch_size, shuffle=ld.shuffle)
+    bs_val = bsr if reg_loader is not None else bs            # cli.build_loaders: the eval loaders take the stage-2 batch size
+    return trainset, clone(train_loader, bs), clone(reg_loader, bsr), clone(val_loader, bs_val), clone(test_loader, bs_val)
+
+
 def csv_name(opt):
     """run_multiple/final_main_iteration_wb.py:1166-1189."""
     name = f"ds_{opt.dataset}_tl_{opt.tl_method}_bs_{opt.batch_size}_lr_{opt.learning_rate}"
@@ -95,19 +116,84 @@ def aggregate(results: dict):
     return pd.concat(frames).round(4)
 
 
+class _MemberRun:
+    """One member in the lock-step driver: its generator and its private RNG streams (torch CPU / CUDA, numpy)."""
+
+    def __init__(self, key, tag, opt, point, seed, loaders):
+        self.key, self.tag = key, tag
+        self.job, self.result, self.last_run = None, None, None
+        self.opt = member_options(opt, point, seed)               # seeds the global RNGs (final_main.py:253) ...
+        self._save_rng()                                          # ... which become this member's streams
+        self.gen = cli.train_all_epochs_gen(self.opt, loaders=loaders)
+
+    def _save_rng(self):
+        self.rng = (torch.get_rng_state(), torch.cuda.get_rng_state() if torch.cuda.is_available() else None, np.random.get_state())
+
+    def _load_rng(self):
+        torch.set_rng_state(self.rng[0])
+        if self.rng[1] is not None:
+            torch.cuda.set_rng_state(self.rng[1])
+        np.random.set_state(self.rng[2])
+
+    def advance(self):
+        """Run this member up to its next training epoch (-> self.job) or to the end (-> self.result)."""
+        self._load_rng()
+        E._member_tag = self.tag
+        try:
+            self.job = next(self.gen) if self.job is None else self.gen.send(None)
+        except StopIteration as e:
+            self.job, self.result = None, e.value
+            self.last_run = getattr(cli.train_all_epochs, "last_run", None)
+        finally:
+            E._member_tag = None
+            self._save_rng()
+
+
+def run_members_lockstep(runs):
+    """Advance all members epoch by epoch; jobs with equal signatures run as one batched call."""
+    for r in runs:
+        r.advance()
+    while True:
+        active = [r for r in runs if r.job is not None]
+        if not active:
+            return
+        groups = {}
+        for r in active:
+            groups.setdefault(r.job.signature(), []).append(r)
+        for sig, rs in groups.items():
+            if sig is None or len(rs) == 1:
+                for r in rs:
+                    r.job.run()
+            else:
+                E.run_jobs_batched([r.job for r in rs])
+        for r in active:
+            r.advance()
+
+
 def run_sweep(opt, loaders=None):
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     points = grid_points(opt)
     mine = {}
-    for n, (gi, it, seed) in enumerate(members(opt)):
-        if n % world != rank:
-            continue
-        print(f"=============Grid point {points[gi]} iteration {it}/{opt.num_iter} (seed {seed}, rank {rank})=============")
-        o = member_options(opt, points[gi], seed)
-        (tr, va, te), (zs_t, zs_s) = cli.train_all_epochs(o, loaders=loaders)
-        mine[(gi, it)] = dict(train=tr, val=va, test=te, zs_target=zs_t, zs_spurious=zs_s)
+    todo = [(gi, it, seed) for n, (gi, it, seed) in enumerate(members(opt)) if n % world == rank]
+    if getattr(opt, "sequential_members", False) or len(todo) <= 1:
+        for gi, it, seed in todo:
+            print(f"=============Grid point {points[gi]} iteration {it}/{opt.num_iter} (seed {seed}, rank {rank})=============")
+            o = member_options(opt, points[gi], seed)
+            (tr, va, te), (zs_t, zs_s) = cli.train_all_epochs(o, loaders=loaders)
+            mine[(gi, it)] = dict(train=tr, val=va, test=te, zs_target=zs_t, zs_spurious=zs_s)
+    else:
+        if loaders is None:                  # one GPU-resident copy of the data for all members of this rank
+            loaders = cli.build_loaders(member_options(opt, points[todo[0][0]], todo[0][2]))
+        runs = []
+        for gi, it, seed in todo:
+            print(f"=============Grid point {points[gi]} iteration {it}/{opt.num_iter} (seed {seed}, rank {rank}): lock step=============")
+            runs.append(_MemberRun((gi, it), f"m{gi}_{it}", opt, points[gi], seed, _member_loaders(loaders, points[gi])))
+        run_members_lockstep(runs)
+        for r in runs:
+            (tr, va, te), (zs_t, zs_s) = r.result
+            mine[r.key] = dict(train=tr, val=va, test=te, zs_target=zs_t, zs_spurious=zs_s)
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)

@@ -11,6 +11,7 @@
  *   dbmm_train_step       final_main.py:455-466, 610-623   forward + CE + backward (+ optim step)
  *                         demo/util.py:118-136      optim.SGD (momentum 0.9, weight decay)
  *   dbmm_train_epoch      final_main.py:426-496, 571-653   the per-batch loop of one epoch
+ *   dbmm_train_epoch_batched  run_multiple/final_main_iteration_wb.py:1129-1197   the sweep's members, one epoch in lock step
  *   dbmm_sgd_step         demo/util.py:118-136      SGD on a flat buffer (data-parallel path)
  *   dbmm_export_embeddings  demo/demo_visualization.ipynb:1117-1215  validate_adapter_with_return (features for the notebooks)
  *   dbmm_widen_f16        data/waterbirds_embeddings.py:69-78  embeddings -> float32 tensors (ingest, fp16 store)
@@ -87,9 +88,10 @@ const char* dbmm_build_info(void);
 /* rows = rows per call (eval: chunk size used internally is bounded, pass N), n_adapters = 1 or 2 */
 size_t dbmm_workspace_bytes(int op, int64_t rows, int D, int H, int C, int n_adapters);
 
-/* Byte offsets (from the start of a DBMM_OP_TRAIN workspace) and element counts of the two fp64 accumulator blocks
- * a data-parallel caller must all-reduce between phases: column sums [n_adapters][2][H] after DBMM_PHASE_GEMM1 and
- * (dgamma, dbeta) [2][H] after DBMM_PHASE_ROWS. */
+/* Byte offsets (from the start of a DBMM_OP_TRAIN workspace) and element counts of the two accumulator blocks a
+ * data-parallel caller must all-reduce between phases: column sums [n_adapters][2][H] after DBMM_PHASE_GEMM1 and
+ * (dgamma, dbeta) [2][H] after DBMM_PHASE_ROWS.  Both are int64 FIXED-POINT sums (binary point at bit 20 / bit 40):
+ * reduce them as int64 with SUM -- integer sums are order-independent, so the replicas stay bit-identical. */
 int dbmm_train_accum_layout(int H, int n_adapters, size_t* colsum_offset, size_t* colsum_count,
                             size_t* dgb_offset, size_t* dgb_count);
 
@@ -141,6 +143,23 @@ int dbmm_train_step(int phases,
                     dbmm_batch_stats stats, int64_t slot,
                     void* ws, size_t ws_bytes, void* stream);
 
+/*
+ * The nn.Module boundary of the same step (final_main.py:66-80, 121-140: CustomCLIP / MultipleAdapter .forward in train()
+ * mode; final_main.py:455-466: output = classifier(x); loss = criterion(output, y); loss.backward(); optimizer.step()):
+ *   dbmm_train_forward   logits_out[B, C] with batch-statistics BatchNorm; update_running_stats != 0 also moves
+ *                        running_mean / running_var / num_batches_tracked of every adapter in the forward, as torch does;
+ *   dbmm_train_backward  flat gradient (dbmm_param_count floats, layout W1 | b1 | gamma | beta | W2 | b2) of the trainable
+ *                        adapter from an arbitrary upstream dL/dlogits [B, C]; the forward is recomputed from X, so no
+ *                        state has to survive between the two calls.
+ * The caller's autograd engine and optimizer own the rest (modules.py wraps the pair in a torch.autograd.Function).
+ */
+int dbmm_train_forward(const float* X, int64_t ldx, const int32_t* idx, int B, int D, int H, int C,
+                       const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight, const float* That, float inv_tau,
+                       float* logits_out, int update_running_stats, void* ws, size_t ws_bytes, void* stream);
+int dbmm_train_backward(const float* X, int64_t ldx, const int32_t* idx, int B, int D, int H, int C,
+                        const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight, const float* That, float inv_tau,
+                        const float* dlogits, float* grads, void* ws, size_t ws_bytes, void* stream);
+
 /* As dbmm_train_step, for callers that chain the steps of an epoch themselves (the data-parallel epoch graph):
  *   fresh != 0   first step of a chain: accumulators are zeroed, Gram matrices and tf32 weight splits computed from
  *                scratch; fresh == 0 relies on the previous step's WGRAD / UPDATE phases having prepared them (same
@@ -190,6 +209,9 @@ int dbmm_train_epoch(const float* X, int64_t ldx, const int32_t* order, int64_t 
 int dbmm_comm_unique_id(void* id_out_128_bytes);
 int dbmm_comm_init(const void* id_128_bytes, int world, int rank, void** comm_out);
 int dbmm_comm_has_p2p(void* comm);      /* 1 if the fused peer-memory all-reduce (below) is active, 0 if NCCL is used throughout */
+/* Synchronises the device; DBMM_ERR_CUDA if a peer-memory wait of an earlier epoch timed out (a rank never arrived within
+ * DBMM_P2P_TIMEOUT_S seconds, default 300): the ranks must issue the same epoch calls in the same order. */
+int dbmm_comm_check(void* comm);
 int dbmm_comm_destroy(void* comm);
 int dbmm_train_epoch_dp(void* comm, int world, int rank, int local_batches,
                         const float* X, int64_t ldx, const int32_t* order, int64_t n_rows, int batch_size,
@@ -199,6 +221,32 @@ int dbmm_train_epoch_dp(void* comm, int world, int rank, int local_batches,
                         float* grads, float* momentum_buf, const float* lr_host, float momentum, float weight_decay,
                         int first_step, dbmm_batch_stats stats, int reduce_stats,
                         void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Batched-adapter training (BASELINE config 5): n_members members of a sweep -- the (seed, learning-rate, ...) grid the
+ * reference walks one run after another, run_multiple/final_main_iteration_wb.py:1129-1197, _ca.py:1179-1256 -- train one
+ * epoch in LOCK STEP over the same resident X / labels: every kernel of the step is launched once for all members (member
+ * index in the grid), so a sweep fills the GPU that a single 1024-row step cannot.  Members share the data, the batch size
+ * (hence the step count), the prompt matrix, momentum and weight decay, and are all in the same stage (old_ad NULL or not);
+ * each has its own batch order, adapters, optimizer state, learning-rate schedule, statistics slots and workspace.  The
+ * result of every member equals dbmm_train_epoch on that member alone (same arithmetic up to the summation order of the
+ * un-split GEMMs: ~1e-6 relative).  `members` is a HOST array; lr_host is [n_members][steps] (host); bws is a device
+ * buffer of dbmm_batched_workspace_bytes() that must stay untouched until the epoch has run.
+ */
+typedef struct dbmm_member {
+    const int32_t* order;              /* device [n_rows]: this member's batch order */
+    const dbmm_adapter* old_ad;        /* NULL (stage 1) or the frozen adapter (stage 2) */
+    const dbmm_adapter* ad;            /* trainable adapter, updated in place */
+    float* grads; float* momentum_buf; /* flat [dbmm_param_count] each */
+    dbmm_batch_stats stats;            /* this member's per-batch slots */
+    void* ws; size_t ws_bytes;         /* this member's DBMM_OP_TRAIN workspace */
+} dbmm_member;
+size_t dbmm_batched_workspace_bytes(int n_members, int64_t steps);
+int dbmm_train_epoch_batched(int n_members, const dbmm_member* members,
+                             const float* X, int64_t ldx, int64_t n_rows, int batch_size, const int32_t* y, const int32_t* grp,
+                             int D, int H, int C, int G, float ebd_weight, const float* That, float inv_tau,
+                             const float* lr_host, float momentum, float weight_decay, int first_step,
+                             void* bws, size_t bws_bytes, void* stream);
 
 /* Measurement aid: the same epoch as stream launches with CUDA events between the kernels of every step;
  * kernel_us_host[6] = mean device microseconds of GEMM-1, reduce/statistics, row kernel, dW1, gradient finalisation,

@@ -366,6 +366,27 @@ E2E_CASES = {
               "--batch_size", "512", "--batch_size_reg", "4", "--learning_rate", "0.1", "--learning_rate_reg", "1.0",
               "--epochs", "10", "--epochs_feature_learning", "5", "--lr_decay_rate", "0.1", "--lr_decay_epochs", "8,9",
               "--train_target", "class", "--save_results", "--random_seed", "32"]),
+    # --tl_method adapter_reg (train_reg_one_epoch, final_main.py:498-569): one optimizer, a pass over the train loader with
+    # class prompts then a pass over the reg loader with group prompts (GP) or class prompts (CP) in every epoch
+    "waterbirds_small_reg_gp": dict(
+        synth=dict(name="waterbirds", dim=1024, seed=1234, scale=0.5, k=0.085, k_text=0.5, text_noise=0.02),
+        argv=["--dataset", "waterbirds", "--tl_method", "adapter_reg", "--batch_size", "256", "--batch_size_reg", "64",
+              "--learning_rate", "0.5", "--epochs", "6", "--lr_decay_rate", "0.1", "--lr_decay_epochs", "5,6",
+              "--train_target", "class", "--save_results", "--random_seed", "42"]),
+    "waterbirds_small_reg_cp": dict(
+        synth=dict(name="waterbirds", dim=1024, seed=1234, scale=0.5, k=0.085, k_text=0.5, text_noise=0.02),
+        argv=["--dataset", "waterbirds", "--tl_method", "adapter_reg", "--use_cls_prompt_in_reg", "--balance_val",
+              "--batch_size", "256", "--batch_size_reg", "64", "--learning_rate", "0.5", "--epochs", "6",
+              "--lr_decay_rate", "0.1", "--lr_decay_epochs", "5,6", "--train_target", "class", "--save_results",
+              "--random_seed", "22"]),
+    # BASELINE.json configs[0] at full size, the reference's own launch script (run_final_main.sh:1-31): 4,795 train rows,
+    # bs 1024 / bsr 256, lr 1.0 / 1.0, 100 epochs of which 40 feature learning, decay 0.1 at 90 and 95
+    "waterbirds_full": dict(
+        synth=dict(name="waterbirds", dim=1024, seed=1234, scale=1.0, k=0.085, k_text=0.5, text_noise=0.02),
+        argv=["--dataset", "waterbirds", "--tl_method", "adapter_reg_seq_alter", "--add_adapter", "--warm_reg",
+              "--batch_size", "1024", "--batch_size_reg", "256", "--learning_rate", "1.0", "--learning_rate_reg", "1.0",
+              "--epochs", "100", "--epochs_feature_learning", "40", "--lr_decay_rate", "0.1", "--lr_decay_epochs", "90,95",
+              "--train_target", "class", "--save_results", "--random_seed", "42"]),
 }
 
 
@@ -378,11 +399,14 @@ def e2e_paths_argv(case, root):
     return ds, argv
 
 
-def gen_e2e(fm, ru):
+def gen_e2e(fm, ru, only_cases=None):
     import io
     import contextlib
-    out = {}
+    path = os.path.join(GOLD, "e2e_cases.json")
+    out = json.load(open(path)) if (only_cases and os.path.exists(path)) else {}
     for name, case in E2E_CASES.items():
+        if only_cases and name not in only_cases:
+            continue
         root = tempfile.mkdtemp(prefix=f"dbmm_e2e_{name}_")
         ds, argv = e2e_paths_argv(case, root)
         old_argv = sys.argv
@@ -393,7 +417,7 @@ def gen_e2e(fm, ru):
             sys.argv = old_argv
         # record what train_all_epochs computes per epoch by wrapping the reference's own epoch functions
         log = dict(train=[], val_test=[], zs=[])
-        t1, t2, tv, tz = fm.train_one_epoch, fm.train_reg_seq_one_epoch, fm.validate, fm.validate_zs
+        t1, t2, t3, tv, tz = fm.train_one_epoch, fm.train_reg_seq_one_epoch, fm.train_reg_one_epoch, fm.validate, fm.validate_zs
 
         def wrap(fn, key):
             def inner(*a, **k):
@@ -402,14 +426,14 @@ def gen_e2e(fm, ru):
                                      group_acc={kk: float(vv) for kk, vv in r[2].items()}))
                 return r
             return inner
-        fm.train_one_epoch, fm.train_reg_seq_one_epoch = wrap(t1, "train"), wrap(t2, "train")
+        fm.train_one_epoch, fm.train_reg_seq_one_epoch, fm.train_reg_one_epoch = wrap(t1, "train"), wrap(t2, "train"), wrap(t3, "train")
         fm.validate, fm.validate_zs = wrap(tv, "val_test"), wrap(tz, "zs")
         buf = io.StringIO()
         try:
             with contextlib.redirect_stdout(buf):
                 res = fm.train_all_epochs(opt)
         finally:
-            fm.train_one_epoch, fm.train_reg_seq_one_epoch, fm.validate, fm.validate_zs = t1, t2, tv, tz
+            fm.train_one_epoch, fm.train_reg_seq_one_epoch, fm.train_reg_one_epoch, fm.validate, fm.validate_zs = t1, t2, t3, tv, tz
         stdout = buf.getvalue()
         best_epoch = int([ln for ln in stdout.splitlines() if ln.startswith("best epoch")][0].split(":")[1])
         folder = os.path.dirname(opt.image_embedding_dir).replace("data", "results")
@@ -425,7 +449,7 @@ def gen_e2e(fm, ru):
             state_dict_abs_sums={k: float(v.double().abs().sum()) for k, v in sd.items()},
             results_json=results_json)
         print(name, "best epoch", best_epoch, "val/test dicts", len(log["val_test"]), files)
-    with open(os.path.join(GOLD, "e2e_cases.json"), "w") as f:
+    with open(path, "w") as f:
         json.dump(out, f)
     print("e2e_cases.json written")
 
@@ -433,6 +457,7 @@ def gen_e2e(fm, ru):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
+    ap.add_argument("--e2e-cases", default="", help="comma-separated subset of E2E_CASES to (re)generate; the others are kept")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     fm, ru = import_reference()
@@ -441,7 +466,10 @@ def main():
                 supcon=gen_supcon, layout=gen_checkpoint_layout, e2e=gen_e2e, export=gen_export)
     for k, fn in todo.items():
         if a.only in ("all", k):
-            fn(fm, ru)
+            if k == "e2e" and a.e2e_cases:
+                fn(fm, ru, only_cases=a.e2e_cases.split(","))
+            else:
+                fn(fm, ru)
 
 
 if __name__ == "__main__":

@@ -17,11 +17,14 @@ import types
 REFERENCE_ROOT = "/root/reference"
 
 
-def import_reference():
+def import_reference(root=None):
+    """root: where the reference lives -- /root/reference in the build container, or the copy staged by
+    oracle/stage_reference.py under oracle/_ref/reference (the only form that reaches the GPU box)."""
     import torch
 
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = root or REFERENCE_ROOT
+    if root not in sys.path:
+        sys.path.insert(0, root)
     if "visualizer_supcon" not in sys.modules:
         stub = types.ModuleType("visualizer_supcon")
         stub.skim_dataloader_by_group = lambda *a, **k: None

@@ -48,7 +48,7 @@ class OracleStep:
         from dbmm import _lib
         s = self.s
         ws = self.ops.workspace(0, "cpu")
-        colsum, dgb = self.parallel.accum_views(ws, H, 1)
+        colsum, dgb = self.parallel.accum_views(ws, H, 1, torch.float64)      # the oracle's sums are plain doubles
         p = ad                                                   # dict of float64 numpy arrays (this rank's replica)
         rows = idx.numpy()
         Xb, yb, gb = X.numpy()[rows], y[rows], grp[rows]
