@@ -12,6 +12,8 @@
 #pragma once
 #include "gemm1_tc.cuh"
 #include "rows_train.cuh"
+#include "hs_rows.cuh"
+#include "hs_w2.cuh"
 #include "wgrad_tc.cuh"
 #include "step_tail.cuh"
 #include "tn_gemm.cuh"
@@ -54,6 +56,34 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train_b(RowsTrainArgs a, const
     a.loss_sum = m.loss_sum; a.counts = m.counts;
     a.dahat = m.w.dahat; a.dgb = m.w.dgb; a.Lrows = m.w.Lrows; a.Hrows = m.w.Hrows;
     rows_train_body<NAD, CT, NW>(a);
+}
+
+__global__ void __launch_bounds__(HR_THREADS, 1) k_hs_rows_b(HsRowsArgs a, const MemberDev* mem, int64_t pos0) {
+    const MemberDev& m = mem[blockIdx.y];
+    a.idx = m.order + pos0; a.A = m.w.A; a.gram = m.w.gram; a.colsum = m.w.colsum;
+    a.ad[0] = m.ad[0]; a.ad[1] = m.ad[1];
+    a.loss_sum = m.loss_sum; a.counts = m.counts;
+    a.dahat = m.w.dahat; a.dgb = m.w.dgb; a.Spart = m.w.Spart;
+    hs_rows_body(a);
+}
+
+__global__ void __launch_bounds__(256) k_sum_spart_b(SumSpartArgs a, const MemberDev* mem) {
+    const MemberDev& m = mem[blockIdx.y];
+    a.Spart = m.w.Spart; a.S = m.w.S; a.ST = m.w.ST;
+    sum_spart_body(a);
+}
+
+__global__ void __launch_bounds__(HR_THREADS, 1) k_hs_w2_b(HsW2Args a, const MemberDev* mem, int step) {
+    const MemberDev& m = mem[blockIdx.y];
+    a.W2 = const_cast<float*>(m.ad[1].W2); a.b2 = const_cast<float*>(m.ad[1].b2); a.g = m.grads; a.v = m.mom;
+    a.lr_dev = m.lr + step; a.ST = m.w.ST; a.Gpart = m.w.Gpart;
+    hs_w2_body(a);
+}
+
+__global__ void __launch_bounds__(256) k_sum_gpart_b(SumGpartArgs a, const MemberDev* mem, int nad) {
+    const MemberDev& m = mem[blockIdx.y];
+    a.Gpart = m.w.Gpart; a.G = m.w.gram + (size_t)(nad - 1) * (a.H + 1) * (a.H + 1 + a.C);
+    sum_gpart_body(a);
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc_b(WgradTcArgs a, const MemberDev* mem, int64_t pos0, int nad) {
@@ -133,6 +163,16 @@ static int batched_step(const MemberDev* dmem, int M, int step, int64_t pos0, in
         kern<<<dim3(ceil_div(B, G1_BM), nad, M), G1_THREADS, Cfg::SMEM, st>>>(t, dmem);
         DBMM_LAUNCH_CHECK();
     }
+    const bool tc_rows = hs_rows_supported(H, C) && !(getenv("DBMM_ROWS") && strcmp(getenv("DBMM_ROWS"), "simt") == 0);
+    if (tc_rows) {
+        HsRowsArgs ha;
+        memset(&ha, 0, sizeof(ha));
+        ha.B = B; ha.Bg = B; ha.y = y; ha.grp = grp; ha.H = H; ha.C = C; ha.G = G; ha.nad = nad; ha.strideA = (int64_t)B * H;
+        ha.w_old = ebd_weight; ha.inv_tau = inv_tau; ha.inv_B = 1.0f / (float)B; ha.slot = step;
+        DBMM_CUDA(set_smem(k_hs_rows_b, HR_SMEM));
+        k_hs_rows_b<<<dim3(ceil_div(B, HR_ROWS), M), HR_THREADS, HR_SMEM, st>>>(ha, dmem, pos0);
+        DBMM_LAUNCH_CHECK();
+    } else
     {
         RowsTrainArgs ra;
         memset(&ra, 0, sizeof(ra));
@@ -176,6 +216,14 @@ static int batched_step(const MemberDev* dmem, int M, int step, int64_t pos0, in
     if (ta.n_w1_ctas > 128) ta.n_w1_ctas = 128;
     k_tail_w1_b<<<dim3(ta.n_w1_ctas + 1, M), ST_THREADS, 0, st>>>(ta, dmem, step);
     DBMM_LAUNCH_CHECK();
+    if (tc_rows) {   // S = sum of the row kernel's S^T tiles, in tile order
+        SumSpartArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.tiles = ceil_div(B, HR_ROWS); sa.H = H; sa.C = C;
+        const int n = (H + 1) * (H + 1 + C) + (H + 1 + C) * (s_stride(H) - (H + 1));
+        k_sum_spart_b<<<dim3(ceil_div(n, 256), M), 256, 0, st>>>(sa, dmem);
+        DBMM_LAUNCH_CHECK();
+    } else
     {   // S = L^T [h | 1]
         TnGemmArgs g;
         memset(&g, 0, sizeof(g));
@@ -184,6 +232,22 @@ static int batched_step(const MemberDev* dmem, int M, int step, int64_t pos0, in
         DBMM_CUDA(set_smem(k_tn_gemm_b, TNG_SMEM));
         k_tn_gemm_b<<<dim3(ceil_div(g.M, TNG_TM), ceil_div(g.n_store, TNG_TN), M), TNG_THREADS, TNG_SMEM, st>>>(g, dmem, 0, nad);
         DBMM_LAUNCH_CHECK();
+    }
+    const bool tc_w2 = tc_rows && !(getenv("DBMM_W2") && strcmp(getenv("DBMM_W2"), "simt") == 0);
+    if (tc_w2) {   // dW2a = [W2 | b2 | That] S -> SGD on W2 / b2 -> Gram tiles -> next step's Gram matrix
+        HsW2Args wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.oW2 = (size_t)H * D + 3 * (size_t)H; wa.ob2 = wa.oW2 + (size_t)D * H;
+        wa.momentum = momentum; wa.wd = wd; wa.That = That; wa.D = D; wa.H = H; wa.C = C;
+        DBMM_CUDA(set_smem(k_hs_w2_b, HW_SMEM));
+        k_hs_w2_b<<<dim3(ceil_div(D, HW_ROWS), M), HR_THREADS, HW_SMEM, st>>>(wa, dmem, step);
+        DBMM_LAUNCH_CHECK();
+        SumGpartArgs sg;
+        memset(&sg, 0, sizeof(sg));
+        sg.tiles = ceil_div(D, HW_ROWS); sg.H = H; sg.C = C;
+        k_sum_gpart_b<<<dim3(ceil_div((H + 1) * (H + 1 + C), 256), M), 256, 0, st>>>(sg, dmem, nad);
+        DBMM_LAUNCH_CHECK();
+        return DBMM_OK;
     }
     {   // dW2a = [W2 | b2 | That] S -> SGD on W2 / b2
         const int w2_rows = 64;
@@ -198,6 +262,7 @@ static int batched_step(const MemberDev* dmem, int M, int step, int64_t pos0, in
         memset(&g, 0, sizeof(g));
         g.A = cat_mat(nullptr, H, H, nullptr, 1, 1); g.B = cat_mat(nullptr, H, H, nullptr, 1, 1, That, C, C);
         g.M = H + 1; g.N = H + 1 + C; g.K = D; g.ldc = H + 1 + C; g.n_store = H + 1 + C;
+        DBMM_CUDA(set_smem(k_tn_gemm_b, TNG_SMEM));
         k_tn_gemm_b<<<dim3(ceil_div(g.M, TNG_TM), ceil_div(g.n_store, TNG_TN), M), TNG_THREADS, TNG_SMEM, st>>>(g, dmem, 1, nad);
         DBMM_LAUNCH_CHECK();
     }

@@ -156,6 +156,9 @@ struct TrainWs {
     float* gram2;     // second half of the Gram double buffer (fused step tail: step s reads half s & 1, fills the other)
     int* tn_ticket;   // [16]          tile tickets of the K-sliced TN GEMMs (zero between launches)
     float* tn_part;   // K-slice tiles of the TN GEMMs (S and the Gram matrix run one after the other and share it)
+    float* Spart;     // [ceil(B/64)][H+1][144]  S^T tiles of the tensor-core row kernel (hs_rows.cuh)
+    float* ST;        // [H+1][144]    S^T summed over the tiles (operand of the tensor-core W2 kernel, hs_w2.cuh)
+    float* Gpart;     // [ceil(D/64)][H+1][144]  Gram tiles of the tensor-core W2 kernel
     float* Lrows;     // [B][l_stride]  rows [c*h | c | ds] of the trainable adapter (operand of S)
     float* Hrows;     // [B][s_stride]  rows [h | 1]
     float* A;         // [nad][B][H]   pre-BatchNorm activations
@@ -183,6 +186,9 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     size_t o_tk = take(sizeof(int) * 32);
     w.accum_bytes = off;
     size_t o_tp = take(sizeof(float) * (size_t)8 * 16 * 32 * 48);       // TNG_MAX_KSPLIT * TNG_MAX_TILES * TNG_TM * TNG_TN
+    size_t o_sp = take(sizeof(float) * (size_t)((B + 63) / 64) * (H + 1) * 144);
+    size_t o_st = take(sizeof(float) * (size_t)(H + 1) * 144);
+    size_t o_gp = take(sizeof(float) * (size_t)((D + 63) / 64) * (H + 1) * 144);
     size_t o_L = take(sizeof(float) * (size_t)B * l_stride(H, C));
     size_t o_Hr = take(sizeof(float) * (size_t)B * s_stride(H));
     size_t o_A = take(sizeof(float) * (size_t)nad * B * H);
@@ -194,6 +200,7 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     size_t o_lr = take(sizeof(float) * DBMM_LR_TABLE);
     w.total = off;
     w.colsum = (fx64*)(p + o_colsum); w.dgb = (fx64*)(p + o_dgb);
+    w.Spart = (float*)(p + o_sp); w.ST = (float*)(p + o_st); w.Gpart = (float*)(p + o_gp);
     w.Lrows = (float*)(p + o_L); w.Hrows = (float*)(p + o_Hr);
     w.tn_ticket = (int*)(p + o_tk); w.tn_part = (float*)(p + o_tp);
     w.A = (float*)(p + o_A); w.dahat = (float*)(p + o_da);

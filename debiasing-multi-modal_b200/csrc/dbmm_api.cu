@@ -7,6 +7,8 @@
 #include "gemm1_tc.cuh"
 #include "kernels_simt.cuh"
 #include "rows_train.cuh"
+#include "hs_rows.cuh"
+#include "hs_w2.cuh"
 #include "wgrad_tc.cuh"
 #include "tn_gemm.cuh"
 #include "update.cuh"
@@ -133,6 +135,33 @@ static int launch_s_gemm(const float* Lrows, const float* Hrows, float* S, int B
     g.B = cat_mat(Hrows, s_stride(H), H + 1);
     g.M = H + 1 + C; g.N = H + 1; g.K = B; g.C = S; g.ldc = s_stride(H); g.n_store = s_stride(H);
     g.no_early_trigger = 0;
+    return launch_tn_gemm(g, st, false);
+}
+
+// Row phase of a SINGLE run: the CUDA-core kernel (128 CTAs of 8 rows: 11 us per 1024-row step) beats the tensor-core kernel
+// (16 CTAs of 64 rows, ~25 us each: built for the batched sweep, where its 8x fewer, fatter CTAs win) on latency.
+// DBMM_ROWS=tc / simt overrides.
+static bool use_tc_rows(int H, int C) {
+    const char* e = getenv("DBMM_ROWS");
+    if (e && strcmp(e, "tc") == 0) return hs_rows_supported(H, C);
+    return false;
+}
+
+static bool use_tc_w2(int H, int C) {
+    const char* e = getenv("DBMM_W2");             // debugging switch: DBMM_W2=simt forces k_tail_w2 (mma.sync) + the TN GEMM for the Gram matrix
+    if (e && strcmp(e, "simt") == 0) return false;
+    return hs_rows_supported(H, C);
+}
+
+// S^T = [h | 1]^T [c*h | c | ds] ((H+1) x (H+1+C), row stride HR_SP_LD, zero padded): the operand layout of k_hs_w2, from the
+// row operands the CUDA-core row kernel writes.
+static int launch_st_gemm(const float* Lrows, const float* Hrows, float* ST, int B, int H, int C, cudaStream_t st, const TnSplit* sp) {
+    TnGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    if (sp) { g.ksplit = tn_ksplit(B); g.part = sp->part; g.ticket = sp->ticket; }
+    g.A = cat_mat(Hrows, s_stride(H), H + 1);
+    g.B = cat_mat(Lrows, l_stride(H, C), H + 1 + C);
+    g.M = H + 1; g.N = H + 1 + C; g.K = B; g.C = ST; g.ldc = HR_SP_LD; g.n_store = HR_SP_LD;
     return launch_tn_gemm(g, st, false);
 }
 
@@ -451,6 +480,7 @@ static int train_step_impl(int phases, bool fresh,
     float* S_cur = fused && tail->parity ? w.S2 : w.S;
     const bool tc1 = use_tc_gemm1(D, H);
     const TnSplit tsp = {w.tn_part, w.tn_ticket};
+    const bool tc_rows = use_tc_rows(H, C);
 #ifdef DBMM_EXPERIMENTS
     static const int skip = getenv("DBMM_SKIP") ? atoi(getenv("DBMM_SKIP")) : 0;   // timing experiments only: drop kernels by bit mask
     if (skip) phases &= ~skip;
@@ -487,10 +517,42 @@ static int train_step_impl(int phases, bool fresh,
         ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.slot = slot;
         ra.dahat = w.dahat; ra.dgb = w.dgb; ra.Lrows = w.Lrows; ra.Hrows = w.Hrows;
         if (ex) { ra.logits_out = ex->logits_out; ra.dlogits_in = ex->dlogits_in; }
-        if (int rc = launch_rows_train(ra, nad, st)) return rc;
-        if (!fused) if (int rc = launch_s_gemm(w.Lrows, w.Hrows, w.S, B, H, C, st, &tsp)) return rc;
+        if (tc_rows) {
+            HsRowsArgs ha;
+            memset(&ha, 0, sizeof(ha));
+            ha.B = B; ha.Bg = B_global; ha.idx = idx; ha.y = y; ha.grp = grp; ha.H = H; ha.C = C; ha.G = G; ha.nad = nad;
+            ha.A = w.A; ha.strideA = (int64_t)B * H; ha.gram = gram_cur; ha.colsum = w.colsum;
+            ha.ad[0] = ra.ad[0]; ha.ad[1] = ra.ad[1];
+            ha.w_old = ebd_weight; ha.inv_tau = inv_tau; ha.inv_B = ra.inv_B;
+            ha.loss_sum = stats.loss_sum; ha.counts = stats.counts; ha.slot = slot;
+            ha.dahat = w.dahat; ha.dgb = w.dgb; ha.logits_out = ra.logits_out; ha.dlogits_in = ra.dlogits_in; ha.Spart = w.Spart;
+            if (int rc = launch_hs_rows(ha, st)) return rc;
+            if (!fused) if (int rc = launch_sum_spart(w.Spart, B, H, C, w.S, nullptr, st, true)) return rc;
+        } else {
+            if (int rc = launch_rows_train(ra, nad, st)) return rc;
+            if (!fused) if (int rc = launch_s_gemm(w.Lrows, w.Hrows, w.S, B, H, C, st, &tsp)) return rc;
+        }
     }
     StepTailArgs ta;
+    // W2 branch of the fused tail: S (sum of the row kernel's tiles, or the TN GEMM) -> dW2a, SGD on W2 / b2 -> next Gram matrix
+    auto w2_branch = [&](cudaStream_t s_, bool first_pdl) -> int {
+        const bool tc_w2 = use_tc_w2(H, C) && !(p2p && p2p->world > 1);
+        if (tc_rows) { if (int rc = launch_sum_spart(w.Spart, B, H, C, S_cur, tc_w2 ? w.ST : nullptr, s_, first_pdl)) return rc; }
+        else if (tc_w2) { if (int rc = launch_st_gemm(w.Lrows, w.Hrows, w.ST, B, H, C, s_, &tsp)) return rc; }
+        else if (int rc = launch_s_gemm(w.Lrows, w.Hrows, S_cur, B, H, C, s_, &tsp)) return rc;
+        if (tc_w2) {
+            HsW2Args wa;
+            memset(&wa, 0, sizeof(wa));
+            wa.W2 = ad->W2; wa.b2 = ad->b2; wa.g = grads; wa.v = momentum_buf; wa.oW2 = oW2; wa.ob2 = ob2;
+            wa.lr_dev = lr_dev; wa.lr = lr; wa.momentum = momentum; wa.wd = weight_decay; wa.That = That; wa.ST = w.ST; wa.Gpart = w.Gpart;
+            wa.D = D; wa.H = H; wa.C = C;
+            if (int rc = launch_hs_w2(wa, s_, true)) return rc;
+            return launch_sum_gpart(w.Gpart, D, H, C, gram_next_t, s_);
+        }
+        ta.roles = 2;
+        if (int rc = launch_step_tail(ta, s_)) return rc;
+        return launch_gram_gemm(ad, That, gram_next_t, D, H, C, s_, &tsp, true);
+    };
     if (fused) {
         DBMM_CHECK_ARG((phases & (DBMM_PHASE_WGRAD | DBMM_PHASE_UPDATE)) == (DBMM_PHASE_WGRAD | DBMM_PHASE_UPDATE) || skip,
                        "fused step tail runs whole steps only");
@@ -508,9 +570,7 @@ static int train_step_impl(int phases, bool fresh,
             DBMM_CUDA(cudaEventRecord(tail->ev_fork, st));
             DBMM_CUDA(cudaStreamWaitEvent(tail->side, tail->ev_fork, 0));
             ta.roles = 2;
-            if (int rc = launch_s_gemm(w.Lrows, w.Hrows, S_cur, B, H, C, tail->side, &tsp)) return rc;
-            if (int rc = launch_step_tail(ta, tail->side)) return rc;
-            if (int rc = launch_gram_gemm(ad, That, gram_next_t, D, H, C, tail->side, &tsp, true)) return rc;
+            if (int rc = w2_branch(tail->side, false)) return rc;
             DBMM_CUDA(cudaEventRecord(tail->ev_join, tail->side));
             tail->join_pending = true;
         }
@@ -552,9 +612,7 @@ static int train_step_impl(int phases, bool fresh,
                 mark(5);
                 if (!tail->side) {                               // no fork (stream launches, profiling): W2 role in line
                     ta.roles = 2;
-                    if (int rc = launch_s_gemm(w.Lrows, w.Hrows, S_cur, B, H, C, st, &tsp)) return rc;
-                    if (int rc = launch_step_tail(ta, st)) return rc;
-                    if (int rc = launch_gram_gemm(ad, That, gram_next_t, D, H, C, st, &tsp, true)) return rc;
+                    if (int rc = w2_branch(st, true)) return rc;
                 }
             }
             mark(6);
@@ -626,6 +684,12 @@ int dbmm_train_step_ex(int phases, int fresh,
     return train_step_impl(phases, fresh != 0, X, ldx, idx, y, grp, B_local, B_global, D, H, C, G, old_ad, ad, ebd_weight, That,
                            inv_tau, grads, momentum_buf, lr, lr_dev, momentum, weight_decay, stats, slot, w, st);
 }
+
+#ifdef DBMM_PHASE_TIMERS
+extern "C" int dbmm_debug_phase_clocks(long long* out32) {
+    return cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(long long) * 32) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // ---- nn.Module boundary: train-mode forward (logits) and backward (parameter gradients from dL/dlogits) as two calls, so
 // that the reference's own loop -- output = classifier(x); loss = criterion(output, y); loss.backward(); optimizer.step()
