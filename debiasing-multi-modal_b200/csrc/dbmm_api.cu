@@ -16,6 +16,7 @@
 #include "batched.cuh"
 #include "export_rows.cuh"
 #include "head_supcon.cuh"
+#include "eval_f16.cuh"
 #include "nccl_dyn.cuh"
 #include "linear_probe.cuh"
 
@@ -411,6 +412,91 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
         ra.logits_out = logits_out; ra.pred_out = pred_out;
         ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.batch_size = batch_size; ra.slot_fixed = -1;
         if (int rc = launch_rows<false>(ra, nad, H, C, st)) return rc;
+    }
+    return DBMM_OK;
+}
+
+
+// ---- eval forward over the fp16-resident embedding matrix (eval_f16.cuh)
+constexpr int64_t EVAL_F16_CHUNK = 1 << 20;
+struct EvalF16Ws {
+    float* gram; __half *wh, *wl, *qh, *ql, *hh, *hl; float2* affine; float *gt, *gb, *scal, *park, *tn_part; int* tn_ticket;
+    int64_t chunk; size_t total;
+};
+static EvalF16Ws carve_eval_f16_ws(void* base, int64_t N, int D, int H, int C, int nad) {
+    EvalF16Ws w; char* p = (char*)base; size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+    w.chunk = N < EVAL_F16_CHUNK ? N : EVAL_F16_CHUNK;
+    const size_t o1 = take(sizeof(float) * (size_t)nad * (H + 1) * (H + 1 + C)), o2 = take(sizeof(__half) * (size_t)nad * H * D),
+                 o3 = take(sizeof(__half) * (size_t)nad * H * D), o4 = take(sizeof(__half) * (size_t)nad * H * H),
+                 o5 = take(sizeof(__half) * (size_t)nad * H * H), o6 = take(sizeof(__half) * (size_t)w.chunk * H),
+                 o7 = take(sizeof(__half) * (size_t)w.chunk * H), o8 = take(sizeof(float2) * (size_t)nad * H),
+                 o9 = take(sizeof(float) * (size_t)nad * H * 8), o10 = take(sizeof(float) * (size_t)nad * H),
+                 o11 = take(sizeof(float) * (size_t)nad * 8), o12 = take(sizeof(float) * (size_t)w.chunk * 8),
+                 o13 = take(sizeof(float) * tn_gemm_part_floats()), o14 = take(sizeof(int) * 32);
+    w.total = off;
+    w.tn_part = (float*)(p + o13); w.tn_ticket = (int*)(p + o14);
+    w.gram = (float*)(p + o1); w.wh = (__half*)(p + o2); w.wl = (__half*)(p + o3); w.qh = (__half*)(p + o4); w.ql = (__half*)(p + o5);
+    w.hh = (__half*)(p + o6); w.hl = (__half*)(p + o7); w.affine = (float2*)(p + o8); w.gt = (float*)(p + o9); w.gb = (float*)(p + o10);
+    w.scal = (float*)(p + o11); w.park = (float*)(p + o12);
+    return w;
+}
+
+int dbmm_eval_f16_supported(int D, int H, int C) { return (H == 128 && D % 8 == 0 && D >= 64 && C >= 1 && C <= 4) ? 1 : 0; }
+
+size_t dbmm_eval_f16_workspace_bytes(int64_t rows, int D, int H, int C, int n_adapters) {
+    if (rows < 1 || !dbmm_eval_f16_supported(D, H, C) || n_adapters < 1 || n_adapters > 2) return 0;
+    return carve_eval_f16_ws(nullptr, rows, D, H, C, n_adapters).total;
+}
+
+int dbmm_eval_fwd_f16(const void* X16, int64_t ldx, const int32_t* y, const int32_t* grp,
+                      int64_t N, int D, int H, int C, int G,
+                      const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                      const float* That, float inv_tau, int64_t batch_size,
+                      dbmm_batch_stats stats, float* logits_out, int32_t* pred_out,
+                      void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_dims(D, H, C, G)) return rc;
+    DBMM_CHECK_SHAPE(dbmm_eval_f16_supported(D, H, C), "fp16 eval path needs H == 128, D %% 8 == 0, C <= 4 (D=%d H=%d C=%d): use dbmm_eval_fwd", D, H, C);
+    if (int rc = check_adapter(ad, "eval")) return rc;
+    if (old_ad) if (int rc = check_adapter(old_ad, "old")) return rc;
+    DBMM_CHECK_ARG(X16 && That && ws, "NULL X / That / workspace");
+    DBMM_CHECK_ARG(y || (!stats.loss_sum && !stats.counts), "labels are required when batch statistics are requested");
+    DBMM_CHECK_ARG(N >= 0 && ldx >= D && ldx % 8 == 0 && batch_size >= 1, "bad N=%lld ldx=%lld batch_size=%lld", (long long)N, (long long)ldx, (long long)batch_size);
+    if (N == 0) return DBMM_OK;
+    const int nad = old_ad ? 2 : 1, ldg = H + 1 + C;
+    EvalF16Ws w = carve_eval_f16_ws(ws, N, D, H, C, nad);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    const dbmm_adapter* ads[2] = {old_ad ? old_ad : ad, ad};
+    DBMM_CUDA(cudaMemsetAsync(w.tn_ticket, 0, sizeof(int) * 32, st));
+    const TnSplit tsp = {w.tn_part, w.tn_ticket};
+    if (int rc = launch_gram(old_ad, ad, That, w.gram, D, H, C, st, &tsp)) return rc;
+    for (int i = 0; i < nad; ++i) {
+        k_split_f16<<<148, 256, 0, st>>>(ads[i]->W1, w.wh + (size_t)i * H * D, w.wl + (size_t)i * H * D, (int64_t)H * D);
+        EvalF16Prep pp;
+        pp.gram = w.gram + (size_t)i * (H + 1) * ldg; pp.H = H; pp.C = C;
+        pp.b1 = ads[i]->b1; pp.mean = ads[i]->running_mean; pp.var = ads[i]->running_var; pp.gamma = ads[i]->gamma; pp.beta = ads[i]->beta;
+        pp.affine = w.affine + (size_t)i * H; pp.q_hi = w.qh + (size_t)i * H * H; pp.q_lo = w.ql + (size_t)i * H * H;
+        pp.gt = w.gt + (size_t)i * H * 8; pp.gb = w.gb + (size_t)i * H; pp.scal = w.scal + (size_t)i * 8;
+        k_eval_f16_prep<<<64, 256, 0, st>>>(pp);
+        DBMM_LAUNCH_CHECK();
+    }
+    const __half* X = (const __half*)X16;
+    for (int64_t pos0 = 0; pos0 < N; pos0 += w.chunk) {
+        const int64_t B = (N - pos0) < w.chunk ? (N - pos0) : w.chunk;
+        for (int i = 0; i < nad; ++i) {
+            EvalF16Args g;
+            memset(&g, 0, sizeof(g));
+            g.M = B; g.K = D; g.bn_affine = w.affine + (size_t)i * H; g.h_hi = w.hh; g.h_lo = w.hl;
+            if (int rc = launch_f16_gemm<EF_G1>(X + pos0 * ldx, nullptr, ldx, w.wh + (size_t)i * H * D, w.wl + (size_t)i * H * D, D, g, st)) return rc;
+            EvalF16Args h;
+            memset(&h, 0, sizeof(h));
+            h.M = B; h.K = H; h.h_hi = w.hh; h.h_lo = w.hl; h.gb = w.gb + (size_t)i * H; h.gt = w.gt + (size_t)i * H * 8; h.scal = w.scal + (size_t)i * 8;
+            h.C = C; h.G = G; h.nad_pass = (nad == 2 && i == 0) ? 1 : 0; h.park = w.park; h.parked = (nad == 2 && i == 1) ? w.park : nullptr;
+            h.w_old = ebd_weight; h.inv_tau = inv_tau; h.y = y; h.grp = grp; h.pos0 = pos0; h.batch_size = batch_size;
+            h.loss_sum = stats.loss_sum; h.counts = stats.counts; h.logits_out = logits_out; h.pred_out = pred_out;
+            if (int rc = launch_f16_gemm<EF_HS>(w.hh, w.hl, H, w.qh + (size_t)i * H * H, w.ql + (size_t)i * H * H, H, h, st)) return rc;
+        }
     }
     return DBMM_OK;
 }

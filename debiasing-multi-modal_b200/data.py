@@ -65,13 +65,23 @@ class EmbeddingDataset:
         self.group_ratio = self.group_counts / len(self)
         # device-resident store
         self.device = device if device is not None else _device()
-        if x.dtype == np.float16 and torch.device(self.device).type == "cuda":
+        # x16: fp16-resident copy for the eval forward (dbmm_eval_fwd_f16) whenever the values are fp16-representable -- CLIP
+        # emits fp16, so the reference's JSON files and the packed store both are; None otherwise (fp32 path only)
+        self.x16 = None
+        on_gpu = torch.device(self.device).type == "cuda"
+        if x.dtype == np.float16 and on_gpu:
             # fp16 packed store (pack.py): half the host -> device bytes, widened exactly on the device (dbmm_widen_f16)
             from . import ops
             with torch.cuda.device(self.device):
-                self.x = ops.widen_f16(torch.from_numpy(np.ascontiguousarray(x)).to(self.device))
+                self.x16 = torch.from_numpy(np.ascontiguousarray(x)).to(self.device)
+                self.x = ops.widen_f16(self.x16)
         else:
-            self.x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
+            x32 = np.ascontiguousarray(x, dtype=np.float32)
+            self.x = torch.from_numpy(x32).to(self.device)
+            if on_gpu and x32.shape[1] % 8 == 0:
+                h = x32.astype(np.float16)
+                if np.array_equal(h.astype(np.float32), x32):
+                    self.x16 = torch.from_numpy(h).to(self.device)
         self.labels = {
             "class": torch.from_numpy(self.y_array.astype(np.int32)).to(self.device),
             "spurious": torch.from_numpy(self.confounder_array.astype(np.int32)).to(self.device),

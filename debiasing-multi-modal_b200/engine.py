@@ -8,6 +8,8 @@ per-group counters, replayed through the reference's meter arithmetic on the hos
 """
 from __future__ import annotations
 
+import os
+
 import sys
 import time
 
@@ -256,8 +258,23 @@ def _run_eval(loader, classifier, target, spurious_prompts=False):
         return loss_sum, counts, sizes, base.n_groups
     old, ad, w = classifier.kernel_adapters()
     That = classifier.prompt_matrix(spurious=spurious_prompts)
-    ops.eval_fwd(base.x, base.labels[target], base.labels["group"], ad, That, 1.0 / classifier.temperature, stats, bs,
-                 idx=idx, n_rows=n, old_ad=old, ebd_weight=w, G=base.n_groups)
+    if getattr(base, "x16", None) is not None and n > 0 and ops.eval_f16_supported(base.x16.shape[1], ad.H, That.shape[1]) \
+            and os.environ.get("DBMM_EVAL_F16", "1") != "0":
+        # fp16-resident rows through the kind::f16 kernels; a Subset (the val half of the reference's stratified split) is
+        # gathered once into its own contiguous copy and kept with the loader
+        if contiguous:
+            x16, yy, gg = base.x16, base.labels[target], base.labels["group"]
+        else:
+            cache = loader.__dict__.setdefault("_f16_rows", {})
+            key = (hash(rows.tobytes()), target)
+            if key not in cache:
+                il = idx.long()
+                cache[key] = (base.x16[il].contiguous(), base.labels[target][il].contiguous(), base.labels["group"][il].contiguous())
+            x16, yy, gg = cache[key]
+        ops.eval_fwd_f16(x16, yy, gg, ad, That, 1.0 / classifier.temperature, stats, bs, old_ad=old, ebd_weight=w, G=base.n_groups)
+    else:
+        ops.eval_fwd(base.x, base.labels[target], base.labels["group"], ad, That, 1.0 / classifier.temperature, stats, bs,
+                     idx=idx, n_rows=n, old_ad=old, ebd_weight=w, G=base.n_groups)
     loss_sum, counts = stats.host()
     return loss_sum, counts, sizes, base.n_groups
 

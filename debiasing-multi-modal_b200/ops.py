@@ -176,6 +176,37 @@ def eval_fwd(X: torch.Tensor, y: torch.Tensor, grp, ad: AdapterTensors, That: to
     return logits, pred
 
 
+def eval_f16_supported(D: int, H: int, Cn: int) -> bool:
+    return bool(_lib.load().dbmm_eval_f16_supported(D, H, Cn))
+
+
+def eval_fwd_f16(X16: torch.Tensor, y: torch.Tensor, grp, ad: AdapterTensors, That: torch.Tensor, inv_tau: float,
+                 stats: BatchStatsBuffers | None, batch_size: int, *, old_ad: AdapterTensors | None = None,
+                 ebd_weight: float = 0.5, G: int = 4, want_logits=False, want_pred=False):
+    """validate()/validate_zs() forward over the fp16-resident copy of the embeddings (dbmm_eval_fwd_f16): same results as
+    eval_fwd when the embeddings are fp16-valued, at half the bytes and twice the tensor-core rate."""
+    lib = _lib.load()
+    _check(X16, torch.float16, "X16", contiguous=False)
+    if X16.stride(1) != 1:
+        raise DbmmError("X16 rows must be contiguous")
+    _check(That, torch.float32, "That")
+    N, D, H, Cn = X16.shape[0], X16.shape[1], ad.H, That.shape[1]
+    if That.shape[0] != D or ad.D != D:
+        raise DbmmError("dimension mismatch between X, adapter and text prompts")
+    G = _label_args(y, grp, G)
+    nad = 2 if old_ad is not None else 1
+    ws = workspace(lib.dbmm_eval_f16_workspace_bytes(max(N, 1), D, H, Cn, nad), X16.device)
+    logits = torch.empty((N, Cn), dtype=torch.float32, device=X16.device) if want_logits else None
+    pred = torch.empty((N,), dtype=torch.int32, device=X16.device) if want_pred else None
+    st = stats.c() if stats is not None else BatchStats(None, None)
+    old_p = old_ad.ptrs() if old_ad is not None else None
+    _lib.check(lib.dbmm_eval_fwd_f16(X16.data_ptr(), X16.stride(0), _ptr(y), _ptr(grp), N, D, H, Cn, G,
+                                     C.byref(old_p) if old_p is not None else None, C.byref(ad.ptrs()), ebd_weight,
+                                     That.data_ptr(), inv_tau, batch_size, st, _ptr(logits), _ptr(pred),
+                                     ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return logits, pred
+
+
 class TrainBuffers:
     """Flat gradient + momentum of one optimizer (torch.optim.SGD state, demo/util.py:118-136)."""
 

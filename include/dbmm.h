@@ -126,6 +126,23 @@ int dbmm_eval_fwd(const float* X, int64_t ldx, const int32_t* idx, const int32_t
                   void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * The same eval forward over an fp16-RESIDENT embedding matrix (X16: IEEE half, row stride ldx halfs, rows contiguous in
+ * dataset order: labels are indexed by row).  CLIP emits fp16 (clip/model.py:375-396 of the reference) and the packed store
+ * keeps it losslessly, so this reads 2 bytes per element and runs kind::f16 tensor-core MMAs (csrc/eval_f16.cuh); W1, h and
+ * the Gram block enter as scaled fp16 pairs (22 significant bits, as the tf32 hi + lo of dbmm_eval_fwd).  Needs H == 128,
+ * D % 8 == 0, C <= 4 (dbmm_eval_f16_supported); callers fall back to dbmm_eval_fwd otherwise.  Replaces, like
+ * dbmm_eval_fwd, validate / validate_zs of final_main.py:655-803.
+ */
+int dbmm_eval_f16_supported(int D, int H, int C);
+size_t dbmm_eval_f16_workspace_bytes(int64_t rows, int D, int H, int C, int n_adapters);
+int dbmm_eval_fwd_f16(const void* X16, int64_t ldx, const int32_t* y, const int32_t* grp,
+                      int64_t N, int D, int H, int C, int G,
+                      const dbmm_adapter* old_ad, const dbmm_adapter* ad, float ebd_weight,
+                      const float* That, float inv_tau, int64_t batch_size,
+                      dbmm_batch_stats stats, float* logits_out, int32_t* pred_out,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/*
  * One training step on B_local rows (train_one_epoch / train_reg_seq_one_epoch body).
  *   B_global: rows of the whole (possibly multi-GPU) batch -- BatchNorm statistics and the CE mean use it.
  *   old_ad != NULL selects the stage-2 MultipleAdapter step: both adapters run batch-stat BatchNorm and
