@@ -44,10 +44,14 @@ def peaks():
 
 
 def traffic_from_profiles(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(path):
-        return json.load(open(path)).get(kernel)
+    """dram bytes per launch of `kernel` from the committed ncu --set full captures (profiles/r2_traffic.json, then the
+    round-1 file), or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            v = json.load(open(path)).get(kernel)
+            if v is not None:
+                return v
     return None
 
 
@@ -179,6 +183,37 @@ def reference_dataloader_leg():
             "num_workers": r["num_workers"], "cores": r["threads"], "note": r["note"]}
 
 
+def accuracy_leg():
+    """The other half of BASELINE.json's metric: worst-group accuracy delta against the reference on the FULL config 0 / 1
+    hyper-parameters (run_final_main.sh:1-31: 4,795 train rows, bs 1024 / bsr 256, 100 epochs / 40 feature-learning, lr 1.0).
+    The reference's numbers for these synthetic files and this seed are the committed golden (tests/golden/e2e_cases.json,
+    generated by oracle/make_golden.py from the unmodified reference); the drop-in runs the same CLI here."""
+    import contextlib
+    import io
+    import tempfile
+    from dbmm import cli, synth
+    case = json.load(open(os.path.join(ROOT, "tests", "golden", "e2e_cases.json")))["waterbirds_full"]
+    t0 = time.perf_counter()
+    with tempfile.TemporaryDirectory() as tmp, contextlib.redirect_stdout(io.StringIO()):
+        ds = synth.make_dataset(**case["synth"])
+        paths = synth.write_reference_files(ds, tmp)
+        argv = [a for a in case["argv"] if a != "--save_results"]
+        for k, v in paths.items():
+            argv += [f"--{k}", v]
+        t1 = time.perf_counter()
+        (tr, va, te), _ = cli.train_all_epochs(cli.parse_option(argv))
+        run = cli.train_all_epochs.last_run
+    t2 = time.perf_counter()
+    ref_test = case["final"][2]
+    keys = ("acc_0_0", "acc_0_1", "acc_1_0", "acc_1_1", "mean_acc", "worst_acc")
+    return {"case": "waterbirds-shaped synthetic, adapter_reg_seq_alter --add_adapter --warm_reg, bs 1024 / bsr 256, lr 1.0, 100 epochs / 40 FL, seed 42",
+            "worst_group_acc": float(te["worst_acc"]), "reference_worst_group_acc": float(ref_test["worst_acc"]),
+            "worst_group_acc_delta": float(te["worst_acc"]) - float(ref_test["worst_acc"]),
+            "selected_epoch": int(run["best_epoch"]), "reference_selected_epoch": int(case["best_epoch"]),
+            "test_dict_max_abs_delta": max(abs(float(te[k]) - float(ref_test[k])) for k in keys),
+            "train_seconds": t2 - t1, "file_write_seconds": t1 - t0}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -226,6 +261,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dbmm", choices=["dbmm", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-accuracy", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -384,24 +420,103 @@ def main():
                         "hbm_frac": ALG_BYTES_PER_EMB * BATCH / t_step / 1e9 / P["hbm"]}
         out["roofline"] = roof
 
-    # ---- eval leg: validate()-style forward over the resident matrix (HBM-bound half of the path)
+    # ---- eval leg: validate()-style forward over the resident matrix (HBM-bound half of the path).  The resident format is
+    #      what the packed store holds: fp16 (lossless for CLIP embeddings) -> dbmm_eval_fwd_f16; the fp32-resident kernel
+    #      (dbmm_eval_fwd, tf32 hi + lo) is timed beside it.  Roofline: ALGORITHMIC bytes of SURVEY.md section 8d (one fp32 row,
+    #      4,096 B per embedding) over the measured copy bandwidth, whatever the kernel really moves (`traffic`).
     st_e = ops.BatchStatsBuffers((N_TRAIN + 511) // 512, G, device=dev)
-    for _ in range(2):
-        ops.eval_fwd(X, y, g, ad, That, 100.0, st_e, 512, G=G)
-    barrier()
-    e0.record()
-    n_eval = 5
-    for _ in range(n_eval):
-        ops.eval_fwd(X, y, g, ad, That, 100.0, st_e, 512, G=G)
-    e1.record()
-    barrier()
-    ms_e = e0.elapsed_time(e1) / n_eval
+    X16 = X.half()
+    f16_exact = bool(torch.equal(X16.float(), X)) and ops.eval_f16_supported(D, H, C)
+
+    def time_eval(fn, reps=5):
+        for _ in range(2):
+            fn()
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / reps
+
+    ms_e32 = time_eval(lambda: ops.eval_fwd(X, y, g, ad, That, 100.0, st_e, 512, G=G))
+    ms_e = time_eval(lambda: ops.eval_fwd_f16(X16, y, g, ad, That, 100.0, st_e, 512, G=G)) if f16_exact else ms_e32
+    del X16
     if rank == 0:
         ev = N_TRAIN / (ms_e * 1e-3)
         out["eval"] = {"value": ev * world, "unit": "embeddings/s", "ms_per_pass": ms_e,
+                       "resident_dtype": "f16 (dbmm_eval_fwd_f16, kind::f16 tcgen05)" if f16_exact else "f32",
                        "roofline": {"bound": "hbm", "achieved": ev * ALG_BYTES_PER_EMB / 1e9, "peak": P["hbm"], "unit": "GB/s",
                                     "frac": ev * ALG_BYTES_PER_EMB / 1e9 / P["hbm"],
-                                    "traffic": traffic_from_profiles("eval_fwd_per_row"), "traffic_unit": "DRAM bytes per row (algorithmic 4096)"}}
+                                    "traffic": traffic_from_profiles("eval_fwd_f16_per_row" if f16_exact else "eval_fwd_per_row"),
+                                    "traffic_unit": "DRAM bytes per row (algorithmic 4096)"},
+                       "fp32_resident": {"value": N_TRAIN / (ms_e32 * 1e-3) * world, "ms_per_pass": ms_e32,
+                                         "frac": N_TRAIN / (ms_e32 * 1e-3) * ALG_BYTES_PER_EMB / 1e9 / P["hbm"]}}
+
+    # ---- batched-adapter sweep (BASELINE config 5): 64 members in lock step over one resident matrix, members sharded over
+    #      the ranks with no communication.  Rows bounded to 40,960 per member-epoch to keep the leg short.
+    M_total, n_b = 64, 40 * BATCH
+    M_local = M_total // world
+    from dbmm.modules import Adapter
+    members = []
+    for m in range(M_local):
+        torch.manual_seed(1000 + rank * M_local + m)
+        members.append(ops.SweepMember(order=torch.randperm(n_b, device=dev).to(torch.int32), ad=Adapter(D, H).to(dev).tensors(),
+                                       buf=ops.TrainBuffers(D, H, device=dev), stats=ops.BatchStatsBuffers(n_b // BATCH, G, device=dev),
+                                       lrs=np.full(n_b // BATCH, 0.01, np.float32)))
+    Xb = X[:n_b]
+    ops.train_epoch_batched(Xb, members, BATCH, y, g, That, 100.0)
+    barrier()
+    e0.record()
+    for _ in range(2):
+        ops.train_epoch_batched(Xb, members, BATCH, y, g, That, 100.0)
+    e1.record()
+    barrier()
+    ms_b = e0.elapsed_time(e1) / 2
+    if world > 1:
+        t = torch.tensor([ms_b], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_b = float(t.item())
+    del members
+    if rank == 0:
+        rate = M_total * n_b / (ms_b * 1e-3)
+        out["batched_sweep"] = {"members": M_total, "members_per_gpu": M_local, "rows_per_member_epoch": n_b, "value": rate,
+                                "unit": "embeddings/s (all members, all GPUs)", "ms_per_epoch": ms_b,
+                                "us_per_member_step": 1e3 * ms_b / (n_b // BATCH) / M_local,
+                                "algorithmic_tflops_per_gpu": ALG_FLOP_TRAIN * rate / world / 1e12,
+                                "frac_of_bf16_sustained_peak": ALG_FLOP_TRAIN * rate / world / 1e12 / P["tc_sustained"],
+                                "hbm_frac": ALG_BYTES_PER_EMB * rate / world / 1e9 / P["hbm"],
+                                "scaling": "members sharded over the ranks, zero communication",
+                                "api": "dbmm_train_epoch_batched (k_gemm1_tc / k_hs_rows / k_wgrad_tc / k_tail_w1 / k_hs_w2, one launch per step for all members)"}
+
+    # ---- data-parallel parity (N > 1, outside the timed region): one epoch over shards of ONE global batch order against
+    #      the single-rank run of the same order from the same initial weights
+    if world > 1:
+        xs, ys, gs, _ = synth_rows(12 * BATCH + 333, seed=777)
+        Xs, ys_d, gs_d = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev), torch.from_numpy(gs).to(dev)
+        n_s = Xs.shape[0]
+        st_s = (n_s + BATCH - 1) // BATCH
+        order_s = torch.randperm(n_s, generator=torch.Generator().manual_seed(3)).to(torch.int32).to(dev)
+        lr_s = np.full(st_s, 0.05, np.float32)
+        _, ad_dp = fresh_model()
+        buf_dp, stats_dp = ops.TrainBuffers(D, H, device=dev), ops.BatchStatsBuffers(st_s, G, device=dev)
+        dp_g = parallel.DataParallelTrainer(local_batches=False)
+        dp_g.train_epoch(Xs, order_s, BATCH, ys_d, gs_d, ad_dp, That, 100.0, buf_dp, lr_s, stats_dp, G=G)
+        barrier()
+        if rank == 0:
+            _, ad_1 = fresh_model()
+            buf_1, stats_1 = ops.TrainBuffers(D, H, device=dev), ops.BatchStatsBuffers(st_s, G, device=dev)
+            ops.train_epoch(Xs, order_s, BATCH, ys_d, gs_d, ad_1, That, 100.0, buf_1, lr_s, stats_1, G=G)
+            torch.cuda.synchronize()
+            a, b = ad_dp.to_numpy(), ad_1.to_numpy()
+            dev_max = max(float(np.abs(a[k].astype(np.float64) - b[k]).max() / max(np.abs(b[k]).max(), 1e-30))
+                          for k in ("W1", "gamma", "beta", "W2", "b2", "running_mean", "running_var"))
+            c_dp, c_1 = stats_dp.host()[1], stats_1.host()[1]
+            out["dp_parity"] = {"max_rel_dev": dev_max, "counters_identical": bool(np.array_equal(c_dp, c_1)),
+                                "counter_max_abs_diff": int(np.abs(c_dp - c_1).max()), "rows": int(n_s), "steps": int(st_s),
+                                "what": f"one epoch, global batch {BATCH} sharded over {world} ranks vs the same order on one rank"}
+        dp_g.close()
+        barrier()
 
     # ---- kernels of BASELINE configs 3 / 4 (tcgen05 + TMA GEMMs), short legs, N = 1 only
     if rank == 0 and world == 1:
@@ -506,6 +621,11 @@ def main():
             out["reference_on_b200"] = {"value": rg["emb_per_s"], "unit": "embeddings/s",
                                         "what": "unmodified reference train_one_epoch under stock PyTorch eager on cuda:0, batches resident",
                                         "seconds": rg["seconds"], "rows": rg["rows"], "speedup_of_value": value / rg["emb_per_s"]}
+    if rank == 0 and world == 1 and not args.no_accuracy:
+        try:
+            out["accuracy"] = accuracy_leg()
+        except Exception as exc:                      # the throughput line must not die with the accuracy leg
+            out["accuracy"] = {"error": repr(exc)[:300]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
