@@ -150,6 +150,67 @@ def extra_legs(torch, ops, dev, P, e0, e1):
     return res
 
 
+def multi_gpu_legs(torch, dist, ops, parallel, dev, P, e0, e1, world, rank, barrier):
+    """BASELINE configs 4 and 3 at N > 1.  Config 4: the zero-shot head over 10 M x 1024-d rows x 1,000 prompts sharded by rows
+    (1.25 M rows = 5.1 GB per GPU, the 8-GPU share; rows independent, counters and loss all-reduced ONCE at the end).  Config 3: the
+    contrastive regulariser at global B = 8192, d = 768 with all-gathered negatives (parallel.supcon_distributed: NCCL all-gather
+    of the normalised rows, tcgen05 similarity GEMMs on each rank's anchors, reduce-scatter of the contrast-role gradient)."""
+    res = {}
+    n, c = 1250000, 1000
+    U = torch.empty(n, D, device=dev)
+    for s0 in range(0, n, 250000):
+        U[s0:s0 + 250000] = torch.randn(min(250000, n - s0), D, device=dev).half().float()
+    yh = torch.randint(0, c, (n,), device=dev, dtype=torch.int32)
+    gh = torch.randint(0, G, (n,), device=dev, dtype=torch.int32)
+    Th = ops.normalize_text(torch.randn(D, c, device=dev, generator=torch.Generator(device=dev).manual_seed(9)))
+    st = ops.BatchStatsBuffers((n + 1023) // 1024, G, device=dev)
+
+    def head_pass():
+        st.zero_()
+        ops.logits_ce(U, yh, gh, Th, 100.0, st, 1024, G=G)
+        tot = torch.cat([st.loss_sum.sum().reshape(1), st.counts.sum(0).reshape(-1).to(torch.float64)])
+        dist.all_reduce(tot)                       # the one exchange of the sharded head: loss sum + 2 G counters
+        return tot
+    head_pass()
+    barrier()
+    e0.record()
+    for _ in range(2):
+        tot = head_pass()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / 2], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ts = float(t.item()) * 1e-3
+    fl = 2.0 * D * c * n * world
+    res["head_c1000_sharded"] = {"rows_total": n * world, "rows_per_gpu": n, "prompts": c, "emb_per_s": n * world / ts, "ms": ts * 1e3,
+                                 "algorithmic_tflops_per_gpu": fl / ts / 1e12 / world,
+                                 "frac_of_bf16_sustained_peak": fl / ts / 1e12 / world / P["tc_sustained"],
+                                 "rows_counted": int(tot[1 + G:].sum().item()), "exchange": "one all-reduce of loss sum + 2G counters"}
+    del U
+    B, d = 8192, 768
+    Bl = B // world
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    Z = torch.nn.functional.normalize(torch.randn(Bl, d, device=dev, generator=gen), dim=1).contiguous()
+    lab = torch.randint(0, 4, (Bl,), device=dev, dtype=torch.int32, generator=gen)
+    for _ in range(2):
+        loss, dZ = parallel.supcon_distributed(Z, lab)
+    barrier()
+    e0.record()
+    for _ in range(3):
+        loss, dZ = parallel.supcon_distributed(Z, lab)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ts = float(t.item()) * 1e-3
+    fl = 6.0 * B * d * B
+    res["supcon_b8192_d768_global_negatives"] = {"global_batch": B, "rows_per_gpu": Bl, "emb_per_s": B / ts, "ms": ts * 1e3,
+                                                 "algorithmic_tflops_per_gpu": fl / ts / 1e12 / world, "loss": loss,
+                                                 "dZ_finite": bool(torch.isfinite(dZ).all().item()),
+                                                 "collectives": "all-gather Z + labels, all-reduce (loss, n_valid), reduce-scatter dZ (NCCL)"}
+    return res
+
+
 def cpu_reference_step(rows_x, rows_y, rows_g, T, n_sgd_steps):
     """`n_sgd_steps` batches through the reference's train_one_epoch on the host cores, tensors pre-loaded (bounded sample).
     kind "reference": the UNMODIFIED reference modules (final_main.Adapter / CustomCLIP / train_one_epoch, demo.util
@@ -282,6 +343,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"            # the version banner goes to stdout, where ONE JSON line is expected
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     P = peaks()
 
@@ -358,7 +420,7 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": workload_config(world), "clocks": clocks,
                "us_per_sgd_step": 1e3 * ms_per_step / steps_per_epoch, "final_epoch_mean_loss": final_loss,
-               "gpu_launches": args.steps * (steps_per_epoch * 6 + 3)}
+               "gpu_launches": args.steps * (steps_per_epoch * (8 if world == 1 else 6) + 3)}
 
     # ---- per-kernel timing inside the running step (CUDA events between the kernels, stream launches) -> roofline of the
     #      dominant kernel.  Algorithmic bytes / flops per launch: GEMM-1 and dW1 each stream the
@@ -501,7 +563,7 @@ def main():
         _, ad_dp = fresh_model()
         buf_dp, stats_dp = ops.TrainBuffers(D, H, device=dev), ops.BatchStatsBuffers(st_s, G, device=dev)
         dp_g = parallel.DataParallelTrainer(local_batches=False)
-        dp_g.train_epoch(Xs, order_s, BATCH, ys_d, gs_d, ad_dp, That, 100.0, buf_dp, lr_s, stats_dp, G=G)
+        dp_g.train_epoch(Xs, order_s, BATCH, ys_d, gs_d, ad_dp, That, 100.0, buf_dp, lr_s, stats_dp, G=G, reduce_stats=True)
         barrier()
         if rank == 0:
             _, ad_1 = fresh_model()
@@ -521,6 +583,10 @@ def main():
     # ---- kernels of BASELINE configs 3 / 4 (tcgen05 + TMA GEMMs), short legs, N = 1 only
     if rank == 0 and world == 1:
         out["extra"] = extra_legs(torch, ops, dev, P, e0, e1)
+    if world > 1:
+        ex = multi_gpu_legs(torch, dist, ops, parallel, dev, P, e0, e1, world, rank, barrier)
+        if rank == 0:
+            out["extra"] = ex
 
     # ---- e2e leg: host buffers in, statistics out, copies inside the timed region.  Two device buffer sets: the
     #      pinned-host -> device copy of epoch i+1's inputs runs on a copy stream while epoch i trains.  Host embeddings
