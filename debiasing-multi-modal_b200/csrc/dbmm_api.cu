@@ -622,9 +622,13 @@ static int train_step_impl(int phases, bool fresh,
     StepTailArgs ta;
     // W2 branch of the fused tail: S (sum of the row kernel's tiles, or the TN GEMM) -> dW2a, SGD on W2 / b2 -> next Gram matrix
     auto w2_branch = [&](cudaStream_t s_, bool first_pdl) -> int {
-        const bool tc_w2 = use_tc_w2(H, C) && !(p2p && p2p->world > 1);
+        const bool dp_p2p = p2p && p2p->world > 1;
+        const bool tc_w2 = use_tc_w2(H, C) && !(dp_p2p && tc_rows);      // (data parallel: the row kernel is the CUDA-core one)
         if (tc_rows) { if (int rc = launch_sum_spart(w.Spart, B, H, C, S_cur, tc_w2 ? w.ST : nullptr, s_, first_pdl)) return rc; }
-        else if (tc_w2) { if (int rc = launch_st_gemm(w.Lrows, w.Hrows, w.ST, B, H, C, s_, &tsp)) return rc; }
+        else if (tc_w2) {
+            if (int rc = launch_st_gemm(w.Lrows, w.Hrows, w.ST, B, H, C, s_, &tsp)) return rc;
+            if (dp_p2p) if (int rc = launch_p2p_sum_st(w.ST, H, *p2p, s_)) return rc;       // S^T summed over the ranks, in place
+        }
         else if (int rc = launch_s_gemm(w.Lrows, w.Hrows, S_cur, B, H, C, s_, &tsp)) return rc;
         if (tc_w2) {
             HsW2Args wa;

@@ -15,6 +15,7 @@
 // row m = H of G (b2-weighted sums) is column H of the tiles by symmetry plus three scalars per tile.
 #pragma once
 #include "hs_rows.cuh"
+#include "p2p.cuh"
 
 namespace dbmm {
 
@@ -336,6 +337,53 @@ __device__ __forceinline__ void sum_gpart_body(const SumGpartArgs& a) {
     a.G[e] = v;
 }
 __global__ void __launch_bounds__(256) k_sum_gpart(SumGpartArgs a) { sum_gpart_body(a); }
+
+// Data parallel: S^T summed over the ranks in place (peer memory, the S slots and flags of p2p.cuh).  CTA c pushes slice c of
+// the rank's S^T to every rank, raises flag [c][rank] everywhere, waits for slice c of every rank and adds them in rank order:
+// every rank ends with the same bits.  Off the critical path (W2 branch).
+constexpr int PS_CTAS = 16, PS_THREADS = 256;
+__global__ void __launch_bounds__(PS_THREADS) k_p2p_sum_st(float* ST, int n4, P2pArgs p) {
+    ptx::pdl_wait();                // S^T comes from the TN GEMM in front of this kernel
+    ptx::pdl_launch();
+    const unsigned inst = p2p_instance(p);
+    const int parity = inst & 1u, c = blockIdx.x, tid = threadIdx.x;
+    const int per = (n4 + PS_CTAS - 1) / PS_CTAS, lo4 = c * per, hi4 = min(n4, lo4 + per);
+    for (int e = lo4 + tid; e < hi4; e += PS_THREADS) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(ST) + e);
+        for (int r = 0; r < p.world; ++r) reinterpret_cast<float4*>(p2p_s_slot(p.peer[r], parity, p.rank))[e] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < p.world) {
+        unsigned* f = p2p_s_flag(p.peer[tid], c, p.rank);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(inst + 1u) : "memory");
+    }
+    if (tid < p.world) {
+        const unsigned* f = p2p_s_flag(p.peer[p.rank], c, tid);
+        unsigned v = 0;
+        unsigned long long t0 = 0;
+        for (unsigned spin = 0;; ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - (inst + 1u)) >= 0 || (p.skip & 8) || p2p_expired(p, t0, spin)) break;
+        }
+    }
+    __syncthreads();
+    char* me = p.peer[p.rank];
+    for (int e = lo4 + tid; e < hi4; e += PS_THREADS) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < p.world; ++r) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(p2p_s_slot(me, parity, r)) + e);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(ST)[e] = acc;
+    }
+}
+static int launch_p2p_sum_st(float* ST, int H, const P2pArgs& p, cudaStream_t st) {
+    const int n4 = (H + 1) * HR_SP_LD / 4;
+    DBMM_CHECK_ARG((size_t)(H + 1) * HR_SP_LD <= P2P_S_FLOATS && PS_CTAS <= P2P_S_CTAS, "S^T exceeds the peer-memory slot");
+    DBMM_CUDA(launch_pdl(k_p2p_sum_st, dim3(PS_CTAS), dim3(PS_THREADS), 0, st, ST, n4, p));
+    return DBMM_OK;
+}
 
 static inline size_t hs_gpart_floats(int D) { return (size_t)((D + HW_ROWS - 1) / HW_ROWS) * (HR_H + 1) * HR_SP_LD; }
 

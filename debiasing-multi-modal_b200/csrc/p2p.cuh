@@ -4,10 +4,12 @@
 //   channel 0  BatchNorm column sums [nad][2][H] fx64   k_reduce_stats: the LAST CTA to finish (atomic ticket) pushes the
 //              rank's vector to the other ranks, polls theirs, adds in rank order, writes the global sums back in place
 //   channel 1  (dgamma, dbeta) [2][H] fx64              k_wgrad_tc: CTA (0, 0) pushes in its prologue, every CTA polls
-//   dW1        [H][D] fp32                              k_tail_w1: every thread pushes its chunk-summed quad and polls the
-//              same quad of its peers; own quad from registers; no cross-CTA synchronisation at all
-//   S          [H+1+C][H+1] fp32                        k_tail_w2: CTA c stores slice c to every rank and raises flag
-//              [c][rank] (release, system scope); every CTA waits for all slices (off the critical path)
+//   dW1        [H][D] fp32                              k_tail_w1: reduce-scatter + all-gather by OWNER: rank o owns a contiguous
+//              1 / world of the quads; every thread pushes its chunk-summed quad to the owner only, the owner's thread sums the
+//              ranks in rank order, does the SGD step and pushes the UPDATED weights to every rank (2 x (N-1)/N x |W1| per rank
+//              instead of (N-1) x |W1|; momentum lives on the owner).  No cross-CTA synchronisation at all
+//   S          [H+1+C][H+1] fp32                        k_tail_w2 / k_p2p_sum_st: CTA c stores slice c to every rank and raises flag
+//              [c][rank] (release, system scope); the consumer waits for the slices it needs (off the critical path)
 //
 // Channels 0 / 1 and dW1 travel as "LL" words: every 32 data bits ride in an 8-byte store together with the instance tag;
 // 8-byte stores are atomic over NVLink, so the consumer polls the data words themselves -- no system fence, no flag store,
@@ -34,7 +36,8 @@ constexpr size_t P2P_S_OFF = P2P_CTRL_BYTES;                                    
 constexpr size_t P2P_G_OFF = P2P_S_OFF + sizeof(float) * 2 * P2P_MAX_WORLD * P2P_S_FLOATS;          // dW1 LL slots [parity][rank][P2P_G_FLOATS] x 8 B
 constexpr size_t P2P_SF_OFF = P2P_G_OFF + 8 * (size_t)2 * P2P_MAX_WORLD * P2P_G_FLOATS;             // S flags
 constexpr size_t P2P_LL_OFF = P2P_SF_OFF + (size_t)P2P_S_CTAS * 128;                               // fp64 LL slots [channel][parity][rank][P2P_VEC] x 16 B
-constexpr size_t P2P_BYTES = P2P_LL_OFF + (size_t)P2P_CHANNELS * 2 * P2P_MAX_WORLD * P2P_VEC * 16;
+constexpr size_t P2P_W_OFF = P2P_LL_OFF + (size_t)P2P_CHANNELS * 2 * P2P_MAX_WORLD * P2P_VEC * 16;   // updated-W1 LL slots [parity][P2P_G_FLOATS] x 8 B
+constexpr size_t P2P_BYTES = P2P_W_OFF + 8 * (size_t)2 * P2P_G_FLOATS;
 
 struct P2pArgs {
     unsigned long long timeout_ns;   // wall-clock bound of every wait
@@ -158,6 +161,10 @@ __device__ __forceinline__ float4 p2p_g_load(const P2pArgs& p, const unsigned lo
         if (ok || no_wait || p2p_expired(p, t0, spin)) break;
     }
     return make_float4(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1), __uint_as_float((unsigned)w2), __uint_as_float((unsigned)w3));
+}
+// the owner's updated W1 quads (all-gather half of the dW1 exchange): one slot per parity, written by the owner of each quad
+__device__ __forceinline__ unsigned long long* p2p_w_ll(char* buf, int parity) {
+    return reinterpret_cast<unsigned long long*>(buf + P2P_W_OFF) + (size_t)parity * P2P_G_FLOATS;
 }
 __device__ __forceinline__ float* p2p_s_slot(char* buf, int parity, int src) {
     return reinterpret_cast<float*>(buf + P2P_S_OFF) + ((size_t)parity * P2P_MAX_WORLD + src) * P2P_S_FLOATS;

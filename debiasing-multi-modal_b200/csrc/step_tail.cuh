@@ -74,15 +74,28 @@ __device__ __forceinline__ void tail_w1_body(const StepTailArgs& a) {
             for (int c = 0; c < ST_MAXCHUNK; ++c)
                 pt[c] = c < a.nchunk ? __ldcg(reinterpret_cast<const float4*>(a.part) + c * plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             if constexpr (P2P) {
-                // Data parallel: the rank's chunk-summed quad goes to every OTHER rank as LL words (data + instance tag in
-                // each 8-byte store: no fence, no flag, no barrier); the peers' quads are polled and everything is added
-                // in rank order, the own quad from registers -- every rank adds the same numbers in the same order.
+                // Data parallel, reduce-scatter + all-gather by owner (LL words: data + instance tag in each 8-byte store, no
+                // fence, no flag, no barrier).  A non-owner sends its chunk-summed quad to the owner and takes the owner's
+                // UPDATED weights back; the owner adds the ranks' quads in rank order (own quad from registers), runs SGD
+                // below and pushes the new weights to every rank: all replicas hold the same bits.
                 float4 mine = pt[0];
 #pragma unroll
                 for (int c = 1; c < ST_MAXCHUNK; ++c) { mine.x += pt[c].x; mine.y += pt[c].y; mine.z += pt[c].z; mine.w += pt[c].w; }
-                for (int r = 0; r < a.p2p.world; ++r)
-                    if (r != a.p2p.rank) p2p_g_store(p2p_g_ll(a.p2p.peer[r], parity, a.p2p.rank), i, mine, inst + 1u);
+                const int64_t per = (n4 + a.p2p.world - 1) / a.p2p.world;
+                const int owner = (int)(i / per);
                 char* me = a.p2p.peer[a.p2p.rank];
+                if (owner != a.p2p.rank) {
+                    p2p_g_store(p2p_g_ll(a.p2p.peer[owner], parity, a.p2p.rank), i, mine, inst + 1u);
+                    const float4 w = p2p_g_load(a.p2p, p2p_w_ll(me, parity), i, inst + 1u, (a.p2p.skip & 4) != 0);
+                    const float wx[4] = {w.x, w.y, w.z, w.w};
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { hi[q] = __uint_as_float(__float_as_uint(wx[q]) & 0xffffe000u); lo[q] = wx[q] - hi[q]; }
+                    reinterpret_cast<float4*>(a.W1)[i] = w;
+                    reinterpret_cast<float4*>(a.whi)[i] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    reinterpret_cast<float4*>(a.wlo)[i] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    continue;
+                }
 #pragma unroll
                 for (int c = 0; c < ST_MAXCHUNK; ++c) pt[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -109,6 +122,11 @@ __device__ __forceinline__ void tail_w1_body(const StepTailArgs& a) {
             reinterpret_cast<float4*>(a.whi)[i] = make_float4(hi[0], hi[1], hi[2], hi[3]);
             reinterpret_cast<float4*>(a.wlo)[i] = make_float4(lo[0], lo[1], lo[2], lo[3]);
             reinterpret_cast<float4*>(a.g + oW1)[i] = gs;
+            if constexpr (P2P) {
+                const float4 w = make_float4(po[0], po[1], po[2], po[3]);
+                for (int r = 0; r < a.p2p.world; ++r)
+                    if (r != a.p2p.rank) p2p_g_store(p2p_w_ll(a.p2p.peer[r], parity), i, w, inst + 1u);
+            }
         }
         return;
     }
