@@ -86,6 +86,9 @@ SIGNATURES = {
     "dbmm_eval_f16_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),
     "dbmm_eval_fwd_f16": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32, _vp, _f32,
                                     _i64, BatchStats, _vp, _vp, _vp, _sz, _vp]),
+    "dbmm_contrastive_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "dbmm_contrastive_step": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _AP, _i32, _f32, _f32, _vp, _vp, _f32, _f32, _f32, _i32,
+                                        _vp, _vp, _vp, _sz, _vp]),
     "dbmm_train_step": (C.c_int, [_i32, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32,
                                   _vp, _f32, _vp, _vp, _f32, _f32, _f32, _i32, BatchStats, _i64, _vp, _sz, _vp]),
     "dbmm_train_step_ex": (C.c_int, [_i32, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32,

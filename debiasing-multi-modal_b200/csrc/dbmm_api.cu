@@ -17,6 +17,7 @@
 #include "export_rows.cuh"
 #include "head_supcon.cuh"
 #include "eval_f16.cuh"
+#include "contrastive.cuh"
 #include "nccl_dyn.cuh"
 #include "linear_probe.cuh"
 
@@ -1546,6 +1547,112 @@ int dbmm_sgd_step(float* p, const float* g, float* v, int64_t n, float lr, float
     int grid = ceil_div(n, 256 * 4);
     if (grid > 148 * 8) grid = 148 * 8;
     k_sgd_flat<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, v, n, lr, momentum, weight_decay, first_step);
+    DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+// ---- contrastive-adapter training step (contrastive.cuh)
+struct ContrastiveWs {
+    float *h, *h_hi, *h_lo, *w2_hi, *w2_lo, *w2t_hi, *w2t_lo, *U, *dUa, *dUb, *dz_hi, *dz_lo, *dzt_hi, *dzt_lo, *ht_hi, *ht_lo, *dh, *inv_xn, *inv_n;
+    int32_t* labels_b; double* loss_sum; int32_t* n_valid; void* train; void* supcon; size_t train_bytes, supcon_bytes, total; int Bp;
+};
+static ContrastiveWs carve_contrastive_ws(void* base, int B, int D, int H) {
+    ContrastiveWs w; char* p = (char*)base; size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+    w.Bp = (B + 3) & ~3;
+    const size_t bh = sizeof(float) * (size_t)B * H, bd = sizeof(float) * (size_t)B * D, dh = sizeof(float) * (size_t)D * H;
+    const size_t o[] = {take(bh), take(bh), take(bh), take(dh), take(dh), take(dh), take(dh), take(bd), take(bd), take(bd), take(bd), take(bd),
+                        take(sizeof(float) * (size_t)D * w.Bp), take(sizeof(float) * (size_t)D * w.Bp), take(sizeof(float) * (size_t)H * w.Bp),
+                        take(sizeof(float) * (size_t)H * w.Bp), take(bh), take(sizeof(float) * B), take(sizeof(float) * B),
+                        take(sizeof(int32_t) * B), take(sizeof(double)), take(sizeof(int32_t))};
+    w.train_bytes = carve_train_ws(nullptr, B, D, H, 1, 1).total;
+    w.supcon_bytes = carve_supcon_ws(nullptr, B, B, D).total;
+    const size_t ot = take(w.train_bytes), os = take(w.supcon_bytes);
+    w.total = off;
+    float** f[] = {&w.h, &w.h_hi, &w.h_lo, &w.w2_hi, &w.w2_lo, &w.w2t_hi, &w.w2t_lo, &w.U, &w.dUa, &w.dUb, &w.dz_hi, &w.dz_lo, &w.dzt_hi, &w.dzt_lo,
+                   &w.ht_hi, &w.ht_lo, &w.dh, &w.inv_xn, &w.inv_n};
+    for (int i = 0; i < 19; ++i) *f[i] = (float*)(p + o[i]);
+    w.labels_b = (int32_t*)(p + o[19]); w.loss_sum = (double*)(p + o[20]); w.n_valid = (int32_t*)(p + o[21]);
+    w.train = p + ot; w.supcon = p + os;
+    return w;
+}
+
+size_t dbmm_contrastive_workspace_bytes(int B, int D, int H) {
+    if (B < 2 || D < 4 || H < 1) return 0;
+    return carve_contrastive_ws(nullptr, B, D, H).total;
+}
+
+int dbmm_contrastive_step(const float* X, int64_t ldx, const int32_t* idx, const int32_t* labels, int B, int D, int H,
+                          const dbmm_adapter* ad, int pre_norm, float inv_tau_cl, float loss_weight,
+                          float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
+                          double* loss_out, int32_t* n_valid_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_dims(D, H, 1, 1)) return rc;
+    if (int rc = check_adapter(ad, "trainable")) return rc;
+    DBMM_CHECK_ARG(X && labels && grads && momentum_buf && ws && ldx >= D, "NULL X / labels / grads / momentum / workspace");
+    DBMM_CHECK_ARG(B > 1, "BatchNorm needs more than 1 row per batch in training (got %d)", B);
+    DBMM_CHECK_SHAPE(use_tc_gemm1(D, H) && use_tc_wgrad(D, H) && H % 4 == 0, "contrastive step needs the tensor-core GEMM shapes (D %% 128 == 0, H %% 32 == 0; D=%d H=%d)", D, H);
+    ContrastiveWs w = carve_contrastive_ws(ws, B, D, H);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    TrainWs tw = carve_train_ws(w.train, B, D, H, 1, 1);
+    const size_t np = dbmm_param_count(D, H);
+    const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
+    if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * np, st));
+    DBMM_CUDA(cudaMemsetAsync(w.loss_sum, 0, sizeof(double), st));
+    DBMM_CUDA(cudaMemsetAsync(w.n_valid, 0, sizeof(int32_t), st));
+    // ---- forward: x' = x / |x|, a = x' W1^T + b1 (batch statistics), h, z = h W2^T + b2, u = z / |z|
+    k_ca_rows_in<<<ceil_div(B, 8), 256, 0, st>>>(X, ldx, idx, B, D, labels, pre_norm, w.inv_xn, w.labels_b);
+    if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, nullptr, ad, tw.A, nullptr, tw.whi, tw.wlo, true, 1, nullptr, st)) return rc;
+    k_ca_bn_stats<<<ceil_div(H, 32), 256, 0, st>>>(tw.A, ad->b1, w.inv_xn, B, H, tw.colsum);
+    k_ca_hidden<<<148, 256, 0, st>>>(tw.A, tw.colsum, ad->gamma, ad->beta, B, H, w.h, w.h_hi, w.h_lo);
+    k_split_hi_lo<<<148, 256, 0, st>>>(ad->W2, H, w.w2_hi, w.w2_lo, D, H, H);
+    DBMM_LAUNCH_CHECK();
+    TcGemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = B; g.N = D; g.K = H; g.scale = 1.f; g.C = w.U; g.ldc = D;
+    if (int rc = launch_tc_gemm_nt<true, EPI_STORE>(w.h_hi, w.h_lo, H, w.w2_hi, w.w2_lo, H, g, st)) return rc;
+    k_ca_normalize<<<ceil_div(B, 8), 256, 0, st>>>(w.U, ad->b2, B, D, w.inv_n);
+    DBMM_LAUNCH_CHECK();
+    // ---- loss and its gradient w.r.t. u: the B x B similarity GEMMs
+    if (int rc = dbmm_supcon_fwd(w.U, B, D, 0, B, w.labels_b, inv_tau_cl, w.loss_sum, w.n_valid, nullptr, w.supcon, w.supcon_bytes, stream)) return rc;
+    if (int rc = dbmm_supcon_bwd(w.U, B, D, 0, B, inv_tau_cl, w.n_valid, w.dUa, w.dUb, 0, w.supcon, w.supcon_bytes, stream)) return rc;
+    k_ca_loss_out<<<1, 1, 0, st>>>(w.loss_sum, w.n_valid, loss_weight, loss_out, n_valid_out);
+    // ---- backward: dz, db2, dh = dz W2, dW2 = dz^T h, ReLU / BatchNorm backward, dW1 = da^T x'
+    k_ca_dz<<<ceil_div(B, 8), 256, 0, st>>>(w.U, w.dUa, w.dUb, w.inv_n, loss_weight, B, D, w.dz_hi, w.dz_lo);
+    k_colsum_rows<<<ceil_div(D, 32), 256, 0, st>>>(w.dUa, B, D, D, grads + ob2);
+    k_transpose_split<<<dim3(ceil_div(H, 32), ceil_div(D, 32)), 256, 0, st>>>(ad->W2, H, w.w2t_hi, w.w2t_lo, D, H, D);       // [H][D]
+    DBMM_LAUNCH_CHECK();
+    memset(&g, 0, sizeof(g));
+    g.M = B; g.N = H; g.K = D; g.scale = 1.f; g.C = w.dh; g.ldc = H;
+    if (int rc = launch_tc_gemm_nt<true, EPI_STORE>(w.dz_hi, w.dz_lo, D, w.w2t_hi, w.w2t_lo, D, g, st)) return rc;
+    k_transpose_split<<<dim3(ceil_div(D, 32), ceil_div(B, 32)), 256, 0, st>>>(w.dUa, D, w.dzt_hi, w.dzt_lo, B, D, w.Bp);      // dz^T [D][Bp]
+    k_transpose_split<<<dim3(ceil_div(H, 32), ceil_div(B, 32)), 256, 0, st>>>(w.h, H, w.ht_hi, w.ht_lo, B, H, w.Bp);          // h^T  [H][Bp]
+    DBMM_LAUNCH_CHECK();
+    memset(&g, 0, sizeof(g));
+    g.M = D; g.N = H; g.K = B; g.scale = 1.f; g.C = grads + oW2; g.ldc = H;
+    if (int rc = launch_tc_gemm_nt<true, EPI_STORE>(w.dzt_hi, w.dzt_lo, w.Bp, w.ht_hi, w.ht_lo, w.Bp, g, st)) return rc;
+    k_ca_bn_bwd<<<ceil_div(H, 32), 256, 0, st>>>(w.dh, tw.A, tw.colsum, ad->gamma, ad->beta, B, H, tw.dahat, tw.dgb, grads + ob1, grads + og, grads + obeta);
+    DBMM_LAUNCH_CHECK();
+    WgradTcArgs t;
+    memset(&t, 0, sizeof(t));
+    t.X = X; t.ldx = ldx; t.idx = idx; t.B = B; t.Bg = B; t.D = D; t.H = H; t.A = tw.A; t.dahat = tw.dahat; t.colsum = tw.colsum; t.dgb = tw.dgb;
+    t.gamma = ad->gamma; t.part = tw.part; t.dgb_wb = tw.dgb; t.rowscale = pre_norm ? w.inv_xn : nullptr;
+    const int nchunk = wgrad_tc_chunks(B, &t.rows_per_chunk);
+    if (int rc = launch_wgrad_tc(t, nchunk, st)) return rc;
+    k_sum_chunks<<<148, 256, 0, st>>>(tw.part, nchunk, (int64_t)H * D / 4, grads + oW1);
+    DBMM_LAUNCH_CHECK();
+    // ---- optimizer (torch.optim.SGD semantics) and the BatchNorm running statistics of the train-mode forward
+    {
+        float* tensors[6] = {ad->W1, ad->b1, ad->gamma, ad->beta, ad->W2, ad->b2};
+        const size_t offs[7] = {oW1, ob1, og, obeta, oW2, ob2, np};
+        for (int k = 0; k < 6; ++k)
+            if (int rc = dbmm_sgd_step(tensors[k], grads + offs[k], momentum_buf + offs[k], (int64_t)(offs[k + 1] - offs[k]), lr, momentum,
+                                       weight_decay, 0, stream)) return rc;
+    }
+    BnRunningArgs b;
+    b.colsum = tw.colsum; b.nad = 1; b.H = H; b.Bg = B;
+    b.rm[0] = b.rm[1] = ad->running_mean; b.rv[0] = b.rv[1] = ad->running_var; b.nbt[0] = b.nbt[1] = (long long*)ad->num_batches_tracked;
+    k_bn_running<<<1, 256, 0, st>>>(b);
     DBMM_LAUNCH_CHECK();
     return DBMM_OK;
 }

@@ -37,6 +37,7 @@ struct WgradTcArgs {
     int rows_per_chunk;    // multiple of WG_BK
     int pack;              // data parallel: request only the used part of the stage ring
     int stages;            // set by the launcher: min(WG_STAGES, 64-row sub-tiles per chunk)
+    const float* rowscale; // optional [B]: da of row b is multiplied by it (input normalisation of the contrastive step: x' = x / |x|)
     P2pArgs p2p; fx64* dgb_wb;     // data parallel over peer memory: global dgamma / dbeta in (channel 1), written back by CTA (0, 0)
 };
 
@@ -118,12 +119,13 @@ __device__ __forceinline__ void wgrad_tc_body(const WgradTcArgs& a) {
             float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
             if (b < b_end && j < H) {
                 const float ax[4] = {av[i].x, av[i].y, av[i].z, av[i].w}, dx[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+                const float rs = a.rowscale ? __ldg(a.rowscale + b) : 1.0f;
                 float h4[4], l4[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float rstd = sCst[1][j + q];
                     const float ah = (ax[q] - sCst[0][j + q]) * rstd;
-                    const float da = (dx[q] - sCst[2][j + q] - ah * sCst[3][j + q]) * rstd;
+                    const float da = (dx[q] - sCst[2][j + q] - ah * sCst[3][j + q]) * rstd * rs;
                     h4[q] = __uint_as_float(__float_as_uint(da) & 0xffffe000u);
                     l4[q] = da - h4[q];
                 }

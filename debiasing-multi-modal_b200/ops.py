@@ -494,6 +494,26 @@ def logits_ce(U: torch.Tensor, y, grp, That: torch.Tensor, inv_tau: float, stats
     return pred
 
 
+def contrastive_step(X, labels, ad: AdapterTensors, buf: "TrainBuffers", lr: float, *, idx=None, pre_norm=True, tau_cl=0.1,
+                     loss_weight=0.1, momentum=0.9, weight_decay=5e-5, loss_out=None, n_valid_out=None):
+    """One SGD step of `--tl_method contrastive_adapter` on the rows idx (or all rows) of X: u = L2(adapter(L2(x))), all-anchor
+    supervised contrastive loss with the given labels, D-wide backward, SGD (dbmm_contrastive_step).  loss_out: float64 [1]
+    device tensor the weighted mean loss is ADDED to."""
+    lib = _lib.load()
+    _check(X, torch.float32, "X", contiguous=False)
+    _check(labels, torch.int32, "labels")
+    if idx is not None:
+        _check(idx, torch.int32, "idx")
+    B = int(idx.numel() if idx is not None else X.shape[0])
+    D, H = X.shape[1], ad.H
+    ws = workspace(lib.dbmm_contrastive_workspace_bytes(B, D, H), X.device)
+    _lib.check(lib.dbmm_contrastive_step(X.data_ptr(), X.stride(0), _ptr(idx), labels.data_ptr(), B, D, H, C.byref(ad.ptrs()),
+                                         1 if pre_norm else 0, 1.0 / tau_cl, loss_weight, buf.grads.data_ptr(), buf.momentum.data_ptr(),
+                                         lr, momentum, weight_decay, 1 if buf.first_step else 0, _ptr(loss_out), _ptr(n_valid_out),
+                                         ws.data_ptr(), ws.numel(), _stream_ptr()))
+    buf.first_step = False
+
+
 class SupconState:
     """Device scalars of one contrastive step: sum of per-anchor losses and number of valid anchors."""
 

@@ -143,6 +143,22 @@ int dbmm_eval_fwd_f16(const void* X16, int64_t ldx, const int32_t* y, const int3
                       void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * One training step of `--tl_method contrastive_adapter` (accepted by the reference's CLI, final_main.py:230, without a runnable
+ * branch; formula and epoch: demo/visualizer_supcon.py:412-508, 1522-1587; forward_ca: workspace/jinsu/SupCon.ipynb:109-113):
+ *     u = L2(adapter(L2(x)))  (pre_norm != 0: the input normalisation of forward_ca; head = identity),
+ *     L = loss_weight * all-anchor supervised contrastive loss of the batch (labels[row], temperature 1 / inv_tau_cl),
+ * forward, D-wide backward through the normalisation / GEMM-2 / ReLU / batch-stat BatchNorm / GEMM-1, SGD on the six adapter
+ * tensors (torch.optim.SGD semantics) and the BatchNorm running statistics.  The B x B similarity and its gradients are the
+ * tcgen05 GEMMs of dbmm_supcon_fwd / dbmm_supcon_bwd.  *loss_out += the weighted mean loss over the valid anchors.
+ * grads: [dbmm_param_count] flat gradient (written), momentum_buf: flat momentum (zeroed when first_step).
+ */
+size_t dbmm_contrastive_workspace_bytes(int B, int D, int H);
+int dbmm_contrastive_step(const float* X, int64_t ldx, const int32_t* idx, const int32_t* labels, int B, int D, int H,
+                          const dbmm_adapter* ad, int pre_norm, float inv_tau_cl, float loss_weight,
+                          float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
+                          double* loss_out, int32_t* n_valid_out, void* ws, size_t ws_bytes, void* stream);
+
+/*
  * One training step on B_local rows (train_one_epoch / train_reg_seq_one_epoch body).
  *   B_global: rows of the whole (possibly multi-GPU) batch -- BatchNorm statistics and the CE mean use it.
  *   old_ad != NULL selects the stage-2 MultipleAdapter step: both adapters run batch-stat BatchNorm and
