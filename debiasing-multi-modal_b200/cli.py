@@ -11,6 +11,7 @@ import os
 from copy import deepcopy
 from functools import partial
 
+import numpy as np
 import torch
 
 from . import data as D
@@ -51,6 +52,17 @@ def build_parser():
     p.add_argument("--tl_method", type=str, default="linear_probing",
                    choices=["linear_probing", "adapter", "adapter_reg", "adapter_reg_seq", "adapter_reg_seq_alter",
                             "contrastive_adapter"], help="transfer learning method")
+    # contrastive_adapter (demo/visualizer_supcon.py; the reference's final_main accepts the method name only)
+    p.add_argument("--ca_head", type=str, default=None, help="projection head of forward_ca (only None = identity is built)")
+    p.add_argument("--contrastive_weight", type=float, default=0.1, help="weight of the contrastive loss (visualizer_supcon.py:255)")
+    p.add_argument("--cl_temperature", type=float, default=0.1, help="contrastive temperature (visualizer_supcon.py:250)")
+    p.add_argument("--num_anchor", type=int, default=1)
+    p.add_argument("--num_positive", type=int, default=64)
+    p.add_argument("--num_negative", type=int, default=64)
+    p.add_argument("--batch_factor", type=int, default=8, help="anchor groups per contrastive loader batch")
+    p.add_argument("--ca_update", type=int, default=1 << 30, help="contrastive loader batches used per epoch")
+    p.add_argument("--balance_by_zs_pred", action="store_true")
+    p.add_argument("--no_ca_pre_norm", action="store_true", help="skip the input normalisation of forward_ca")
     p.add_argument("--balance_val", action="store_true", help="Balancing Val-reg loader.")
     p.add_argument("--resample_ce", action="store_true", help="accepted; only tags the result file name (reference no-op)")
     p.add_argument("--use_cls_prompt_in_reg", action="store_true", help="use class prompts in regularization")
@@ -112,7 +124,9 @@ def set_model(opt):
     if opt.tl_method == "linear_probing":
         print("Off-the-shelf classifier : [Linear Classifier]")
         classifier = LinearClassifier(input_dim=input_dim, num_classes=opt.n_cls)
-    elif opt.tl_method == "adapter" or opt.tl_method in REG_METHODS:
+    elif opt.tl_method in ("adapter", "contrastive_adapter") or opt.tl_method in REG_METHODS:
+        if opt.tl_method == "contrastive_adapter" and opt.ca_head not in (None, "none"):
+            raise NotImplementedError("--ca_head linear / mlp is not built: forward_ca uses the adapter output itself (head = identity)")
         tail = " with group regularized training" if opt.tl_method in REG_METHODS else ""
         print("Off-the-shelf classifier : [Adapter + (temperatured) image-text jointly normalized prediction]" + tail)
         adapter = Adapter(input_dim=input_dim, hidden_dim=opt.adapter_feat_dim)
@@ -204,6 +218,19 @@ def train_all_epochs_gen(opt, loaders=None):
     multiple_adapter, optimizer_reg = None, None
     train_group_accs, val_group_accs, test_group_accs = [], [], []
     FL = opt.epochs_feature_learning
+    ca_batches = None
+    if opt.tl_method == "contrastive_adapter":
+        # anchor / positive / negative groups from the zero-shot predictions stored with the embeddings, built once with the
+        # global numpy RNG (visualizer_supcon.py:1100-1484; contrastive.py)
+        from . import contrastive as CA
+        base, rows = train_loader.base_rows(np.arange(len(trainset)))
+        groups, ca_batches, adj = CA.contrastive_batches(
+            base.y_array[rows], base.confounder_array[rows], base.y_pred_array[rows], n_cls=opt.n_cls, num_anchor=opt.num_anchor,
+            num_positive=opt.num_positive, num_negative=opt.num_negative, batch_factor=opt.batch_factor,
+            balance_by_zs_pred=opt.balance_by_zs_pred)
+        ca_batches = [rows[b] for b in ca_batches]                 # positions in the train split -> rows of the resident matrix
+        print(f"Contrastive groups: {groups.shape[0]} x (anchors {adj[0]} + positives {adj[1]} + negatives {adj[2]}), "
+              f"{len(ca_batches)} loader batches of {opt.batch_factor} groups")
 
     for epoch in range(1, opt.epochs + 1):
         adjust_learning_rate(opt, optimizer, epoch)
@@ -243,6 +270,10 @@ def train_all_epochs_gen(opt, loaders=None):
                 _, _, group_acc = yield from E.train_reg_seq_one_epoch_gen(opt, reg_loader, model, criterion, optimizer_reg, epoch,
                                                                            get_yp_func, target=opt.train_target, print_label=label,
                                                                            use_group=use_group)
+        elif opt.tl_method == "contrastive_adapter":
+            E.train_one_epoch_cl(opt, train_loader, ca_batches, classifier, optimizer, epoch, print_label="Train (Contrastive)")
+            _, _, group_acc = E.validate(opt, train_loader, classifier, criterion, get_yp_func, train_group_ratio,
+                                         target=opt.train_target, print_label="Train (eval pass)")
         else:
             _, _, group_acc = yield from E.train_one_epoch_gen(opt, train_loader, classifier, criterion, optimizer, epoch, get_yp_func,
                                                                target=opt.train_target, print_label=f"Train({opt.train_target})")

@@ -243,6 +243,29 @@ def train_reg_one_epoch(*a, **k):
     return drive(train_reg_one_epoch_gen(*a, **k))
 
 
+def train_one_epoch_cl(opt, train_loader, batches, classifier, optimizer, epoch, print_label='Train'):
+    """Contrastive epoch (demo/visualizer_supcon.py:412-508): one optimizer step per contrastive loader batch (batch_factor
+    anchor groups), the same per-batch warm-up hook; the batch is scored by ONE all-anchor B x B contraction with the rows'
+    class labels (dbmm_contrastive_step) instead of the reference's Python loop over single anchors.  Returns the mean loss."""
+    classifier.train()
+    base, _ = train_loader.base_rows(np.arange(1))
+    ad = classifier.adapter.tensors()
+    loss = torch.zeros(1, dtype=torch.float64, device=base.device)
+    n_used = 0
+    t0 = time.time()
+    for idx, rows in enumerate(batches):
+        if idx >= opt.ca_update:
+            continue
+        warmup_learning_rate(opt, epoch, idx, len(batches), optimizer)
+        ops.contrastive_step(base.x, base.labels["class"], ad, optimizer.buffers, optimizer.lr, idx=_order_to_device(base, rows),
+                             pre_norm=not opt.no_ca_pre_norm, tau_cl=opt.cl_temperature, loss_weight=opt.contrastive_weight,
+                             momentum=optimizer.momentum, weight_decay=optimizer.weight_decay, loss_out=loss)
+        n_used += 1
+    avg = float(loss.item()) / max(n_used, 1)
+    print(f"Loss in {print_label}: {avg:.3f} ({n_used} batches, {time.time() - t0:.2f} s)")
+    return avg
+
+
 def _run_eval(loader, classifier, target, spurious_prompts=False):
     classifier.eval()
     base, rows = loader.base_rows(loader.draw_order())

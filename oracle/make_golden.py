@@ -476,3 +476,54 @@ if __name__ == "__main__":
     main()
 
 
+
+
+def contrastive_construction_golden(out_path=None):
+    """Golden for debiasing-multi-modal_b200/contrastive.py: the reference's own sampling functions
+    (demo/visualizer_supcon.py:1051-1080, 1100-1146 semantics, 1148-1340, 1342-1435, 1437-1467) executed IN PLACE from an excerpt
+    of the source file (the module itself cannot be imported here: it drags in matplotlib / umap), on seeded synthetic labels."""
+    import types
+    src = open(os.path.join("/root/reference", "demo", "visualizer_supcon.py")).read().split("\n")
+
+    def excerpt(lo, hi):
+        return "\n".join(src[lo - 1:hi])
+    class _NP:                                   # numpy >= 1.24 refuses the ragged np.array(list of per-slice arrays) at :1162
+        def __getattr__(self, k):                # (the reference's pinned numpy made an object array of it)
+            return getattr(np, k)
+
+        @staticmethod
+        def array(x, *a, **k):
+            try:
+                return np.array(x, *a, **k)
+            except ValueError:
+                o = np.empty(len(x), dtype=object)
+                for i, v in enumerate(x):
+                    o[i] = v
+                return o
+    ns = {"np": _NP(), "tqdm": (lambda it, **k: it), "print": (lambda *a, **k: None)}
+    exec(excerpt(1051, 1081), ns)            # adjust_num_pos_neg_
+    exec(excerpt(1148, 1341), ns)            # prepare_contrastive_points
+    exec(excerpt(1342, 1435), ns)            # construct_contrastive_data
+    rng = np.random.default_rng(77)
+    n = 1500
+    g = rng.choice(4, n, p=[0.55, 0.1, 0.05, 0.3])
+    y, sp = g // 2, g % 2
+    y_pred = np.where(rng.random(n) < 0.8, y, 1 - y)          # zero-shot prediction: 80 % correct
+    # compute_slice_indices (1100-1146) reads a pandas frame of the dataset; its arithmetic on (pseudo_labels, labels):
+    correct = y_pred == y
+    sl_ix = [np.where(y_pred == lab)[0] for lab in np.unique(y_pred)]
+    sl_ok = [correct[ix] for ix in sl_ix]
+    ds = types.SimpleNamespace(y_array=y, confounder_array=sp)
+    anchors, negatives, positives, _ = ns["prepare_contrastive_points"](ds, sl_ix, sl_ok)
+    args = types.SimpleNamespace(num_anchor=2, num_positive=12, num_negative=10, n_cls=2)
+    ns["adjust_num_pos_neg_"](positives, negatives, args)
+    np.random.seed(123)
+    samples = ns["construct_contrastive_data"](anchors, negatives, positives, args)
+    groups = np.concatenate(samples)
+    np.random.shuffle(groups)                                  # load_contrastive_loader, no balancing, re_shuffle_ca_loader
+    out = dict(y=y, spurious=sp, y_pred=y_pred, groups=groups, adjusted=np.array([args.num_anchor, args.num_positive, args.num_negative]),
+               neg_counts=np.array([len(d["ix"]) for d in negatives]), pos_counts=np.array([len(positives[c]["ix"]) for c in range(2)]),
+               anchor_counts=np.array([len(a["ix"]) for a in anchors]))
+    out_path = out_path or os.path.join(GOLD, "contrastive_construction.npz")
+    np.savez_compressed(out_path, **out)
+    return out

@@ -85,3 +85,26 @@ def test_contrastive_step_matches_torch_autograd(ops, B, D, pre_norm):
     assert rel(got["running_mean"], 0.9 * p["running_mean"] + 0.1 * mu_ref) < 1e-4
     assert rel(got["running_var"], 0.9 * p["running_var"] + 0.1 * var_ref) < 1e-4
     assert int(got["num_batches_tracked"]) == int(p["num_batches_tracked"]) + 1
+
+
+def test_contrastive_adapter_cli_runs(tmp_path):
+    """`--tl_method contrastive_adapter` end to end through the drop-in CLI: groups from the stored zero-shot predictions,
+    contrastive epochs, the usual val / test evaluation and model selection; the loss falls."""
+    import contextlib
+    import io
+    import dbmm
+    from dbmm import cli, synth
+    ds = synth.make_dataset(name="waterbirds", dim=1024, seed=1234, scale=0.3, k=0.085, k_text=0.5, text_noise=0.02)
+    paths = synth.write_reference_files(ds, str(tmp_path))
+    argv = ["--dataset", "waterbirds", "--tl_method", "contrastive_adapter", "--batch_size", "256", "--learning_rate", "0.05",
+            "--epochs", "3", "--lr_decay_rate", "0.1", "--lr_decay_epochs", "3", "--train_target", "class", "--random_seed", "7",
+            "--num_positive", "32", "--num_negative", "32", "--batch_factor", "4"]
+    for k, v in paths.items():
+        argv += [f"--{k}", v]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        (tr, va, te), _ = cli.train_all_epochs(cli.parse_option(argv))
+    out = buf.getvalue()
+    losses = [float(l.split(":")[1].split("(")[0]) for l in out.splitlines() if l.startswith("Loss in Train (Contrastive)")]
+    assert len(losses) == 3 and losses[-1] < losses[0], losses
+    assert 0.0 <= float(te["worst_acc"]) <= 1.0 and "Contrastive groups:" in out
