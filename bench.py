@@ -208,6 +208,36 @@ def multi_gpu_legs(torch, dist, ops, parallel, dev, P, e0, e1, world, rank, barr
                                                  "algorithmic_tflops_per_gpu": fl / ts / 1e12 / world, "loss": loss,
                                                  "dZ_finite": bool(torch.isfinite(dZ).all().item()),
                                                  "collectives": "all-gather Z + labels, all-reduce (loss, n_valid), reduce-scatter dZ (NCCL)"}
+    # the same regulariser TRAINING an adapter under data parallelism (parallel.contrastive_step_distributed): forward_ca of the
+    # rank's rows, global negatives, D-wide backward, gradient all-reduce, SGD; the replicas must stay identical
+    from dbmm.modules import Adapter
+    torch.manual_seed(11)
+    ad_c = Adapter(d, 128).to(dev).tensors()
+    buf_c = ops.TrainBuffers(d, 128, device=dev)
+    Xc = torch.randn(16 * Bl, d, device=dev, generator=gen).half().float()
+    yc = torch.randint(0, 2, (16 * Bl,), device=dev, dtype=torch.int32, generator=gen)
+    Xc += 0.5 * (yc.float()[:, None] * 2 - 1) * torch.randn(1, d, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    Xc = Xc.half().float()
+    losses = []
+    for s in range(2):
+        parallel.contrastive_step_distributed(Xc, yc, ad_c, buf_c, 0.05, torch.arange(s * Bl, (s + 1) * Bl, device=dev, dtype=torch.int32))
+    barrier()
+    e0.record()
+    for s in range(2, 12):
+        losses.append(parallel.contrastive_step_distributed(Xc, yc, ad_c, buf_c, 0.05,
+                                                            torch.arange(s * Bl, (s + 1) * Bl, device=dev, dtype=torch.int32)))
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    chk = torch.stack([ad_c.W1.double().sum(), ad_c.W2.double().abs().sum()])
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    res["contrastive_adapter_train_step_dp"] = {"global_batch": B, "rows_per_gpu": Bl, "ms_per_step": float(t.item()),
+                                                "emb_per_s": B / (float(t.item()) * 1e-3), "loss_first": losses[0], "loss_last": losses[-1],
+                                                "replicas_identical": bool(all(torch.equal(c, allc[0]) for c in allc)),
+                                                "what": "forward_ca + all-gathered negatives + D-wide backward + gradient all-reduce + SGD per step "
+                                                        "(host-driven: includes the loss read-back of every step)"}
     return res
 
 
@@ -339,6 +369,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = parallel.bind_to_gpu_numa_node(local_rank) if world > 1 else None      # host staging next to the GPU (e2e leg)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -418,7 +449,7 @@ def main():
         out = {"metric": "adapter-train embeddings/sec", "value": value, "unit": "embeddings/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": workload_config(world), "clocks": clocks,
+               "config": workload_config(world), "clocks": clocks, "numa_binding": numa,
                "us_per_sgd_step": 1e3 * ms_per_step / steps_per_epoch, "final_epoch_mean_loss": final_loss,
                "gpu_launches": args.steps * (steps_per_epoch * (8 if world == 1 else 6) + 3)}
 

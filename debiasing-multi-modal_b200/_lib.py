@@ -87,8 +87,12 @@ SIGNATURES = {
     "dbmm_eval_fwd_f16": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32, _vp, _f32,
                                     _i64, BatchStats, _vp, _vp, _vp, _sz, _vp]),
     "dbmm_contrastive_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "dbmm_contrastive_forward": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _AP, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "dbmm_contrastive_backward": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _AP, _i32, _vp, _vp, _f32, _vp, _vp, _sz, _vp]),
+    "dbmm_contrastive_apply": (C.c_int, [_i32, _i32, _i32, _AP, _vp, _vp, _f32, _f32, _f32, _i32, _vp, _sz, _vp]),
     "dbmm_contrastive_step": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _AP, _i32, _f32, _f32, _vp, _vp, _f32, _f32, _f32, _i32,
                                         _vp, _vp, _vp, _sz, _vp]),
+    "dbmm_device_pci_bus_id": (C.c_int, [_i32, C.c_char_p, _i32]),
     "dbmm_train_step": (C.c_int, [_i32, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32,
                                   _vp, _f32, _vp, _vp, _f32, _f32, _f32, _i32, BatchStats, _i64, _vp, _sz, _vp]),
     "dbmm_train_step_ex": (C.c_int, [_i32, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _AP, _AP, _f32,

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_ca_normalize(float* __restrict__ Z, con
 }
 
 // dz = w * (du - u (u.du)) * inv_n with du = dU_a + dU_b (anchor-role + contrast-role gradients of the supcon kernels);
-// written over dU_a, also split hi + lo
+// (dU_b may be NULL: dU_a is the whole gradient); written over dU_a, also split hi + lo
 __global__ void __launch_bounds__(256) k_ca_dz(const float* __restrict__ U, float* __restrict__ dUa, const float* __restrict__ dUb,
                                                const float* __restrict__ inv_n, float weight, int B, int D, float* __restrict__ dz_hi,
                                                float* __restrict__ dz_lo) {
@@ -98,11 +98,11 @@ __global__ void __launch_bounds__(256) k_ca_dz(const float* __restrict__ U, floa
     float* da = dUa + (size_t)b * D;
     const float* db = dUb + (size_t)b * D;
     float dot = 0.f;
-    for (int k = lane; k < D; k += 32) dot = fmaf(u[k], da[k] + db[k], dot);
+    for (int k = lane; k < D; k += 32) dot = fmaf(u[k], da[k] + (dUb ? db[k] : 0.f), dot);
     dot = warp_sum(dot);
     const float sc = weight * inv_n[b];
     for (int k = lane; k < D; k += 32) {
-        const float v = sc * ((da[k] + db[k]) - u[k] * dot);
+        const float v = sc * ((da[k] + (dUb ? db[k] : 0.f)) - u[k] * dot);
         const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
         da[k] = v; dz_hi[(size_t)b * D + k] = hi; dz_lo[(size_t)b * D + k] = v - hi;
     }

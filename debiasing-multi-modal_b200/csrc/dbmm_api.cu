@@ -1582,25 +1582,26 @@ size_t dbmm_contrastive_workspace_bytes(int B, int D, int H) {
     return carve_contrastive_ws(nullptr, B, D, H).total;
 }
 
-int dbmm_contrastive_step(const float* X, int64_t ldx, const int32_t* idx, const int32_t* labels, int B, int D, int H,
-                          const dbmm_adapter* ad, int pre_norm, float inv_tau_cl, float loss_weight,
-                          float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
-                          double* loss_out, int32_t* n_valid_out, void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int contrastive_check(const float* X, int64_t ldx, int B, int D, int H, const dbmm_adapter* ad, void* ws, size_t ws_bytes, ContrastiveWs* w) {
     if (int rc = check_dims(D, H, 1, 1)) return rc;
     if (int rc = check_adapter(ad, "trainable")) return rc;
-    DBMM_CHECK_ARG(X && labels && grads && momentum_buf && ws && ldx >= D, "NULL X / labels / grads / momentum / workspace");
+    DBMM_CHECK_ARG(X && ws && ldx >= D, "NULL X / workspace");
     DBMM_CHECK_ARG(B > 1, "BatchNorm needs more than 1 row per batch in training (got %d)", B);
     DBMM_CHECK_SHAPE(use_tc_gemm1(D, H) && use_tc_wgrad(D, H) && H % 4 == 0, "contrastive step needs the tensor-core GEMM shapes (D %% 128 == 0, H %% 32 == 0; D=%d H=%d)", D, H);
-    ContrastiveWs w = carve_contrastive_ws(ws, B, D, H);
-    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    *w = carve_contrastive_ws(ws, B, D, H);
+    DBMM_CHECK_ARG(w->total <= ws_bytes, "workspace too small: need %zu, have %zu", w->total, ws_bytes);
+    return DBMM_OK;
+}
+
+// forward_ca of this rank's rows: u = L2(adapter_train(L2(x))) -> U_out [B][D]; the rows' labels -> labels_out [B].  The
+// workspace keeps what the backward needs (a', BatchNorm sums, h, the two norms).
+int dbmm_contrastive_forward(const float* X, int64_t ldx, const int32_t* idx, const int32_t* labels, int B, int D, int H,
+                             const dbmm_adapter* ad, int pre_norm, float* U_out, int32_t* labels_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ContrastiveWs w;
+    if (int rc = contrastive_check(X, ldx, B, D, H, ad, ws, ws_bytes, &w)) return rc;
+    DBMM_CHECK_ARG(labels && U_out, "NULL labels / U_out");
     TrainWs tw = carve_train_ws(w.train, B, D, H, 1, 1);
-    const size_t np = dbmm_param_count(D, H);
-    const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
-    if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * np, st));
-    DBMM_CUDA(cudaMemsetAsync(w.loss_sum, 0, sizeof(double), st));
-    DBMM_CUDA(cudaMemsetAsync(w.n_valid, 0, sizeof(int32_t), st));
-    // ---- forward: x' = x / |x|, a = x' W1^T + b1 (batch statistics), h, z = h W2^T + b2, u = z / |z|
     k_ca_rows_in<<<ceil_div(B, 8), 256, 0, st>>>(X, ldx, idx, B, D, labels, pre_norm, w.inv_xn, w.labels_b);
     if (int rc = launch_gemm1(X, ldx, idx, 0, B, D, H, nullptr, ad, tw.A, nullptr, tw.whi, tw.wlo, true, 1, nullptr, st)) return rc;
     k_ca_bn_stats<<<ceil_div(H, 32), 256, 0, st>>>(tw.A, ad->b1, w.inv_xn, B, H, tw.colsum);
@@ -1613,19 +1614,30 @@ int dbmm_contrastive_step(const float* X, int64_t ldx, const int32_t* idx, const
     if (int rc = launch_tc_gemm_nt<true, EPI_STORE>(w.h_hi, w.h_lo, H, w.w2_hi, w.w2_lo, H, g, st)) return rc;
     k_ca_normalize<<<ceil_div(B, 8), 256, 0, st>>>(w.U, ad->b2, B, D, w.inv_n);
     DBMM_LAUNCH_CHECK();
-    // ---- loss and its gradient w.r.t. u: the B x B similarity GEMMs
-    if (int rc = dbmm_supcon_fwd(w.U, B, D, 0, B, w.labels_b, inv_tau_cl, w.loss_sum, w.n_valid, nullptr, w.supcon, w.supcon_bytes, stream)) return rc;
-    if (int rc = dbmm_supcon_bwd(w.U, B, D, 0, B, inv_tau_cl, w.n_valid, w.dUa, w.dUb, 0, w.supcon, w.supcon_bytes, stream)) return rc;
-    k_ca_loss_out<<<1, 1, 0, st>>>(w.loss_sum, w.n_valid, loss_weight, loss_out, n_valid_out);
-    // ---- backward: dz, db2, dh = dz W2, dW2 = dz^T h, ReLU / BatchNorm backward, dW1 = da^T x'
-    k_ca_dz<<<ceil_div(B, 8), 256, 0, st>>>(w.U, w.dUa, w.dUb, w.inv_n, loss_weight, B, D, w.dz_hi, w.dz_lo);
-    k_colsum_rows<<<ceil_div(D, 32), 256, 0, st>>>(w.dUa, B, D, D, grads + ob2);
+    if (U_out != w.U) DBMM_CUDA(cudaMemcpyAsync(U_out, w.U, sizeof(float) * (size_t)B * D, cudaMemcpyDeviceToDevice, st));
+    if (labels_out) DBMM_CUDA(cudaMemcpyAsync(labels_out, w.labels_b, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    return DBMM_OK;
+}
+
+// D-wide backward from dL/du (dU [B][D], overwritten; dU2 optional second addend) into the flat gradient; the workspace must
+// still hold the state of dbmm_contrastive_forward on the same rows.
+int dbmm_contrastive_backward(const float* X, int64_t ldx, const int32_t* idx, int B, int D, int H, const dbmm_adapter* ad, int pre_norm,
+                              float* dU, const float* dU2, float loss_weight, float* grads, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ContrastiveWs w;
+    if (int rc = contrastive_check(X, ldx, B, D, H, ad, ws, ws_bytes, &w)) return rc;
+    DBMM_CHECK_ARG(dU && grads, "NULL dU / grads");
+    TrainWs tw = carve_train_ws(w.train, B, D, H, 1, 1);
+    const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
+    k_ca_dz<<<ceil_div(B, 8), 256, 0, st>>>(w.U, dU, dU2, w.inv_n, loss_weight, B, D, w.dz_hi, w.dz_lo);
+    k_colsum_rows<<<ceil_div(D, 32), 256, 0, st>>>(dU, B, D, D, grads + ob2);
     k_transpose_split<<<dim3(ceil_div(H, 32), ceil_div(D, 32)), 256, 0, st>>>(ad->W2, H, w.w2t_hi, w.w2t_lo, D, H, D);       // [H][D]
     DBMM_LAUNCH_CHECK();
+    TcGemmArgs g;
     memset(&g, 0, sizeof(g));
     g.M = B; g.N = H; g.K = D; g.scale = 1.f; g.C = w.dh; g.ldc = H;
     if (int rc = launch_tc_gemm_nt<true, EPI_STORE>(w.dz_hi, w.dz_lo, D, w.w2t_hi, w.w2t_lo, D, g, st)) return rc;
-    k_transpose_split<<<dim3(ceil_div(D, 32), ceil_div(B, 32)), 256, 0, st>>>(w.dUa, D, w.dzt_hi, w.dzt_lo, B, D, w.Bp);      // dz^T [D][Bp]
+    k_transpose_split<<<dim3(ceil_div(D, 32), ceil_div(B, 32)), 256, 0, st>>>(dU, D, w.dzt_hi, w.dzt_lo, B, D, w.Bp);        // dz^T [D][Bp]
     k_transpose_split<<<dim3(ceil_div(H, 32), ceil_div(B, 32)), 256, 0, st>>>(w.h, H, w.ht_hi, w.ht_lo, B, H, w.Bp);          // h^T  [H][Bp]
     DBMM_LAUNCH_CHECK();
     memset(&g, 0, sizeof(g));
@@ -1641,19 +1653,60 @@ int dbmm_contrastive_step(const float* X, int64_t ldx, const int32_t* idx, const
     if (int rc = launch_wgrad_tc(t, nchunk, st)) return rc;
     k_sum_chunks<<<148, 256, 0, st>>>(tw.part, nchunk, (int64_t)H * D / 4, grads + oW1);
     DBMM_LAUNCH_CHECK();
-    // ---- optimizer (torch.optim.SGD semantics) and the BatchNorm running statistics of the train-mode forward
-    {
-        float* tensors[6] = {ad->W1, ad->b1, ad->gamma, ad->beta, ad->W2, ad->b2};
-        const size_t offs[7] = {oW1, ob1, og, obeta, oW2, ob2, np};
-        for (int k = 0; k < 6; ++k)
-            if (int rc = dbmm_sgd_step(tensors[k], grads + offs[k], momentum_buf + offs[k], (int64_t)(offs[k + 1] - offs[k]), lr, momentum,
-                                       weight_decay, 0, stream)) return rc;
-    }
+    return DBMM_OK;
+}
+
+// SGD on the six adapter tensors from the flat gradient (torch.optim.SGD semantics) + the BatchNorm running statistics of the
+// forward whose state is in the workspace.
+int dbmm_contrastive_apply(int B, int D, int H, const dbmm_adapter* ad, const float* grads, float* momentum_buf, float lr, float momentum,
+                           float weight_decay, int first_step, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ContrastiveWs w;
+    DBMM_CHECK_ARG(grads && momentum_buf && ws && B > 1, "NULL grads / momentum / workspace");
+    if (int rc = check_adapter(ad, "trainable")) return rc;
+    w = carve_contrastive_ws(ws, B, D, H);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small");
+    TrainWs tw = carve_train_ws(w.train, B, D, H, 1, 1);
+    const size_t np = dbmm_param_count(D, H);
+    const size_t oW1 = 0, ob1 = (size_t)H * D, og = ob1 + H, obeta = og + H, oW2 = obeta + H, ob2 = oW2 + (size_t)D * H;
+    if (first_step) DBMM_CUDA(cudaMemsetAsync(momentum_buf, 0, sizeof(float) * np, st));
+    float* tensors[6] = {ad->W1, ad->b1, ad->gamma, ad->beta, ad->W2, ad->b2};
+    const size_t offs[7] = {oW1, ob1, og, obeta, oW2, ob2, np};
+    for (int k = 0; k < 6; ++k)
+        if (int rc = dbmm_sgd_step(tensors[k], grads + offs[k], momentum_buf + offs[k], (int64_t)(offs[k + 1] - offs[k]), lr, momentum,
+                                   weight_decay, 0, stream)) return rc;
     BnRunningArgs b;
     b.colsum = tw.colsum; b.nad = 1; b.H = H; b.Bg = B;
     b.rm[0] = b.rm[1] = ad->running_mean; b.rv[0] = b.rv[1] = ad->running_var; b.nbt[0] = b.nbt[1] = (long long*)ad->num_batches_tracked;
     k_bn_running<<<1, 256, 0, st>>>(b);
     DBMM_LAUNCH_CHECK();
+    return DBMM_OK;
+}
+
+int dbmm_contrastive_step(const float* X, int64_t ldx, const int32_t* idx, const int32_t* labels, int B, int D, int H,
+                          const dbmm_adapter* ad, int pre_norm, float inv_tau_cl, float loss_weight,
+                          float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
+                          double* loss_out, int32_t* n_valid_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ContrastiveWs w;
+    if (int rc = contrastive_check(X, ldx, B, D, H, ad, ws, ws_bytes, &w)) return rc;
+    DBMM_CHECK_ARG(labels && grads && momentum_buf, "NULL labels / grads / momentum");
+    DBMM_CUDA(cudaMemsetAsync(w.loss_sum, 0, sizeof(double), st));
+    DBMM_CUDA(cudaMemsetAsync(w.n_valid, 0, sizeof(int32_t), st));
+    if (int rc = dbmm_contrastive_forward(X, ldx, idx, labels, B, D, H, ad, pre_norm, w.U, nullptr, ws, ws_bytes, stream)) return rc;
+    // loss and its gradient w.r.t. u: the B x B similarity GEMMs
+    if (int rc = dbmm_supcon_fwd(w.U, B, D, 0, B, w.labels_b, inv_tau_cl, w.loss_sum, w.n_valid, nullptr, w.supcon, w.supcon_bytes, stream)) return rc;
+    if (int rc = dbmm_supcon_bwd(w.U, B, D, 0, B, inv_tau_cl, w.n_valid, w.dUa, w.dUb, 0, w.supcon, w.supcon_bytes, stream)) return rc;
+    k_ca_loss_out<<<1, 1, 0, st>>>(w.loss_sum, w.n_valid, loss_weight, loss_out, n_valid_out);
+    DBMM_LAUNCH_CHECK();
+    if (int rc = dbmm_contrastive_backward(X, ldx, idx, B, D, H, ad, pre_norm, w.dUa, w.dUb, loss_weight, grads, ws, ws_bytes, stream)) return rc;
+    return dbmm_contrastive_apply(B, D, H, ad, grads, momentum_buf, lr, momentum, weight_decay, first_step, ws, ws_bytes, stream);
+}
+
+// PCI bus id of a device ("0000:1b:00.0"): lets the host side find the GPU's NUMA node in sysfs (parallel.bind_to_gpu_numa_node)
+int dbmm_device_pci_bus_id(int device, char* out, int len) {
+    DBMM_CHECK_ARG(out && len >= 16, "output buffer of at least 16 bytes required");
+    DBMM_CUDA(cudaDeviceGetPCIBusId(out, len, device));
     return DBMM_OK;
 }
 

@@ -514,6 +514,37 @@ def contrastive_step(X, labels, ad: AdapterTensors, buf: "TrainBuffers", lr: flo
     buf.first_step = False
 
 
+def contrastive_forward(X, labels, ad: AdapterTensors, *, idx=None, pre_norm=True):
+    """forward_ca of the rows (train-mode BatchNorm on THESE rows): returns (U [B, D] L2-normalised, labels of the rows [B],
+    workspace handle to pass to contrastive_backward / contrastive_apply)."""
+    lib = _lib.load()
+    _check(X, torch.float32, "X", contiguous=False)
+    _check(labels, torch.int32, "labels")
+    B = int(idx.numel() if idx is not None else X.shape[0])
+    D, H = X.shape[1], ad.H
+    ws = torch.empty(int(lib.dbmm_contrastive_workspace_bytes(B, D, H)), dtype=torch.uint8, device=X.device)
+    U = torch.empty((B, D), dtype=torch.float32, device=X.device)
+    lab = torch.empty((B,), dtype=torch.int32, device=X.device)
+    _lib.check(lib.dbmm_contrastive_forward(X.data_ptr(), X.stride(0), _ptr(idx), labels.data_ptr(), B, D, H, C.byref(ad.ptrs()),
+                                            1 if pre_norm else 0, U.data_ptr(), lab.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return U, lab, ws
+
+
+def contrastive_backward(X, ad: AdapterTensors, dU, grads, ws, *, idx=None, pre_norm=True, loss_weight=0.1):
+    """Flat parameter gradient from dL/du (dU is overwritten); `ws` from contrastive_forward on the same rows."""
+    lib = _lib.load()
+    B, D, H = dU.shape[0], X.shape[1], ad.H
+    _lib.check(lib.dbmm_contrastive_backward(X.data_ptr(), X.stride(0), _ptr(idx), B, D, H, C.byref(ad.ptrs()), 1 if pre_norm else 0,
+                                             dU.data_ptr(), None, loss_weight, grads.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr()))
+
+
+def contrastive_apply(ad: AdapterTensors, buf: "TrainBuffers", lr, B, ws, *, momentum=0.9, weight_decay=5e-5):
+    lib = _lib.load()
+    _lib.check(lib.dbmm_contrastive_apply(B, ad.D, ad.H, C.byref(ad.ptrs()), buf.grads.data_ptr(), buf.momentum.data_ptr(), lr, momentum,
+                                          weight_decay, 1 if buf.first_step else 0, ws.data_ptr(), ws.numel(), _stream_ptr()))
+    buf.first_step = False
+
+
 class SupconState:
     """Device scalars of one contrastive step: sum of per-anchor losses and number of valid anchors."""
 

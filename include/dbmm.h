@@ -153,10 +153,24 @@ int dbmm_eval_fwd_f16(const void* X16, int64_t ldx, const int32_t* y, const int3
  * grads: [dbmm_param_count] flat gradient (written), momentum_buf: flat momentum (zeroed when first_step).
  */
 size_t dbmm_contrastive_workspace_bytes(int B, int D, int H);
+/* The same step in three calls, for data parallelism with GLOBAL negatives (BASELINE config 3): forward of the rank's rows
+ * (U_out [B, D] normalised embeddings), then -- on the caller's side -- all-gather, dbmm_supcon_fwd / _bwd with row0 / Bl,
+ * reduce-scatter of the contrast-role gradient; backward from dL/du into the flat gradient (all-reduced by the caller);
+ * SGD + BatchNorm running statistics.  The workspace carries the forward's state between the calls. */
+int dbmm_contrastive_forward(const float* X, int64_t ldx, const int32_t* idx, const int32_t* labels, int B, int D, int H,
+                             const dbmm_adapter* ad, int pre_norm, float* U_out, int32_t* labels_out, void* ws, size_t ws_bytes, void* stream);
+int dbmm_contrastive_backward(const float* X, int64_t ldx, const int32_t* idx, int B, int D, int H, const dbmm_adapter* ad, int pre_norm,
+                              float* dU, const float* dU2, float loss_weight, float* grads, void* ws, size_t ws_bytes, void* stream);
+int dbmm_contrastive_apply(int B, int D, int H, const dbmm_adapter* ad, const float* grads, float* momentum_buf, float lr, float momentum,
+                           float weight_decay, int first_step, void* ws, size_t ws_bytes, void* stream);
 int dbmm_contrastive_step(const float* X, int64_t ldx, const int32_t* idx, const int32_t* labels, int B, int D, int H,
                           const dbmm_adapter* ad, int pre_norm, float inv_tau_cl, float loss_weight,
                           float* grads, float* momentum_buf, float lr, float momentum, float weight_decay, int first_step,
                           double* loss_out, int32_t* n_valid_out, void* ws, size_t ws_bytes, void* stream);
+
+/* PCI bus id ("0000:1b:00.0") of a CUDA device: the host side binds each rank's staging threads / pinned buffers to the
+ * GPU's NUMA node (no reference counterpart: the reference is single-GPU). */
+int dbmm_device_pci_bus_id(int device, char* out, int len);
 
 /*
  * One training step on B_local rows (train_one_epoch / train_reg_seq_one_epoch body).
