@@ -17,6 +17,7 @@
 #include "export_rows.cuh"
 #include "head_supcon.cuh"
 #include "eval_f16.cuh"
+#include "head_f16.cuh"
 #include "contrastive.cuh"
 #include "nccl_dyn.cuh"
 #include "linear_probe.cuh"
@@ -1395,6 +1396,73 @@ int dbmm_logits_ce(const float* U, int64_t ldu, const int32_t* idx, const int32_
         if (int rc = launch_tc_gemm_nt<false, EPI_SOFTMAX_PART>(A, nullptr, lda, w.thi, w.tlo, D, g, st)) return rc;
         k_head_finish<<<ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8, 256, 0, st>>>(
             w.part, w.ntile, n, pos0, idx, grp, G, batch_size, stats.loss_sum, stats.counts, pred_out, y);
+        DBMM_LAUNCH_CHECK();
+    }
+    return DBMM_OK;
+}
+
+// fp16-resident zero-shot head (head_f16.cuh): same results as dbmm_logits_ce, kind::f16 MMAs on the rows as stored
+namespace dbmm {
+struct HeadF16Ws { __half* thi; __half* tlo; float* inv_norm; SoftmaxPart* part; float* bscale; int64_t chunk; int ntile; size_t total; };
+static HeadF16Ws carve_head_f16_ws(void* base, int64_t N, int D, int C) {
+    HeadF16Ws w; char* p = (char*)base; size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    w.ntile = ceil_div(C, HF_BN);
+    int64_t chunk = 1 << 20;                    // rows per launch: partials of 1 M rows x 8 column tiles = 128 MB
+    if (chunk > N) chunk = N;
+    w.chunk = chunk;
+    const size_t o_thi = take(sizeof(__half) * (size_t)C * D), o_tlo = take(sizeof(__half) * (size_t)C * D);
+    const size_t o_in = take(sizeof(float) * (size_t)chunk), o_part = take(sizeof(SoftmaxPart) * (size_t)chunk * w.ntile);
+    const size_t o_sc = take(256);              // [0]: max |That| bits, [1]: 2^k, [2]: 2^-k
+    w.total = off;
+    w.thi = (__half*)(p + o_thi); w.tlo = (__half*)(p + o_tlo); w.inv_norm = (float*)(p + o_in); w.part = (SoftmaxPart*)(p + o_part);
+    w.bscale = (float*)(p + o_sc);
+    return w;
+}
+}  // namespace dbmm
+
+size_t dbmm_head_f16_workspace_bytes(int64_t N, int D, int C) {
+    if (N < 1 || D < 1 || C < 1) return 0;
+    return carve_head_f16_ws(nullptr, N, D, C).total;
+}
+
+int dbmm_logits_ce_f16(const void* U16, int64_t ldu, const int32_t* y, const int32_t* grp,
+                       int64_t N, int D, int C, int G, const float* That, const float* col_bias, float inv_tau, int normalize_rows,
+                       int64_t batch_size, dbmm_batch_stats stats, int32_t* pred_out, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DBMM_CHECK_ARG(U16 && That && ws, "NULL U16 / That / workspace");
+    DBMM_CHECK_SHAPE(D >= 64 && D % 8 == 0 && C >= 1 && G >= 1 && G <= DBMM_MAX_G, "fp16 head needs D >= 64, D %% 8 == 0 (D=%d C=%d G=%d)", D, C, G);
+    DBMM_CHECK_ARG(N >= 0 && ldu >= D && ldu % 8 == 0 && batch_size >= 1, "bad N=%lld ldu=%lld batch_size=%lld", (long long)N,
+                   (long long)ldu, (long long)batch_size);
+    DBMM_CHECK_ARG(y || (!stats.loss_sum && !stats.counts), "labels are required when batch statistics are requested");
+    if (N == 0) return DBMM_OK;
+    HeadF16Ws w = carve_head_f16_ws(ws, N, D, C);
+    DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    const __half* U = (const __half*)U16;
+    // prompts: [D, C] -> K-major [C, D] fp16 pair (once per call)
+    // the 256-row single-accumulator kernel (2^k-scaled prompts) is the default; DBMM_HEAD=pair runs the 128-row scaled-fp16-pair kernel
+    static const bool wide = !(getenv("DBMM_HEAD") && strcmp(getenv("DBMM_HEAD"), "pair") == 0);
+    if (wide) {
+        DBMM_CUDA(cudaMemsetAsync(w.bscale, 0, 16, st));
+        k_absmax_bits<<<148, 256, 0, st>>>(That, (int64_t)D * C, (unsigned*)w.bscale);
+        k_head_bscale<<<1, 1, 0, st>>>((const unsigned*)w.bscale, w.bscale + 1);
+        k_transpose_split_f16_scaled<<<dim3(ceil_div(C, 32), ceil_div(D, 32)), 256, 0, st>>>(That, C, w.thi, w.tlo, D, C, D, w.bscale + 1);
+    } else k_transpose_split_f16<<<dim3(ceil_div(C, 32), ceil_div(D, 32)), 256, 0, st>>>(That, C, w.thi, w.tlo, D, C, D);
+    DBMM_LAUNCH_CHECK();
+    for (int64_t pos0 = 0; pos0 < N; pos0 += w.chunk) {
+        const int64_t n = (N - pos0) < w.chunk ? (N - pos0) : w.chunk;
+        const __half* A = U + pos0 * ldu;
+        if (normalize_rows) {
+            k_row_inv_norm_f16<<<148 * 8, 256, 0, st>>>(A, ldu, n, D, w.inv_norm);
+            DBMM_LAUNCH_CHECK();
+        }
+        HeadF16Args g;
+        memset(&g, 0, sizeof(g));
+        g.M = n; g.N = C; g.K = D; g.scale = inv_tau; g.rowscale = normalize_rows ? w.inv_norm : nullptr; g.col_bias = col_bias;
+        g.y = y; g.pos0 = pos0; g.part = w.part; g.n_ntiles = w.ntile; g.bscale_inv = w.bscale + 2;
+        if (int rc = launch_f16_head(A, ldu, w.thi, w.tlo, D, g, wide, st)) return rc;
+        k_head_finish<<<ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8, 256, 0, st>>>(
+            w.part, w.ntile, n, pos0, nullptr, grp, G, batch_size, stats.loss_sum, stats.counts, pred_out, y);
         DBMM_LAUNCH_CHECK();
     }
     return DBMM_OK;

@@ -494,6 +494,32 @@ def logits_ce(U: torch.Tensor, y, grp, That: torch.Tensor, inv_tau: float, stats
     return pred
 
 
+def logits_ce_f16(U16: torch.Tensor, y, grp, That: torch.Tensor, inv_tau: float, stats: BatchStatsBuffers | None, batch_size: int, *,
+                  G: int = 4, normalize_rows=True, want_pred=False, col_bias=None):
+    """logits_ce over the fp16-resident copy of the embeddings (dbmm_logits_ce_f16: kind::f16 tensor-core head, rows read as
+    stored).  Same loss / argmax / counters as logits_ce on the widened rows."""
+    lib = _lib.load()
+    _check(U16, torch.float16, "U16", contiguous=False)
+    if U16.stride(1) != 1:
+        raise DbmmError("U16 rows must be contiguous")
+    _check(That, torch.float32, "That")
+    N, D, Cn = U16.shape[0], U16.shape[1], That.shape[1]
+    if That.shape[0] != D:
+        raise DbmmError("dimension mismatch between U16 and the text prompts")
+    G = _label_args(y, grp, G)
+    ws = workspace(lib.dbmm_head_f16_workspace_bytes(max(N, 1), D, Cn), U16.device)
+    pred = torch.empty((N,), dtype=torch.int32, device=U16.device) if want_pred else None
+    st = stats.c() if stats is not None else BatchStats(None, None)
+    _lib.check(lib.dbmm_logits_ce_f16(U16.data_ptr(), U16.stride(0), _ptr(y), _ptr(grp), N, D, Cn, G, That.data_ptr(), _ptr(col_bias),
+                                      inv_tau, 1 if normalize_rows else 0, batch_size, st, _ptr(pred), ws.data_ptr(), ws.numel(),
+                                      _stream_ptr()))
+    return pred
+
+
+def head_f16_supported(D: int) -> bool:
+    return D >= 64 and D % 8 == 0
+
+
 def contrastive_step(X, labels, ad: AdapterTensors, buf: "TrainBuffers", lr: float, *, idx=None, pre_norm=True, tau_cl=0.1,
                      loss_weight=0.1, momentum=0.9, weight_decay=5e-5, loss_out=None, n_valid_out=None):
     """One SGD step of `--tl_method contrastive_adapter` on the rows idx (or all rows) of X: u = L2(adapter(L2(x))), all-anchor

@@ -348,6 +348,17 @@ int dbmm_logits_ce(const float* U, int64_t ldu, const int32_t* idx, const int32_
                    int64_t batch_size, dbmm_batch_stats stats, int32_t* pred_out, void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * The same head over an fp16-RESIDENT embedding matrix (CLIP emits fp16, clip_inference.py:169; the packed store keeps it):
+ * U16[N, D] halves, row stride ldu (multiple of 8), rows 0..N-1.  kind::f16 tcgen05 MMAs on the rows as stored; the prompts
+ * enter as a scaled fp16 pair (22 significant bits), so the logits agree with dbmm_logits_ce to fp32 rounding.  D % 8 == 0,
+ * D >= 64.  Replaces the same reference lines as dbmm_logits_ce (final_main.py:757-768).
+ */
+size_t dbmm_head_f16_workspace_bytes(int64_t N, int D, int C);
+int dbmm_logits_ce_f16(const void* U16, int64_t ldu, const int32_t* y, const int32_t* grp,
+                       int64_t N, int D, int C, int G, const float* That, const float* col_bias, float inv_tau, int normalize_rows,
+                       int64_t batch_size, dbmm_batch_stats stats, int32_t* pred_out, void* ws, size_t ws_bytes, void* stream);
+
+/*
  * Linear probing (--tl_method linear_probing: LinearClassifier, final_main.py:43-49, trained by train_one_epoch,
  * final_main.py:426-496): one epoch of logits = x W^T + b, CE, dW / db, SGD (momentum, weight decay) over rows
  * order[0..n_rows-1] in batches of batch_size; W [C, D], b [C] updated in place; grads / momentum_buf: flat [C*D + C].

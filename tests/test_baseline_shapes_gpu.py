@@ -180,6 +180,16 @@ def test_head_100k_rows_x_1000_prompts(ops):
     corr = pred == y
     for k in range(4):
         assert cn[:, 0, k].sum() == int((corr & (g == k)).sum()) and cn[:, 1, k].sum() == int((g == k).sum())
+    # the fp16-resident head (kind::f16) on the same rows: same decisions, same per-slot loss sums
+    st16 = ops.BatchStatsBuffers((n + bs - 1) // bs, 4)
+    pred16 = ops.logits_ce_f16(dev(x.astype(np.float16)), dev(y, torch.int32), dev(g, torch.int32), ops.normalize_text(dev(T)), 100.0,
+                               st16, bs, G=4, want_pred=True).cpu().numpy()
+    ls16, cn16 = st16.host()
+    assert np.array_equal(pred16[decided], opred[decided])
+    np.testing.assert_allclose(ls16, ls, rtol=1e-5)
+    corr16 = pred16 == y
+    for k in range(4):
+        assert cn16[:, 0, k].sum() == int((corr16 & (g == k)).sum()) and cn16[:, 1, k].sum() == int((g == k).sum())
 
 
 def test_supcon_b8192_d768_against_oracle_subsample(ops):

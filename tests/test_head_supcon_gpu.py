@@ -63,6 +63,58 @@ def test_head_logits_ce(ops, N, D, C, gather):
             assert np.array_equal(cn[s, 0], cc) and np.array_equal(cn[s, 1], tt)
 
 
+@pytest.mark.parametrize("N,D,C", [(1000, 1024, 1000), (515, 768, 2), (700, 1024, 130), (1, 64, 5), (4133, 512, 257)])
+def test_head_logits_ce_f16(ops, N, D, C):
+    """fp16-resident head (dbmm_logits_ce_f16, kind::f16 MMAs, prompts as a scaled fp16 pair) against the oracle and against the
+    fp32-resident tf32 head: losses 1e-3 relative (observed ~1e-6), argmax equal wherever the top-2 margin exceeds fp32 noise,
+    counters exact on decided slots."""
+    rng = np.random.default_rng(300 + C)
+    x, y, mu = _embeddings(rng, N, D, C)
+    g = rng.integers(0, 4, N)
+    T = (mu.T + 0.1 * rng.standard_normal((D, C))).astype(np.float32)
+    That_np = am.normalize_text(T)
+    logits = am.head_logits(x, That_np, 0.01)
+    That = ops.normalize_text(dev(T))
+    bs = 256
+    n_slots = (N + bs - 1) // bs
+    st, st32 = ops.BatchStatsBuffers(n_slots, 4), ops.BatchStatsBuffers(n_slots, 4)
+    yd, gd = dev(y, torch.int32), dev(g, torch.int32)
+    pred = ops.logits_ce_f16(dev(x.astype(np.float16)), yd, gd, That, 100.0, st, bs, G=4, want_pred=True).cpu().numpy()
+    pred32 = ops.logits_ce(dev(x), yd, gd, That, 100.0, st32, bs, G=4, want_pred=True).cpu().numpy()
+    top2 = np.sort(logits, 1)[:, -2:]
+    safe = (top2[:, 1] - top2[:, 0]) > 1e-3 if C > 1 else np.ones(N, bool)
+    assert np.array_equal(pred[safe], logits.argmax(1)[safe]) and np.array_equal(pred[safe], pred32[safe])
+    assert safe.mean() > 0.99
+    (ls, cn), (ls32, _) = st.host(), st32.host()
+    lsm = -am.log_softmax(logits)[np.arange(N), y]
+    for s in range(n_slots):
+        sl = slice(s * bs, min(N, (s + 1) * bs))
+        assert ls[s] == pytest.approx(lsm[sl].sum(), rel=1e-3, abs=1e-3)
+        assert ls[s] == pytest.approx(ls32[s], rel=1e-4, abs=1e-4)
+        if safe[sl].all():
+            cc, tt, _ = am.group_counts(logits[sl], y[sl], g[sl], 4)
+            assert np.array_equal(cn[s, 0], cc) and np.array_equal(cn[s, 1], tt)
+
+
+def test_head_f16_linear_probe_form(ops):
+    """normalize_rows = 0 with a column bias (the linear-probe evaluation form of the head) on the fp16 path."""
+    rng = np.random.default_rng(5)
+    N, D, C = 777, 1024, 3
+    x = rng.standard_normal((N, D)).astype(np.float16)
+    W = (0.03 * rng.standard_normal((D, C))).astype(np.float32)
+    b = rng.standard_normal(C).astype(np.float32)
+    y = rng.integers(0, C, N)
+    logits = x.astype(np.float64) @ W.astype(np.float64) + b
+    st = ops.BatchStatsBuffers(1, 4)
+    pred = ops.logits_ce_f16(dev(x), dev(y, torch.int32), None, dev(W), 1.0, st, 1 << 20, G=1, normalize_rows=False, want_pred=True,
+                             col_bias=dev(b)).cpu().numpy()
+    top2 = np.sort(logits, 1)[:, -2:]
+    safe = (top2[:, 1] - top2[:, 0]) > 1e-4
+    assert np.array_equal(pred[safe], logits.argmax(1)[safe]) and safe.mean() > 0.99
+    nll = -am.log_softmax(logits)[np.arange(N), y]
+    assert st.host()[0][0] == pytest.approx(nll.sum(), rel=1e-4)
+
+
 @pytest.mark.parametrize("B,d", [(300, 128), (256, 768), (36, 64)])
 def test_supcon_loss_and_gradient(ops, B, d):
     rng = np.random.default_rng(B)
