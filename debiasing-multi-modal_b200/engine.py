@@ -369,8 +369,13 @@ def validate_zs(opt, val_loader, classifier, criterion, get_yp_func, train_group
         That = ops.normalize_text(raw.to(base.device, torch.float32).contiguous())
         stats = _stats_buffers(len(sizes), base.n_groups, base.device, "eval")
         contiguous = len(rows) == len(base) and np.array_equal(rows, np.arange(len(base)))
-        ops.logits_ce(base.x, base.labels[target], base.labels["group"], That, 1.0 / opt.zs_temperature, stats, bs,
-                      idx=None if contiguous else _order_to_device(base, rows), n_rows=n, G=base.n_groups, normalize_rows=True)
+        if contiguous and getattr(base, "x16", None) is not None and ops.head_f16_supported(base.x16.shape[1]):
+            # fp16-resident rows (CLIP emits fp16): kind::f16 head on the rows as stored, same results
+            ops.logits_ce_f16(base.x16, base.labels[target], base.labels["group"], That, 1.0 / opt.zs_temperature, stats, bs,
+                              G=base.n_groups, normalize_rows=True)
+        else:
+            ops.logits_ce(base.x, base.labels[target], base.labels["group"], That, 1.0 / opt.zs_temperature, stats, bs,
+                          idx=None if contiguous else _order_to_device(base, rows), n_rows=n, G=base.n_groups, normalize_rows=True)
         loss_sum, counts = stats.host()
         n_groups = base.n_groups
     else:
