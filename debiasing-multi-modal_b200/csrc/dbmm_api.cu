@@ -18,6 +18,7 @@
 #include "head_supcon.cuh"
 #include "eval_f16.cuh"
 #include "head_f16.cuh"
+#include "pair_gemm.cuh"
 #include "contrastive.cuh"
 #include "nccl_dyn.cuh"
 #include "linear_probe.cuh"
@@ -1336,19 +1337,36 @@ static HeadWs carve_head_ws(void* base, int64_t N, int D, int C, bool gathered) 
     w.part = (SoftmaxPart*)(p + o_part); w.gather = (float*)(p + o_g);
     return w;
 }
-struct SupconWs { float *zhi, *zlo, *zthi, *ztlo, *G, *ghi, *glo, *gthi, *gtlo, *scale; int Bgp, Blp; size_t total; };
+struct SupconWs {
+    float *zhi, *zlo, *zthi, *ztlo, *G, *ghi, *glo, *gthi, *gtlo, *scale; int Bgp, Blp;
+    // fp16-pair path (pair_gemm.cuh): Z, Z^T, G, G^T as unscaled fp16 pairs of the 2^k-scaled matrices; sc: [0] |Z| max bits,
+    // [1] 2^kz, [2] 2^-kz, [4] |G| max bits, [5] 2^kg, [6] 2^-kg
+    __half *zh, *zl, *zth, *ztl, *gh, *gl, *gth, *gtl; float* sc; int Bg8, Bl8;
+    size_t total;
+};
+static bool supcon_f16(int d) {
+    static const bool off = getenv("DBMM_SUPCON") && strcmp(getenv("DBMM_SUPCON"), "tf32") == 0;      // debugging switch: 3xTF32 GEMMs
+    return !off && d % 8 == 0 && d >= 64;
+}
 static SupconWs carve_supcon_ws(void* base, int Bl, int Bg, int d) {
     SupconWs w; char* p = (char*)base; size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    w.Bgp = (Bg + 3) & ~3; w.Blp = (Bl + 3) & ~3;
-    const size_t zb = sizeof(float) * (size_t)Bg * d, ztb = sizeof(float) * (size_t)d * w.Bgp;
-    const size_t gb = sizeof(float) * (size_t)Bl * w.Bgp, gtb = sizeof(float) * (size_t)Bg * w.Blp;
-    const size_t o1 = take(zb), o2 = take(zb), o3 = take(ztb), o4 = take(ztb), o5 = take(gb), o6 = take(gb), o7 = take(gb),
+    w.Bgp = (Bg + 3) & ~3; w.Blp = (Bl + 3) & ~3; w.Bg8 = (Bg + 7) & ~7; w.Bl8 = (Bl + 7) & ~7;
+    const bool f16 = supcon_f16(d);
+    const size_t zb = f16 ? 0 : sizeof(float) * (size_t)Bg * d, ztb = f16 ? 0 : sizeof(float) * (size_t)d * w.Bgp;
+    const size_t gb = sizeof(float) * (size_t)Bl * w.Bgp, gtb = f16 ? 0 : sizeof(float) * (size_t)Bg * w.Blp;
+    const size_t o1 = take(zb), o2 = take(zb), o3 = take(ztb), o4 = take(ztb), o5 = take(gb), o6 = take(f16 ? 0 : gb), o7 = take(f16 ? 0 : gb),
                  o8 = take(gtb), o9 = take(gtb), o10 = take(256);
+    const size_t hz = f16 ? sizeof(__half) * (size_t)Bg * d : 0, hzt = f16 ? sizeof(__half) * (size_t)d * w.Bg8 : 0;
+    const size_t hg = f16 ? sizeof(__half) * (size_t)Bl * w.Bg8 : 0, hgt = f16 ? sizeof(__half) * (size_t)Bg * w.Bl8 : 0;
+    const size_t h1 = take(hz), h2 = take(hz), h3 = take(hzt), h4 = take(hzt), h5 = take(hg), h6 = take(hg), h7 = take(hgt), h8 = take(hgt),
+                 h9 = take(256);
     w.total = off;
     w.zhi = (float*)(p + o1); w.zlo = (float*)(p + o2); w.zthi = (float*)(p + o3); w.ztlo = (float*)(p + o4);
     w.G = (float*)(p + o5); w.ghi = (float*)(p + o6); w.glo = (float*)(p + o7); w.gthi = (float*)(p + o8); w.gtlo = (float*)(p + o9);
     w.scale = (float*)(p + o10);
+    w.zh = (__half*)(p + h1); w.zl = (__half*)(p + h2); w.zth = (__half*)(p + h3); w.ztl = (__half*)(p + h4);
+    w.gh = (__half*)(p + h5); w.gl = (__half*)(p + h6); w.gth = (__half*)(p + h7); w.gtl = (__half*)(p + h8); w.sc = (float*)(p + h9);
     return w;
 }
 }  // namespace dbmm
@@ -1473,6 +1491,7 @@ static int supcon_check(const float* Z_all, int Bg, int d, int64_t row0, int Bl,
     DBMM_CHECK_SHAPE(d >= 4 && d % 4 == 0, "embedding width d=%d must be a positive multiple of 4", d);
     DBMM_CHECK_ARG(Bl >= 1 && Bg >= Bl && row0 >= 0 && row0 + Bl <= Bg && row0 % 4 == 0, "bad anchor slice row0=%lld Bl=%d Bg=%d",
                    (long long)row0, Bl, Bg);
+    DBMM_CHECK_ARG(!supcon_f16(d) || row0 % 8 == 0, "fp16-pair contrastive GEMMs need an anchor slice starting at a multiple of 8 (row0=%lld)", (long long)row0);
     (void)labels;
     return DBMM_OK;
 }
@@ -1484,6 +1503,21 @@ int dbmm_supcon_fwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, con
     DBMM_CHECK_ARG(labels && loss_sum && n_valid, "NULL labels / loss_sum / n_valid");
     SupconWs w = carve_supcon_ws(ws, Bl, Bg, d);
     DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
+    if (supcon_f16(d)) {
+        // fp16-pair path: Z 2^kz -> (Zh, Zl); S = Zh Zh^T + Zh Zl^T + Zl Zh^T in one accumulator, unscaled by 2^-2kz in the epilogue
+        DBMM_CUDA(cudaMemsetAsync(w.sc, 0, 32, st));
+        k_absmax_bits<<<148, 256, 0, st>>>(Z_all, (int64_t)Bg * d, (unsigned*)w.sc);
+        k_head_bscale<<<1, 1, 0, st>>>((const unsigned*)w.sc, w.sc + 1);
+        k_pair_split<<<148 * 4, 256, 0, st>>>(Z_all, d, w.zh, w.zl, Bg, d, d, w.sc + 1);
+        DBMM_LAUNCH_CHECK();
+        PairGemmArgs pg;
+        memset(&pg, 0, sizeof(pg));
+        pg.M = Bl; pg.N = Bg; pg.K = d; pg.scale = inv_tau_cl; pg.sdev[0] = w.sc + 2; pg.sdev[1] = w.sc + 2; pg.C = w.G; pg.ldc = w.Bgp;
+        if (int rc = launch_pair_gemm(w.zh + (size_t)row0 * d, w.zl + (size_t)row0 * d, d, w.zh, w.zl, d, pg, st)) return rc;
+        k_supcon_rows<<<Bl, 256, 0, st>>>(w.G, w.Bgp, Bl, Bg, row0, labels, loss_sum, n_valid, row_loss, (unsigned*)(w.sc + 4));
+        DBMM_LAUNCH_CHECK();
+        return DBMM_OK;
+    }
     k_split_hi_lo<<<148 * 2, 256, 0, st>>>(Z_all, d, w.zhi, w.zlo, Bg, d, d);
     DBMM_LAUNCH_CHECK();
     TcGemmArgs g;
@@ -1503,6 +1537,31 @@ int dbmm_supcon_bwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, flo
     SupconWs w = carve_supcon_ws(ws, Bl, Bg, d);
     DBMM_CHECK_ARG(w.total <= ws_bytes, "workspace too small: need %zu, have %zu", w.total, ws_bytes);
     k_supcon_scale<<<1, 1, 0, st>>>(n_valid_global, 1.0f, w.scale);
+    if (supcon_f16(d)) {
+        // G (largest magnitude recorded by k_supcon_rows) and Z^T as fp16 pairs; one pass over G writes it row-major and transposed
+        const bool whole = Bl == Bg && row0 == 0;              // one rank holds every anchor: both roles in ONE GEMM, dZ = (G + G^T) Z
+        k_head_bscale<<<1, 1, 0, st>>>((const unsigned*)(w.sc + 4), w.sc + 5, whole ? 1 : 0);
+        k_pair_split_both<<<dim3(ceil_div(d, 32), ceil_div(Bg, 32)), 256, 0, st>>>(Z_all, d, nullptr, nullptr, 0, w.zth, w.ztl, w.Bg8, Bg, d, w.sc + 1);
+        PairGemmArgs pg;
+        memset(&pg, 0, sizeof(pg));
+        if (whole) {
+            k_pair_split_sym<<<dim3(ceil_div(Bg, 32), ceil_div(Bg, 32)), 256, 0, st>>>(w.G, w.Bgp, w.gh, w.gl, w.Bg8, Bg, w.sc + 5);
+            DBMM_LAUNCH_CHECK();
+            if (!accumulate_all) DBMM_CUDA(cudaMemsetAsync(dZ_all, 0, sizeof(float) * (size_t)Bg * d, st));
+            pg.M = Bg; pg.N = d; pg.K = Bg; pg.scale = inv_tau_cl; pg.sdev[0] = w.scale; pg.sdev[1] = w.sc + 6; pg.sdev[2] = w.sc + 2;
+            pg.C = dZ_local; pg.ldc = d;
+            return launch_pair_gemm(w.gh, w.gl, w.Bg8, w.zth, w.ztl, w.Bg8, pg, st);
+        }
+        k_pair_split_both<<<dim3(ceil_div(Bg, 32), ceil_div(Bl, 32)), 256, 0, st>>>(w.G, w.Bgp, w.gh, w.gl, w.Bg8, w.gth, w.gtl, w.Bl8, Bl, Bg, w.sc + 5);
+        DBMM_LAUNCH_CHECK();
+        // anchor role: dZ_local[i] = (1 / (tau n)) sum_j G_ij z_j
+        pg.M = Bl; pg.N = d; pg.K = Bg; pg.scale = inv_tau_cl; pg.sdev[0] = w.scale; pg.sdev[1] = w.sc + 6; pg.sdev[2] = w.sc + 2;
+        pg.C = dZ_local; pg.ldc = d;
+        if (int rc = launch_pair_gemm(w.gh, w.gl, w.Bg8, w.zth, w.ztl, w.Bg8, pg, st)) return rc;
+        // contrast role: dZ_all[j] (+)= (1 / (tau n)) sum_i G_ij z_i   over this rank's anchors i
+        pg.M = Bg; pg.N = d; pg.K = Bl; pg.C = dZ_all; pg.ldc = d; pg.accumulate = accumulate_all;
+        return launch_pair_gemm(w.gth, w.gtl, w.Bl8, w.zth + row0, w.ztl + row0, w.Bg8, pg, st);
+    }
     k_split_hi_lo<<<148 * 4, 256, 0, st>>>(w.G, w.Bgp, w.ghi, w.glo, Bl, Bg, w.Bgp);
     k_transpose_split<<<dim3(ceil_div(Bg, 32), ceil_div(Bl, 32)), 256, 0, st>>>(w.G, w.Bgp, w.gthi, w.gtlo, Bl, Bg, w.Blp);
     k_transpose_split<<<dim3(ceil_div(d, 32), ceil_div(Bg, 32)), 256, 0, st>>>(Z_all, d, w.zthi, w.ztlo, Bg, d, w.Bgp);

@@ -330,11 +330,11 @@ __global__ void __launch_bounds__(256) k_absmax_bits(const float* __restrict__ i
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 // sc[0] = 2^k with max |T| 2^k in [2^14, 2^15), sc[1] = 2^-k
-__global__ void k_head_bscale(const unsigned* absmax_bits, float* sc) {
+__global__ void k_head_bscale(const unsigned* absmax_bits, float* sc, int headroom = 0) {      // headroom: extra bits kept free
     const float m = __uint_as_float(absmax_bits[0]);
     int e = 0;
     if (m > 0.f) e = ilogbf(m);
-    int k = 14 - e;
+    int k = 14 - e - headroom;
     k = k > 100 ? 100 : (k < -100 ? -100 : k);
     sc[0] = ldexpf(1.0f, k); sc[1] = ldexpf(1.0f, -k);
 }

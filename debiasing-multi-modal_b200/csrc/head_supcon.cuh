@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) k_head_finish(const SoftmaxPart* __restri
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_supcon_rows(float* __restrict__ S, int64_t lds, int Bl, int Bg, int64_t row0,
                                                      const int32_t* __restrict__ labels, double* loss_sum, int* n_valid,
-                                                     float* __restrict__ row_loss) {
+                                                     float* __restrict__ row_loss, unsigned* gmax_bits = nullptr) {
     __shared__ float red[8];
     __shared__ int redi[8];
     const int i = blockIdx.x;
@@ -162,10 +162,16 @@ __global__ void __launch_bounds__(256) k_supcon_rows(float* __restrict__ S, int6
         if (j != self) se += expf(row[j] - mx);
     se = block_sum(se);
     const float inv_se = valid ? 1.0f / se : 0.f, inv_np = valid ? 1.0f / (float)npos : 0.f;
+    float gm = 0.f;
     for (int j = tid; j < Bg; j += 256) {
         float g = 0.f;
         if (valid && j != self) g = expf(row[j] - mx) * inv_se - (labels[j] == li ? inv_np : 0.f);
         row[j] = g;
+        gm = fmaxf(gm, fabsf(g));
+    }
+    if (gmax_bits) {                                   // largest |G| (bit pattern of a non-negative float): scale of the fp16 pair split
+        gm = block_max(gm);
+        if (tid == 0 && gm > 0.f) atomicMax(gmax_bits, __float_as_uint(gm));
     }
     if (tid == 0) {
         const float l = valid ? (logf(se) + mx - psum * inv_np) : 0.f;

@@ -381,6 +381,10 @@ int dbmm_linear_train_epoch(const float* X, int64_t ldx, const int32_t* order, i
  *   bwd:  dZ_local[Bl, d]  = anchor-role gradient of this rank's rows,
  *         dZ_all[Bg, d] (+)= contrast-role gradient of every row of the global batch from this rank's anchors
  *         (reduce-scatter it across ranks; on one GPU the gradient is dZ_local + dZ_all), both scaled by 1 / *n_valid_global.
+ *         When this rank holds EVERY anchor (row0 == 0, Bl == Bg) only the SUM dZ_local + dZ_all is defined per row: the
+ *         fp16-pair path folds both roles into one GEMM, dZ_local = (G + G^T) Z, and leaves dZ_all zero / unchanged.
+ * GEMMs: kind::f16 tcgen05 on fp16 pairs of the power-of-two-scaled operands (22 significant bits, pair_gemm.cuh) when
+ * d % 8 == 0, d >= 64 (then row0 % 8 == 0 is required); 3xTF32 otherwise (DBMM_SUPCON=tf32 forces it).
  */
 size_t dbmm_supcon_workspace_bytes(int Bl, int Bg, int d);
 int dbmm_supcon_fwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, const int32_t* labels, float inv_tau_cl,
