@@ -154,7 +154,8 @@ def extra_legs(torch, ops, dev, P, e0, e1):
     fl = 6.0 * B * d * B
     res["supcon_b8192_d768"] = {"rows": B, "emb_per_s": B / t, "ms": t * 1e3, "algorithmic_tflops": fl / t / 1e12,
                                 "frac_of_bf16_sustained_peak": fl / t / 1e12 / P["tc_sustained"], "loss": sc.loss(),
-                                "note": "3xTF32 (6x the bf16 cost per algorithmic flop); similarity gradient staged in HBM"}
+                                "note": "kind::f16 on fp16 pairs of the power-of-two-scaled operands (three products, one TMEM accumulator: 3x the bf16 cost per "
+                                        "algorithmic flop); whole-batch backward as ONE GEMM dZ = (G + G^T) Z; similarity matrix staged in HBM once"}
     return res
 
 

@@ -1545,7 +1545,7 @@ int dbmm_supcon_bwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, flo
         PairGemmArgs pg;
         memset(&pg, 0, sizeof(pg));
         if (whole) {
-            k_pair_split_sym<<<dim3(ceil_div(Bg, 32), ceil_div(Bg, 32)), 256, 0, st>>>(w.G, w.Bgp, w.gh, w.gl, w.Bg8, Bg, w.sc + 5);
+            k_pair_split_sym<<<dim3(ceil_div(Bg, 64), ceil_div(Bg, 64)), 256, 0, st>>>(w.G, w.Bgp, w.gh, w.gl, w.Bg8, Bg, w.sc + 5);
             DBMM_LAUNCH_CHECK();
             if (!accumulate_all) DBMM_CUDA(cudaMemsetAsync(dZ_all, 0, sizeof(float) * (size_t)Bg * d, st));
             pg.M = Bg; pg.N = d; pg.K = Bg; pg.scale = inv_tau_cl; pg.sdev[0] = w.scale; pg.sdev[1] = w.sc + 6; pg.sdev[2] = w.sc + 2;

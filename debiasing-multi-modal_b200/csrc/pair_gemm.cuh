@@ -9,7 +9,10 @@
 // accumulator (the missing Al*Bl is 2^-22 relative); the epilogue multiplies by the inverse powers of two (device scalars).
 // Against the 3xTF32 GEMM: the same three MMAs per k-step, each at twice the rate and on half the bytes.
 //
-// Users: the contrastive regulariser (config 3): S = Z Z^T / tau and the two gradient GEMMs dZ = G Z, G^T Z.
+// Users: the contrastive regulariser (config 3): S = Z Z^T / tau and the gradient GEMMs dZ = G Z, G^T Z (one GEMM (G + G^T) Z when
+// one rank holds the whole batch).  Measured, B = 8192, d = 768: 256 us per GEMM (1.2 PFLOP/s executed, L2 -> SM bound at 64 KB
+// per 12 MMAs).  Tried and dropped: the masked log-sum-exp row pass inside the S GEMM's epilogue -- 128 columns of online
+// softmax + label compares per thread outlast the tile's MMAs (S GEMM 256 -> 588 us); k_supcon_rows (144 us) stays a kernel.
 // Persistent CTAs walk 128 x 128 tiles (column tiles fastest); TMA boxes of 64 halfs x 128 rows (SWIZZLE_128B), 3-stage ring of
 // (Ah, Al, Bh, Bl), one TMA thread, one MMA thread, four epilogue warps, accumulator double-buffered in TMEM.
 #pragma once
@@ -221,23 +224,33 @@ __global__ void __launch_bounds__(256) k_pair_split_both(const float* __restrict
 // pair of W * sc[0], row-major [n][ld_out].  Tile (bi, bj) reads G tiles (bi, bj) and (bj, bi) (the latter through shared memory).
 __global__ void __launch_bounds__(256) k_pair_split_sym(const float* __restrict__ G, int64_t ldg, __half* __restrict__ hi,
                                                         __half* __restrict__ lo, int64_t ld_out, int n, const float* __restrict__ sc) {
-    __shared__ float t[32][33];
+    // 64 x 64 tiles, a thread owns two adjacent columns: 256-byte row reads, 128-byte row writes per array (ldg, ld_out even)
+    __shared__ float t[64][65];
     const float s2k = sc[0];
-    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8) {                               // transposed partner tile: rows c0.., columns r0..
-        const int r = c0 + i, c = r0 + tx;
-        t[i][tx] = (r < n && c < n) ? G[(size_t)r * ldg + c] : 0.f;
+    for (int i = ty; i < 64; i += 8) {                               // transposed partner tile: rows c0.., columns r0..
+        const int r = c0 + i, c = r0 + 2 * tx;
+        float2 v = make_float2(0.f, 0.f);
+        if (r < n && c + 1 < n) v = *reinterpret_cast<const float2*>(G + (size_t)r * ldg + c);
+        else if (r < n && c < n) v.x = G[(size_t)r * ldg + c];
+        t[i][2 * tx] = v.x; t[i][2 * tx + 1] = v.y;
     }
     __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + tx;
-        if (r < n && c < n) {
-            const float v = (G[(size_t)r * ldg + c] + t[tx][i]) * s2k;
-            const __half h = __float2half_rn(v);
-            hi[(size_t)r * ld_out + c] = h;
-            lo[(size_t)r * ld_out + c] = __float2half_rn(v - __half2float(h));
-        }
+    for (int i = ty; i < 64; i += 8) {
+        const int r = r0 + i, c = c0 + 2 * tx;
+        if (r >= n || c >= n) continue;
+        const bool two = c + 1 < n;
+        float2 g = make_float2(0.f, 0.f);
+        if (two) g = *reinterpret_cast<const float2*>(G + (size_t)r * ldg + c);
+        else g.x = G[(size_t)r * ldg + c];
+        const float v0 = (g.x + t[2 * tx][i]) * s2k, v1 = (g.y + t[2 * tx + 1][i]) * s2k;
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+        if (two) {
+            *reinterpret_cast<__half2*>(hi + (size_t)r * ld_out + c) = __halves2half2(h0, h1);
+            *reinterpret_cast<__half2*>(lo + (size_t)r * ld_out + c) = __halves2half2(l0, l1);
+        } else { hi[(size_t)r * ld_out + c] = h0; lo[(size_t)r * ld_out + c] = l0; }
     }
 }
 
