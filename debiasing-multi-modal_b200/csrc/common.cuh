@@ -80,6 +80,7 @@ static inline bool pdl_enabled() {
     static const bool on = !(getenv("DBMM_PDL") && strcmp(getenv("DBMM_PDL"), "0") == 0);
     return on;
 }
+static thread_local bool g_plain_next_launch = false;     // set by a call site to launch ITS next kernel without the programmatic attribute
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg;
@@ -88,8 +89,15 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = (pdl_enabled() && !g_plain_next_launch) ? 1 : 0;
+    g_plain_next_launch = false;
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+// true when `tag` is listed in DBMM_NOPDL (comma-separated kernel tags: tuning switch): that kernel is then launched without the
+// programmatic attribute, i.e. its CTAs do not become resident before its predecessor has completed
+static inline bool pdl_off_for(const char* tag) {
+    const char* e = getenv("DBMM_NOPDL");
+    return e && strstr(e, tag) != nullptr;
 }
 
 __host__ __device__ static inline int s_stride(int H) { return (H + 1 + 3) & ~3; }     // row stride of the S matrix and of the [h | 1] rows

@@ -111,7 +111,16 @@ static int launch_rows(const RowsArgs& ra, int nad, int H, int C, cudaStream_t s
 
 // Gram matrix of one adapter, G = [W2 | b2]^T [W2 | b2 | That]  ((H+1) x (H+1+C), K = D): atomics-free TN GEMM.
 struct TnSplit { float* part; int* ticket; };       // K-slice scratch of the training workspace (nullptr: one CTA per tile walks all of K)
-static inline int tn_ksplit(int K) { int k = K / 128; return k < 1 ? 1 : (k > TNG_MAX_KSPLIT ? TNG_MAX_KSPLIT : k); }
+// K-slices of the TN GEMMs.  At most 5: the S^T GEMM of a 1024-row step then runs as 75 CTAs, which fit on the ~20 SMs the
+// 128-CTA tensor-core kernels of the main branch leave free (measured, scripts/train_only.py: 8 slices = 120 CTAs 49.2 us / step,
+// 5 slices 47.0, 4 slices 47.6, 3 slices 52.0 -- the W2 branch is co-critical: the step takes 36.1 us without it).
+static inline int tn_ksplit(int K) {
+    static const int env = getenv("DBMM_TN_KSPLIT") ? atoi(getenv("DBMM_TN_KSPLIT")) : 0;       // tuning switch
+    int k = K / 128;
+    if (k > 5) k = 5;
+    if (env >= 1 && env <= TNG_MAX_KSPLIT && env <= K / 128) k = env;
+    return k < 1 ? 1 : (k > TNG_MAX_KSPLIT ? TNG_MAX_KSPLIT : k);
+}
 static int launch_gram_gemm(const dbmm_adapter* ad, const float* That, float* gram, int D, int H, int C, cudaStream_t st,
                             const TnSplit* sp = nullptr, bool pdl = false) {
     TnGemmArgs g;
@@ -166,7 +175,10 @@ static int launch_st_gemm(const float* Lrows, const float* Hrows, float* ST, int
     g.A = cat_mat(Hrows, s_stride(H), H + 1);
     g.B = cat_mat(Lrows, l_stride(H, C), H + 1 + C);
     g.M = H + 1; g.N = H + 1 + C; g.K = B; g.C = ST; g.ldc = HR_SP_LD; g.n_store = HR_SP_LD;
-    return launch_tn_gemm(g, st, false);
+    // programmatic launch: as the first kernel of the W2 branch it gets a programmatic edge from the row kernel across the fork, so
+    // its CTAs are resident (waiting in griddepcontrol.wait, before any read of the row operands) when the row kernel retires
+    static const bool pdl = !(getenv("DBMM_ST_PDL") && strcmp(getenv("DBMM_ST_PDL"), "0") == 0);
+    return launch_tn_gemm(g, st, pdl);
 }
 
 static void fill_gemm1(Gemm1Args& g, const float* X, int64_t ldx, const int32_t* idx, int64_t pos0, int B, int D, int H,
@@ -255,6 +267,7 @@ static int launch_gemm1(const float* X, int64_t ldx, const int32_t* idx, int64_t
         r.zero_dgb = nullptr; r.zero_dgb_n = 0; r.zero_S = nullptr; r.zero_S_n = 0;
         if (zero) { r.zero_dgb = zero->dgb; r.zero_dgb_n = zero->dgb_n; }
         DBMM_CUDA(set_smem(k_reduce_stats, 0));
+        g_plain_next_launch = pdl_off_for("reduce");
         DBMM_CUDA(launch_pdl(k_reduce_stats, dim3(ceil_div(B, RS_ROWS), nad), dim3(RS_THREADS), 0, st, r));
     }
     return DBMM_OK;
@@ -659,7 +672,12 @@ static int train_step_impl(int phases, bool fresh,
         ta.rm[0] = a0->running_mean; ta.rv[0] = a0->running_var; ta.nbt[0] = (long long*)a0->num_batches_tracked;
         ta.rm[1] = ad->running_mean; ta.rv[1] = ad->running_var; ta.nbt[1] = (long long*)ad->num_batches_tracked;
         if (p2p) ta.p2p = *p2p;
-        if (tail->side && (phases & DBMM_PHASE_UPDATE)) {        // W2 role off the critical path: concurrent with the dW1 GEMM
+#ifdef DBMM_EXPERIMENTS
+        static const bool w2_skip = getenv("DBMM_W2_SKIP") != nullptr;       // timing experiment: the step without its W2 branch (wrong results)
+#else
+        constexpr bool w2_skip = false;
+#endif
+        if (tail->side && (phases & DBMM_PHASE_UPDATE) && !w2_skip) {        // W2 role off the critical path: concurrent with the dW1 GEMM
             DBMM_CUDA(cudaEventRecord(tail->ev_fork, st));
             DBMM_CUDA(cudaStreamWaitEvent(tail->side, tail->ev_fork, 0));
             ta.roles = 2;
@@ -1037,7 +1055,13 @@ static int train_epoch_impl(DbmmComm* dcomm, int world, int rank, int local_batc
         cudaStream_t cs = g_capture_stream[device];
         if (tmode == 2) {                      // the fork lives inside the captured graph only (under g_graph_mu)
             if (!g_side_stream[device]) {
-                DBMM_CUDA(cudaStreamCreateWithFlags(&g_side_stream[device], cudaStreamNonBlocking));
+                // the W2 branch is co-critical (it must finish before the next step's row kernel): its kernels are captured with
+                // the highest priority so that their CTAs are placed ahead of the main branch's when both are pending
+                int prio_lo = 0, prio_hi = 0;
+                DBMM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+                const char* pe = getenv("DBMM_SIDE_PRIO");
+                const int prio = (pe && strcmp(pe, "0") == 0) ? prio_lo : prio_hi;
+                DBMM_CUDA(cudaStreamCreateWithPriority(&g_side_stream[device], cudaStreamNonBlocking, prio));
                 DBMM_CUDA(cudaEventCreateWithFlags(&g_fork_event[device], cudaEventDisableTiming));
                 DBMM_CUDA(cudaEventCreateWithFlags(&g_join_event[device], cudaEventDisableTiming));
             }

@@ -268,6 +268,7 @@ static int launch_gemm1_tc_impl(const Gemm1TcArgs& a, cudaStream_t st) {
     const int kb_per = (a.D / G1_BK + a.ksplit - 1) / a.ksplit;
     b.stages = kb_per < Cfg::STAGES ? kb_per : Cfg::STAGES;
     const size_t smem = train_smem_bytes((size_t)b.stages * Cfg::STAGE_BYTES + 1024 + 256, Cfg::SMEM, a.pack);
+    g_plain_next_launch = pdl_off_for("gemm1");
     DBMM_CUDA(launch_pdl(kern, grid, dim3(G1_THREADS), smem, st, b));
     return DBMM_OK;
 }

@@ -258,6 +258,7 @@ static int launch_wgrad_tc(const WgradTcArgs& a, int nchunk, cudaStream_t st) {
     const int n_sub_max = (a.rows_per_chunk + WG_BK - 1) / WG_BK;
     b.stages = n_sub_max < WG_STAGES ? n_sub_max : WG_STAGES;
     const size_t smem = train_smem_bytes((size_t)b.stages * WG_STAGE_BYTES + 1024 + 256, WG_SMEM, a.pack);
+    g_plain_next_launch = pdl_off_for("wgrad");
     DBMM_CUDA(launch_pdl(k_wgrad_tc, grid, dim3(WG_THREADS), smem, st, b));
     return DBMM_OK;
 }
