@@ -145,12 +145,16 @@ static inline AdapterView view_of(const dbmm_adapter* a) {
 }
 
 // Train-step workspace carve-up (all offsets in bytes, 256-byte aligned).
-// Shared memory a training launch of the tensor-core kernels asks for: `pack` (data parallel) -> just the stage ring it
-// uses (two CTAs may share an SM, leaving SMs to the W2 role); otherwise the full ring, i.e. one CTA per SM.
+// Shared memory a training launch of the tensor-core kernels asks for: 120 KB: two of these CTAs cannot share an SM (each
+// keeps its SM's load bandwidth), but the 49 KB CTAs of the W2 branch's TN GEMM can sit beside one.  With the full 193 KB ring
+// a TN-GEMM CTA that reached an SM first kept the next tensor-core CTA off it until it retired (measured, scripts/train_only.py:
+// 193 KB 49.2 us / step, 120 KB 44.0; the step takes 36.1 us without its W2 branch).  DBMM_SOLO_KB overrides.
 static inline size_t train_smem_bytes(size_t needed, size_t full, int pack) {
-    static const int env = getenv("DBMM_SOLO_KB") ? atoi(getenv("DBMM_SOLO_KB")) : -1;      // timing experiments
+    static const int env = getenv("DBMM_SOLO_KB") ? atoi(getenv("DBMM_SOLO_KB")) : -1;      // tuning switch
     if (env >= 0) return needed > (size_t)env * 1024 ? needed : (size_t)env * 1024;
-    return pack ? needed : full;
+    (void)pack;         // data parallel used to ask for the used ring only (two CTAs per SM): 2 GPUs 56.5 us / step, 120 KB 55.0, 193 KB 58.8
+    const size_t solo = (size_t)120 * 1024;
+    return needed > solo ? needed : (full < solo ? full : solo);
 }
 constexpr int DBMM_LR_TABLE = 65536;          // learning rates (one per step) a single epoch graph can address
 constexpr int DBMM_G1_PART_ROWS = 16384;      // ksplit * nad * ceil128(B) never exceeds this (see gemm1_ksplit)

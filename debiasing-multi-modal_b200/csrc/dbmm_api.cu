@@ -111,13 +111,12 @@ static int launch_rows(const RowsArgs& ra, int nad, int H, int C, cudaStream_t s
 
 // Gram matrix of one adapter, G = [W2 | b2]^T [W2 | b2 | That]  ((H+1) x (H+1+C), K = D): atomics-free TN GEMM.
 struct TnSplit { float* part; int* ticket; };       // K-slice scratch of the training workspace (nullptr: one CTA per tile walks all of K)
-// K-slices of the TN GEMMs.  At most 5: the S^T GEMM of a 1024-row step then runs as 75 CTAs, which fit on the ~20 SMs the
-// 128-CTA tensor-core kernels of the main branch leave free (measured, scripts/train_only.py: 8 slices = 120 CTAs 49.2 us / step,
-// 5 slices 47.0, 4 slices 47.6, 3 slices 52.0 -- the W2 branch is co-critical: the step takes 36.1 us without it).
+// K-slices of the TN GEMMs: 128 batch rows per slice (the S^T GEMM of a 1024-row step = 120 short CTAs of 49 KB, which share SMs
+// with the 120 KB tensor-core CTAs of the main branch, see train_smem_bytes).  The W2 branch is co-critical: measured
+// (scripts/train_only.py) 8 slices 44.0 us / step, 6 slices 47.6, 5 slices 47.3; DBMM_TN_KSPLIT overrides.
 static inline int tn_ksplit(int K) {
     static const int env = getenv("DBMM_TN_KSPLIT") ? atoi(getenv("DBMM_TN_KSPLIT")) : 0;       // tuning switch
     int k = K / 128;
-    if (k > 5) k = 5;
     if (env >= 1 && env <= TNG_MAX_KSPLIT && env <= K / 128) k = env;
     return k < 1 ? 1 : (k > TNG_MAX_KSPLIT ? TNG_MAX_KSPLIT : k);
 }
@@ -605,7 +604,12 @@ static int train_step_impl(int phases, bool fresh,
                                   fused && !fresh ? &sz : nullptr)) return rc;
     }
     if (phases & DBMM_PHASE_ROWS) {
-        if (fused && tail->join_pending) {                       // the previous step's W2 role: new Gram matrix
+#ifdef DBMM_EXPERIMENTS
+        static const bool late_join = getenv("DBMM_LATE_JOIN") != nullptr;    // timing experiment (wrong results): the row kernel does not wait
+#else
+        constexpr bool late_join = false;
+#endif
+        if (fused && tail->join_pending && !late_join) {                       // the previous step's W2 role: new Gram matrix
             DBMM_CUDA(cudaStreamWaitEvent(st, tail->ev_join, 0));
             tail->join_pending = false;
         }
