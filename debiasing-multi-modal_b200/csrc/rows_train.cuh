@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) { rows_
 
 static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) {
     const int CT = ra.C <= 4 ? 4 : 16;
-    const int nw = nad == 1 ? 16 : 8;
+    static const int nw_env = getenv("DBMM_ROWS_NW") ? atoi(getenv("DBMM_ROWS_NW")) : 0;          // tuning switch (8: half the registers per CTA)
+    const int nw = (nad == 1 && nw_env != 8) ? 16 : 8;
     const size_t smem = rows_train_smem_bytes(ra.H, ra.C, nad, CT, nw);
     DBMM_CHECK_SHAPE(smem <= 227 * 1024, "train row kernel needs %zu bytes of shared memory", smem);
     int grid = ceil_div(ra.B, RT_ROWS);
@@ -364,7 +365,8 @@ static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) 
         DBMM_CUDA(set_smem(kern, smem));    \
         DBMM_CUDA(launch_pdl(kern, dim3(grid), dim3(NW_ * 32), smem, st, ra));                            \
     } while (0)
-    if (nad == 1 && CT == 4) DBMM_RT_CASE(1, 4, 16);
+    if (nad == 1 && CT == 4 && nw == 8) DBMM_RT_CASE(1, 4, 8);
+    else if (nad == 1 && CT == 4) DBMM_RT_CASE(1, 4, 16);
     else if (nad == 1) DBMM_RT_CASE(1, 16, 16);
     else if (CT == 4) DBMM_RT_CASE(2, 4, 8);
     else DBMM_RT_CASE(2, 16, 8);
