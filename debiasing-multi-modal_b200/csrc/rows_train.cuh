@@ -353,8 +353,10 @@ __global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) { rows_
 
 static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) {
     const int CT = ra.C <= 4 ? 4 : 16;
-    static const int nw_env = getenv("DBMM_ROWS_NW") ? atoi(getenv("DBMM_ROWS_NW")) : 0;          // tuning switch (8: half the registers per CTA)
-    const int nw = (nad == 1 && nw_env != 8) ? 16 : 8;
+    // 8 warps: half the register file per CTA, so the W2 branch's light CTAs can share the SM (43.3 vs 44.0 us / step at batch
+    // 1024, 65.6 vs 66.1 at 8 GPUs) although the kernel alone is a little slower than with 16; DBMM_ROWS_NW=16 restores that
+    static const int nw_env = getenv("DBMM_ROWS_NW") ? atoi(getenv("DBMM_ROWS_NW")) : 0;          // tuning switch
+    const int nw = (nad == 1 && nw_env == 16) ? 16 : 8;
     const size_t smem = rows_train_smem_bytes(ra.H, ra.C, nad, CT, nw);
     DBMM_CHECK_SHAPE(smem <= 227 * 1024, "train row kernel needs %zu bytes of shared memory", smem);
     int grid = ceil_div(ra.B, RT_ROWS);

@@ -356,7 +356,9 @@ static int launch_step_tail(StepTailArgs a, cudaStream_t st) {
     DBMM_CHECK_ARG(!p2p || (a.n_w2_ctas <= P2P_S_CTAS && (size_t)a.H * a.D <= P2P_G_FLOATS &&
                             (size_t)(a.H + 1 + a.C) * s_stride(a.H) <= P2P_S_FLOATS), "shape exceeds the peer-memory gradient slots");
     if (a.roles & 1) {
-        g_plain_next_launch = pdl_off_for("tail");
+        // single GPU: no programmatic launch for the W1 role -- its 129 early-resident CTAs otherwise sit on the SMs the W2
+        // branch's k_hs_w2 needs empty (42.9 vs 43.3 us / step); DBMM_NOPDL=none keeps the programmatic edge
+        g_plain_next_launch = pdl_off_for("tail") || (!p2p && !pdl_off_for("none"));
         if (p2p) DBMM_CUDA(launch_pdl(k_tail_w1<true>, dim3(a.n_w1_ctas + 1), dim3(ST_THREADS), 0, st, a));
         else DBMM_CUDA(launch_pdl(k_tail_w1<false>, dim3(a.n_w1_ctas + 1), dim3(ST_THREADS), 0, st, a));
     }
