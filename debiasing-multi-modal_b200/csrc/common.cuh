@@ -100,6 +100,39 @@ static inline bool pdl_off_for(const char* tag) {
     return e && strstr(e, tag) != nullptr;
 }
 
+// ---- step timeline (measurement builds only, -DDBMM_TIMELINE): %globaltimer stamps of every step kernel -- entry of its first
+// CTA, the moment that CTA passed its dependency wait, and the latest exit of any of its CTAs -- in a ring indexed by the kernel's
+// launch count; scripts/step_timeline.py turns them into the timeline of a step inside the running epoch graph (nsys is not
+// available here).  Compiles to nothing in the product build.
+enum { TL_GEMM1 = 0, TL_REDUCE, TL_ROWS, TL_WGRAD, TL_TAIL, TL_TN, TL_W2, TL_GSUM, TL_KERNELS };
+#ifdef DBMM_TIMELINE
+constexpr int TL_RING = 1024;
+__device__ unsigned long long g_tl[TL_RING][TL_KERNELS][3];            // entry, after the wait, last exit
+__device__ unsigned long long g_tl_entry[TL_KERNELS], g_tl_exit[TL_KERNELS];
+__device__ unsigned g_tl_count[TL_KERNELS];
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+struct TlScope {
+    int k; bool on;
+    __device__ __forceinline__ TlScope(int k_) : k(k_), on(threadIdx.x == 0) {
+        if (on && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tl_entry[k] = tl_now();
+    }
+    __device__ __forceinline__ ~TlScope() { if (on) atomicMax(&g_tl_exit[k], tl_now()); }
+};
+__device__ __forceinline__ void tl_wait(int k) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        const unsigned i = atomicAdd(&g_tl_count[k], 1u);
+        if (i > 0) g_tl[(i - 1) % TL_RING][k][2] = atomicExch(&g_tl_exit[k], 0ull);      // the previous launch has fully retired
+        g_tl[i % TL_RING][k][0] = g_tl_entry[k];
+        g_tl[i % TL_RING][k][1] = tl_now();
+    }
+}
+#define DBMM_TL_SCOPE(k) TlScope tl_scope_(k)
+#define DBMM_TL_WAIT(k) tl_wait(k)
+#else
+#define DBMM_TL_SCOPE(k)
+#define DBMM_TL_WAIT(k)
+#endif
+
 __host__ __device__ static inline int s_stride(int H) { return (H + 1 + 3) & ~3; }     // row stride of the S matrix and of the [h | 1] rows
 __host__ __device__ static inline int l_stride(int H, int C) { return (H + 1 + C + 3) & ~3; }     // row stride of the [c*h | c | ds] rows
 
@@ -198,7 +231,9 @@ static inline TrainWs carve_train_ws(void* base, int64_t B, int D, int H, int C,
     size_t o_tk = take(sizeof(int) * 32);
     w.accum_bytes = off;
     size_t o_tp = take(sizeof(float) * (size_t)8 * 16 * 32 * 48);       // TNG_MAX_KSPLIT * TNG_MAX_TILES * TNG_TM * TNG_TN
-    size_t o_sp = take(sizeof(float) * (size_t)((B + 63) / 64) * (H + 1) * 144);
+    // S^T shares: 64-row tiles of the tensor-core row kernel, or one share per CTA (8 rows, at most 296) of the CUDA-core one
+    const size_t sp_tiles = (size_t)((B + 63) / 64), sp_ctas = (size_t)((B + 7) / 8) <= 296 ? (size_t)((B + 7) / 8) : 0;
+    size_t o_sp = take(sizeof(float) * (sp_tiles > sp_ctas ? sp_tiles : sp_ctas) * (H + 1) * 144);
     size_t o_st = take(sizeof(float) * (size_t)(H + 1) * 144);
     size_t o_gp = take(sizeof(float) * (size_t)((D + 63) / 64) * (H + 1) * 144);
     size_t o_L = take(sizeof(float) * (size_t)B * l_stride(H, C));

@@ -582,6 +582,10 @@ static int train_step_impl(int phases, bool fresh,
     const bool tc1 = use_tc_gemm1(D, H);
     const TnSplit tsp = {w.tn_part, w.tn_ticket};
     const bool tc_rows = use_tc_rows(H, C);
+    // S^T shares straight from the CUDA-core row kernel (no TN GEMM on the W2 branch): fused tail with the tensor-core W2 kernel,
+    // one pass over the batch; DBMM_ST=gemm keeps the TN GEMM
+    static const bool st_gemm_env = getenv("DBMM_ST") && strcmp(getenv("DBMM_ST"), "gemm") == 0;
+    const bool fuse_st = fused && !tc_rows && use_tc_w2(H, C) && ceil_div(B, RT_ROWS) <= RT_MAX_FUSED_CTAS && !st_gemm_env;
 #ifdef DBMM_EXPERIMENTS
     static const int skip = getenv("DBMM_SKIP") ? atoi(getenv("DBMM_SKIP")) : 0;   // timing experiments only: drop kernels by bit mask
     if (skip) phases &= ~skip;
@@ -622,6 +626,7 @@ static int train_step_impl(int phases, bool fresh,
         ra.w_old = ebd_weight; ra.inv_tau = inv_tau; ra.inv_B = 1.0f / (float)B_global;
         ra.loss_sum = stats.loss_sum; ra.counts = stats.counts; ra.slot = slot;
         ra.dahat = w.dahat; ra.dgb = w.dgb; ra.Lrows = w.Lrows; ra.Hrows = w.Hrows;
+        if (fuse_st) { ra.Spart = w.Spart; ra.Lrows = nullptr; ra.Hrows = nullptr; }
         if (ex) { ra.logits_out = ex->logits_out; ra.dlogits_in = ex->dlogits_in; }
         if (tc_rows) {
             HsRowsArgs ha;
@@ -646,7 +651,8 @@ static int train_step_impl(int phases, bool fresh,
         const bool tc_w2 = use_tc_w2(H, C) && !(dp_p2p && tc_rows);      // (data parallel: the row kernel is the CUDA-core one)
         if (tc_rows) { if (int rc = launch_sum_spart(w.Spart, B, H, C, S_cur, tc_w2 ? w.ST : nullptr, s_, first_pdl)) return rc; }
         else if (tc_w2) {
-            if (int rc = launch_st_gemm(w.Lrows, w.Hrows, w.ST, B, H, C, s_, &tsp)) return rc;
+            if (fuse_st) { if (int rc = launch_sum_spart_g(w.Spart, ceil_div(B, RT_ROWS), H, C, w.ST, s_)) return rc; }
+            else if (int rc = launch_st_gemm(w.Lrows, w.Hrows, w.ST, B, H, C, s_, &tsp)) return rc;
             if (dp_p2p) if (int rc = launch_p2p_sum_st(w.ST, H, *p2p, s_)) return rc;       // S^T summed over the ranks, in place
         }
         else if (int rc = launch_s_gemm(w.Lrows, w.Hrows, S_cur, B, H, C, s_, &tsp)) return rc;
@@ -1863,6 +1869,22 @@ int dbmm_device_pci_bus_id(int device, char* out, int len) {
     DBMM_CHECK_ARG(out && len >= 16, "output buffer of at least 16 bytes required");
     DBMM_CUDA(cudaDeviceGetPCIBusId(out, len, device));
     return DBMM_OK;
+}
+
+// Measurement builds (-DDBMM_TIMELINE): copies the step-timeline ring (common.cuh) to the host: out[ring][kernel][3] uint64,
+// counts[kernel] launches so far.  Returns DBMM_ERR_UNSUPPORTED_SHAPE in the product build.
+int dbmm_timeline_dump(unsigned long long* out_host, unsigned* counts_host, int* ring, int* kernels) {
+#ifdef DBMM_TIMELINE
+    DBMM_CUDA(cudaDeviceSynchronize());
+    DBMM_CUDA(cudaMemcpyFromSymbol(out_host, g_tl, sizeof(unsigned long long) * TL_RING * TL_KERNELS * 3));
+    DBMM_CUDA(cudaMemcpyFromSymbol(counts_host, g_tl_count, sizeof(unsigned) * TL_KERNELS));
+    *ring = TL_RING; *kernels = TL_KERNELS;
+    return DBMM_OK;
+#else
+    (void)out_host; (void)counts_host; (void)ring; (void)kernels;
+    set_error("dbmm_timeline_dump: build with -DDBMM_TIMELINE");
+    return DBMM_ERR_UNSUPPORTED_SHAPE;
+#endif
 }
 
 int dbmm_train_tail_mode(int batch_size, int last_batch, int n_adapters, int D, int H, int C) {

@@ -114,6 +114,7 @@ __device__ __forceinline__ void gemm1_tc_body(const Gemm1TcArgs& a, const int kz
         }
     }
     ptx::pdl_wait();                // W1 hi / lo come from the previous step's update kernel
+    if (a.ksplit > 1) DBMM_TL_WAIT(TL_GEMM1);
     if (a.zero_colsum && blockIdx.x == 0 && blockIdx.y == 0 && kz == 0)       // (its chores CTA read the column sums)
         for (int e = tid; e < a.zero_colsum_n; e += G1_THREADS) a.zero_colsum[e].v = 0;
     ptx::pdl_launch();
@@ -255,7 +256,7 @@ __device__ __forceinline__ void gemm1_tc_body(const Gemm1TcArgs& a, const int kz
 }
 
 template <int BN, int TERMS>
-__global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) { gemm1_tc_body<BN, TERMS>(a, (int)blockIdx.z); }
+__global__ void __launch_bounds__(G1_THREADS, 1) k_gemm1_tc(Gemm1TcArgs a) { DBMM_TL_SCOPE(TL_GEMM1); gemm1_tc_body<BN, TERMS>(a, (int)blockIdx.z); }
 
 template <int BN, int TERMS>
 static int launch_gemm1_tc_impl(const Gemm1TcArgs& a, cudaStream_t st) {
@@ -314,7 +315,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_reduce_stats(ReduceStatsArgs a) 
     const int tid = threadIdx.x, q = tid >> 5, c = tid & 31;
     const size_t plane = (size_t)a.nad * a.B * H;
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    DBMM_TL_SCOPE(TL_REDUCE);
     ptx::pdl_wait();
+    DBMM_TL_WAIT(TL_REDUCE);
     ptx::pdl_launch();
     if (a.zero_dgb && blockIdx.x == 0 && blockIdx.y == 0)
         for (int e = tid; e < a.zero_dgb_n; e += RS_THREADS) a.zero_dgb[e].v = 0;

@@ -555,6 +555,45 @@ __device__ __forceinline__ void sum_spart_body(const SumSpartArgs& a) {
 }
 __global__ void __launch_bounds__(256) k_sum_spart(SumSpartArgs a) { sum_spart_body(a); }
 
+// S^T [j][l] (row stride HR_SP_LD, padding columns zero) = sum over the CUDA-core row kernel's per-CTA shares (rows_train.cuh:
+// up to 296 shares of 8 batch rows), added in CTA order: a thread owns one element and one of four contiguous GROUPS of shares
+// (all loads of a pass in flight together, added in order), the four group sums are combined in group order -- a fixed order,
+// so the result does not depend on timing.
+constexpr int SG_ELEMS = 64, SG_GROUPS = 4, SG_MAXT = 296, SG_PER = (SG_MAXT + SG_GROUPS - 1) / SG_GROUPS;
+struct SumSpartGArgs { const float* Spart; int tiles, H, C; float* ST; };
+__global__ void __launch_bounds__(SG_ELEMS * SG_GROUPS) k_sum_spart_g(SumSpartGArgs a) {
+    __shared__ float sg[SG_GROUPS][SG_ELEMS];
+    const int H = a.H, ldl = H + 1 + a.C;
+    const int el = threadIdx.x & (SG_ELEMS - 1), grp = threadIdx.x / SG_ELEMS;
+    const int e = blockIdx.x * SG_ELEMS + el;                    // e = j * HR_SP_LD + l over the PADDED row: padding written as zeros
+    const int j = e / HR_SP_LD, l = e - j * HR_SP_LD;
+    const bool live = j <= H && l < ldl;
+    ptx::pdl_wait();
+    ptx::pdl_launch();
+    const int per = (a.tiles + SG_GROUPS - 1) / SG_GROUPS, t0 = grp * per, t1 = min(a.tiles, t0 + per);
+    const size_t ts = (size_t)(H + 1) * HR_SP_LD;
+    const float* src = a.Spart + (size_t)j * HR_SP_LD + l;
+    float v = 0.f;
+    if (live) {
+        for (int tb = t0; tb < t1; tb += 16) {
+            float p[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) p[u] = tb + u < t1 ? __ldcg(src + (size_t)(tb + u) * ts) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v += p[u];
+        }
+    }
+    sg[grp][el] = v;
+    __syncthreads();
+    if (grp == 0 && j <= H) a.ST[(size_t)j * HR_SP_LD + l] = live ? ((sg[0][el] + sg[1][el]) + sg[2][el]) + sg[3][el] : 0.f;
+}
+static int launch_sum_spart_g(const float* Spart, int tiles, int H, int C, float* ST, cudaStream_t st) {
+    DBMM_CHECK_ARG(tiles >= 1 && tiles <= SG_MAXT, "k_sum_spart_g: %d shares", tiles);
+    SumSpartGArgs s; s.Spart = Spart; s.tiles = tiles; s.H = H; s.C = C; s.ST = ST;
+    DBMM_CUDA(launch_pdl(k_sum_spart_g, dim3(ceil_div((H + 1) * HR_SP_LD, SG_ELEMS)), dim3(SG_ELEMS * SG_GROUPS), 0, st, s));
+    return DBMM_OK;
+}
+
 static int launch_hs_rows(const HsRowsArgs& a, cudaStream_t st) {
     DBMM_CHECK_SHAPE(hs_rows_supported(a.H, a.C), "tensor-core row kernel needs H == 128 and C <= 4 (H=%d C=%d)", a.H, a.C);
     DBMM_CUDA(set_smem(k_hs_rows, HR_SMEM));

@@ -112,6 +112,7 @@ __device__ __forceinline__ void hs_w2_body(const HsW2Args& a) {
     }
     HR_TICK(1, 1);
     ptx::pdl_wait();                // S^T comes from k_sum_spart, the kernel in front of this one
+    DBMM_TL_WAIT(TL_W2);
     ptx::pdl_launch();
     HR_TICK(1, 2);
     // B operand: B[n = j][k = l] = S^T[j][l], l < H;  rows j > H: zeros.   144 x 32 tasks, 9 per thread; every load of the
@@ -313,7 +314,7 @@ __device__ __forceinline__ void hs_w2_body(const HsW2Args& a) {
     if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
 }
 
-__global__ void __launch_bounds__(HR_THREADS, 1) k_hs_w2(HsW2Args a) { hs_w2_body(a); }
+__global__ void __launch_bounds__(HR_THREADS, 1) k_hs_w2(HsW2Args a) { DBMM_TL_SCOPE(TL_W2); hs_w2_body(a); }
 
 // G[m][n] (row stride H+1+C) = sum over the W2 tiles, in tile order: m < H: Gpart[t][m][n]; m = H: n < H: Gpart[t][n][H] (symmetry),
 // n >= H: Gpart[t][H][n].  No early launch trigger: a row kernel joined from another stream may read G before its own wait.
@@ -321,6 +322,7 @@ struct SumGpartArgs { const float* Gpart; int tiles, H, C; float* G; };
 __device__ __forceinline__ void sum_gpart_body(const SumGpartArgs& a) {
     const int H = a.H, ldg = H + 1 + a.C;
     ptx::pdl_wait();
+    DBMM_TL_WAIT(TL_GSUM);
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e >= (H + 1) * ldg) return;
     const int m = e / ldg, n = e - m * ldg;
@@ -336,7 +338,7 @@ __device__ __forceinline__ void sum_gpart_body(const SumGpartArgs& a) {
     for (; t < a.tiles; ++t) v += __ldcg(src + (size_t)t * ts);
     a.G[e] = v;
 }
-__global__ void __launch_bounds__(256) k_sum_gpart(SumGpartArgs a) { sum_gpart_body(a); }
+__global__ void __launch_bounds__(256) k_sum_gpart(SumGpartArgs a) { DBMM_TL_SCOPE(TL_GSUM); sum_gpart_body(a); }
 
 // Data parallel: S^T summed over the ranks in place (peer memory, the S slots and flags of p2p.cuh).  CTA c pushes slice c of
 // the rank's S^T to every rank, raises flag [c][rank] everywhere, waits for slice c of every rank and adds them in rank order:

@@ -8,10 +8,13 @@
 #pragma once
 #include "kernels_simt.cuh"
 #include "ptx_sm100.cuh"
+#include "tn_gemm.cuh"
 
 namespace dbmm {
 
 constexpr int RT_ROWS = 8;      // batch rows per CTA; NW warps per CTA (16 for one adapter, 8 when two Gram matrices fill the smem)
+constexpr int RT_SP_LD = 144;   // row stride of an S^T share (== HR_SP_LD of hs_rows.cuh: the operand layout of k_hs_w2)
+constexpr int RT_MAX_FUSED_CTAS = 148 * 2;
 
 struct RowsTrainArgs {
     int B; int64_t Bg;
@@ -28,6 +31,11 @@ struct RowsTrainArgs {
     const float* dlogits_in;              // optional [B][C]: upstream dL/dlogits replaces the fused CE gradient (autograd backward)
     float* Lrows; float* Hrows;           // outputs: [B][l_stride] rows [c*h | c | ds] and [B][s_stride] rows [h | 1]: the operands
                                           // of S = L^T [h | 1] (k_tn_gemm on the second graph branch)
+    float* Spart;                         // != nullptr (one pass over the batch: gridDim.x * RT_ROWS >= B): instead of those rows the CTA
+                                          // writes its share S^T_part[cta][i][j] = sum over its 8 rows of [h | 1]_i [c*h | c | ds]_j
+                                          // ([H+1][RT_SP_LD], one mma.sync k-step per 16 x 8 tile, 3xTF32); k_sum_spart_g adds the
+                                          // CTAs' shares in CTA order.  The TN GEMM this replaces was the longest kernel of the W2
+                                          // branch (14.5 us of a 43.7 us step, profiles/r3_step_timeline.md)
 };
 
 static inline size_t rows_train_smem_bytes(int H, int C, int nad, int CT, int RT_WARPS) {
@@ -75,6 +83,7 @@ __device__ __forceinline__ void rows_train_body(const RowsTrainArgs& a) {
         g_pre = a.grp ? a.grp[dsrow] : 0;
     }
     ptx::pdl_wait();                // A / column sums come from k_reduce_stats; the Gram matrix is two kernels upstream
+    DBMM_TL_WAIT(TL_ROWS);
     ptx::pdl_launch();
     // first row group's activations (adapter 0): in flight while the Gram matrix and the statistics arrive
     float av_pre[RK_HSLOT];
@@ -319,7 +328,28 @@ __device__ __forceinline__ void rows_train_body(const RowsTrainArgs& a) {
         }
         // ---- phase 4: the rows' operands of S = L^T [h | 1] go to global memory, coalesced (the batch reduction itself is a
         // small tensor-core GEMM off the critical path; round 1 issued 17 K fp32 atomics per CTA here)
-        {
+        if (a.Spart) {
+            // S^T share of these 8 rows on the warp-level tensor cores: A[i][k] = [h | 1] of row k at hidden index i, B[k][j] = the
+            // row's [c*h | c | ds]; K = 8 rows = ONE m16n8k8 step per output tile; tiles round-robin over the warps
+            const int g = lane >> 2, t4 = lane & 3;
+            const int MT = (HP + 15) >> 4, NT = (ldg + 7) >> 3;
+            float* outp = a.Spart + (size_t)blockIdx.x * HP * RT_SP_LD;
+            for (int tt = warp; tt < MT * NT; tt += RT_WARPS) {
+                const int mt = tt / NT, nt = tt - mt * NT, i0 = mt * 16 + g, j0 = nt * 8 + g;
+                uint32_t ah[4], al[4], bh[2], bl[2];
+                tf32_split(i0 < HP ? sH[(size_t)t4 * HP + i0] : 0.f, ah[0], al[0]);
+                tf32_split(i0 + 8 < HP ? sH[(size_t)t4 * HP + i0 + 8] : 0.f, ah[1], al[1]);
+                tf32_split(i0 < HP ? sH[(size_t)(t4 + 4) * HP + i0] : 0.f, ah[2], al[2]);
+                tf32_split(i0 + 8 < HP ? sH[(size_t)(t4 + 4) * HP + i0 + 8] : 0.f, ah[3], al[3]);
+                tf32_split(j0 < ldg ? sL[(size_t)t4 * ldg + j0] : 0.f, bh[0], bl[0]);
+                tf32_split(j0 < ldg ? sL[(size_t)(t4 + 4) * ldg + j0] : 0.f, bh[1], bl[1]);
+                float c4[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_3xtf32(c4, ah, al, bh, bl);
+                const int jc = nt * 8 + 2 * t4;
+                if (i0 < HP) *reinterpret_cast<float2*>(outp + (size_t)i0 * RT_SP_LD + jc) = make_float2(c4[0], c4[1]);
+                if (i0 + 8 < HP) *reinterpret_cast<float2*>(outp + (size_t)(i0 + 8) * RT_SP_LD + jc) = make_float2(c4[2], c4[3]);
+            }
+        } else {
             const int LDL = l_stride(H, C), LDH = s_stride(H);
             for (int e = tid; e < RT_ROWS * ldg; e += RT_THREADS) {
                 const int rr = e / ldg, c = e - rr * ldg;
@@ -349,7 +379,7 @@ __device__ __forceinline__ void rows_train_body(const RowsTrainArgs& a) {
 }
 
 template <int NAD, int CT, int NW>
-__global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) { rows_train_body<NAD, CT, NW>(a); }
+__global__ void __launch_bounds__(NW * 32) k_rows_train(RowsTrainArgs a) { DBMM_TL_SCOPE(TL_ROWS); rows_train_body<NAD, CT, NW>(a); }
 
 static int launch_rows_train(const RowsTrainArgs& ra, int nad, cudaStream_t st) {
     const int CT = ra.C <= 4 ? 4 : 16;

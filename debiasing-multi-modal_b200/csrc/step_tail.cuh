@@ -65,6 +65,7 @@ __device__ __forceinline__ void tail_w1_body(const StepTailArgs& a) {
         float4 pv0 = make_float4(0.f, 0.f, 0.f, 0.f), vv0 = pv0;
         if (i0 < n4) { pv0 = reinterpret_cast<const float4*>(a.W1)[i0]; vv0 = reinterpret_cast<const float4*>(a.v + oW1)[i0]; }
         ptx::pdl_wait();            // the chunk partials come from k_wgrad_tc
+        DBMM_TL_WAIT(TL_TAIL);
         ptx::pdl_launch();
         unsigned inst = 0; int parity = 0;
         if constexpr (P2P) { inst = p2p_instance(a.p2p); parity = inst & 1u; }
@@ -160,7 +161,7 @@ __device__ __forceinline__ void tail_w1_body(const StepTailArgs& a) {
 }
 
 template <bool P2P>
-__global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) { tail_w1_body<P2P>(a); }
+__global__ void __launch_bounds__(ST_THREADS) k_tail_w1(StepTailArgs a) { DBMM_TL_SCOPE(TL_TAIL); tail_w1_body<P2P>(a); }
 
 // ---- role bit 1: W2 / b2 rows [d0, d0 + ST2_ROWS):  dW2a[d][n] = sum_k L[d][k] S[k][n],  L = [W2 | b2 | That], then SGD on
 // those rows.  The contraction runs on the tensor cores as warp-level mma.sync m16n8k8 with 3xTF32 split operands

@@ -91,6 +91,7 @@ __device__ __forceinline__ void tn_gemm_body(const TnGemmArgs& a, const int kz =
     const int kb_lo = kz * kb_per;
     const int KB = max(0, min(KB_all, kb_lo + kb_per) - kb_lo);
     ptx::pdl_wait();                // the operands come from the preceding kernel of this branch (row kernel / W2 update)
+    if (a.ksplit > 1) DBMM_TL_WAIT(TL_TN);
     if (!a.no_early_trigger) ptx::pdl_launch();
 
     auto issue = [&](int kb) {
@@ -209,7 +210,7 @@ __device__ __forceinline__ void tn_gemm_body(const TnGemmArgs& a, const int kz =
     }
 }
 
-__global__ void __launch_bounds__(TNG_THREADS) k_tn_gemm(TnGemmArgs a) { tn_gemm_body(a, (int)blockIdx.z); }
+__global__ void __launch_bounds__(TNG_THREADS) k_tn_gemm(TnGemmArgs a) { DBMM_TL_SCOPE(TL_TN); tn_gemm_body(a, (int)blockIdx.z); }
 
 static inline size_t tn_gemm_part_floats() { return (size_t)TNG_MAX_KSPLIT * TNG_MAX_TILES * TNG_TM * TNG_TN; }
 

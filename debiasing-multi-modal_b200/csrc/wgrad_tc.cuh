@@ -149,6 +149,7 @@ __device__ __forceinline__ void wgrad_tc_body(const WgradTcArgs& a) {
     }
     if (warp == 4) ptx::tmem_alloc<WG_TILE>(tmem_ptr);
     ptx::pdl_wait();                // dahat / dgamma / dbeta come from the row kernel (X, idx are constants)
+    DBMM_TL_WAIT(TL_WGRAD);
     ptx::pdl_launch();
     if (warp < 4) load_da(0, 0, av, dv);
     if (a.p2p.world && blockIdx.x == 0 && blockIdx.y == 0) p2p_push_now(a.p2p, 1, a.dgb, 2 * H);     // this rank's sums -> every rank
@@ -240,7 +241,7 @@ __device__ __forceinline__ void wgrad_tc_body(const WgradTcArgs& a) {
     if (warp == 4) ptx::tmem_dealloc<WG_TILE>(tmem_base);
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) { wgrad_tc_body(a); }
+__global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(WgradTcArgs a) { DBMM_TL_SCOPE(TL_WGRAD); wgrad_tc_body(a); }
 
 static inline int wgrad_tc_chunks(int B, int* rows_per_chunk) {
     // ~16 batch chunks (128 CTAs at D = 1024), each a multiple of the 64-row stage

@@ -392,6 +392,11 @@ int dbmm_supcon_fwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, con
 int dbmm_supcon_bwd(const float* Z_all, int Bg, int d, int64_t row0, int Bl, float inv_tau_cl, const int32_t* n_valid_global,
                     float* dZ_local, float* dZ_all, int accumulate_all, void* ws, size_t ws_bytes, void* stream);
 
+/* Measurement aid (-DDBMM_TIMELINE builds only; an error in the product build): %globaltimer stamps {entry of the first CTA,
+ * after its dependency wait, last CTA exit} of every kernel of the training step, ring[1024][8 kernels][3], for
+ * scripts/step_timeline.py (the timeline of a step inside the running epoch graph). */
+int dbmm_timeline_dump(unsigned long long* out_host, unsigned* counts_host, int* ring, int* kernels);
+
 #ifdef __cplusplus
 }
 #endif
