@@ -118,6 +118,36 @@ def test_fused_epoch_b1024_stage2_matches_oracle(ops):
     assert np.array_equal(st.host()[1], counts_ref)
 
 
+def test_large_batch_epoch_uses_tn_gemm_path_and_equals_steps(ops):
+    """Batches the row kernel cannot cover in one pass (more than 296 CTAs of 8 rows: B > 2,368) keep the K-sliced TN GEMM for S^T on
+    the W2 branch; smaller ones take the per-CTA shares + ordered share sum (rows_train.cuh / k_sum_spart_g).  Both must agree with
+    the stepwise API (unfused tail): one epoch of 2,560 + 2,560 + 81 rows, and the same rows at batch 640."""
+    n = 2 * 2560 + 81
+    rng, x, g, T2, _ = _data(n, seed=77)
+    y = (g // 2).astype(np.int64)
+    X, yd, gd = dev(x), dev(y, torch.int32), dev(g, torch.int32)
+    That = ops.normalize_text(dev(T2))
+    order = torch.randperm(n, generator=torch.Generator().manual_seed(5)).to(torch.int32).cuda()
+    from dbmm.modules import Adapter
+    for bs in (2560, 640):
+        steps = (n + bs - 1) // bs
+        torch.manual_seed(3)
+        a1 = Adapter(D, H).cuda().tensors()
+        torch.manual_seed(3)
+        a2 = Adapter(D, H).cuda().tensors()
+        b1, b2 = ops.TrainBuffers(D, H), ops.TrainBuffers(D, H)
+        s1, s2 = ops.BatchStatsBuffers(steps, 4), ops.BatchStatsBuffers(steps, 4)
+        lrs = [0.05] * steps
+        ops.train_epoch(X, order, bs, yd, gd, a1, That, 100.0, b1, lrs, s1)
+        for s in range(steps):
+            idx = order[s * bs:(s + 1) * bs].contiguous()
+            ops.train_step(X, yd, gd, a2, That, 100.0, b2, lrs[s], s2, slot=s, idx=idx)
+        for k in ("W1", "b1", "gamma", "beta", "W2", "b2", "running_mean", "running_var"):
+            assert rel_err(a1.to_numpy()[k], a2.to_numpy()[k]) < 2e-5, (bs, k)
+        assert np.array_equal(s1.host()[1], s2.host()[1])
+        np.testing.assert_allclose(s1.host()[0], s2.host()[0], rtol=1e-5)
+
+
 def test_eval_forward_full_waves_matches_oracle(ops):
     """148 * 128 + 77 rows: whole waves of 128-row tiles plus a ragged tail, both adapters."""
     n = 148 * 128 + 77
