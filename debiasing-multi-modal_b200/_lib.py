@@ -124,6 +124,7 @@ SIGNATURES = {
     "dbmm_head_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "dbmm_logits_ce": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _f32, _i32, _i64, BatchStats, _vp,
                                  _vp, _sz, _vp]),
+    "dbmm_timeline_dump": (C.c_int, [_vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dbmm_head_f16_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "dbmm_logits_ce_f16": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _f32, _i32, _i64, BatchStats, _vp,
                                      _vp, _sz, _vp]),

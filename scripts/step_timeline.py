@@ -41,7 +41,6 @@ if world > 1:
     if rank != 0:
         dist.destroy_process_group(); sys.exit(0)
 lib = _lib.load()
-lib.dbmm_timeline_dump.restype = C.c_int
 ring, kern = C.c_int(0), C.c_int(0)
 out = np.zeros((1024, 8, 3), np.uint64); cnt = np.zeros(8, np.uint32)
 rc = lib.dbmm_timeline_dump(out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), C.byref(ring), C.byref(kern))
