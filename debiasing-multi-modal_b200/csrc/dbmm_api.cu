@@ -651,9 +651,12 @@ static int train_step_impl(int phases, bool fresh,
         const bool tc_w2 = use_tc_w2(H, C) && !(dp_p2p && tc_rows);      // (data parallel: the row kernel is the CUDA-core one)
         if (tc_rows) { if (int rc = launch_sum_spart(w.Spart, B, H, C, S_cur, tc_w2 ? w.ST : nullptr, s_, first_pdl)) return rc; }
         else if (tc_w2) {
-            if (fuse_st) { if (int rc = launch_sum_spart_g(w.Spart, ceil_div(B, RT_ROWS), H, C, w.ST, s_)) return rc; }
-            else if (int rc = launch_st_gemm(w.Lrows, w.Hrows, w.ST, B, H, C, s_, &tsp)) return rc;
-            if (dp_p2p) if (int rc = launch_p2p_sum_st(w.ST, H, *p2p, s_)) return rc;       // S^T summed over the ranks, in place
+            if (fuse_st) {         // (data parallel: the ranks' sums are exchanged inside the kernel, one LL word per element)
+                if (int rc = launch_sum_spart_g(w.Spart, ceil_div(B, RT_ROWS), H, C, w.ST, s_, dp_p2p ? p2p : nullptr)) return rc;
+            } else {
+                if (int rc = launch_st_gemm(w.Lrows, w.Hrows, w.ST, B, H, C, s_, &tsp)) return rc;
+                if (dp_p2p) if (int rc = launch_p2p_sum_st(w.ST, H, *p2p, s_)) return rc;       // S^T summed over the ranks, in place
+            }
         }
         else if (int rc = launch_s_gemm(w.Lrows, w.Hrows, S_cur, B, H, C, s_, &tsp)) return rc;
         if (tc_w2) {

@@ -16,6 +16,7 @@
 // 129 x 131 contraction (8 rows per CTA, 128 CTAs) and 2.2 M fp32 atomics; here a step is 16 CTAs, and 64 sweep members
 // fill the machine (batched.cuh).  k_sum_spart adds the tiles in tile order (deterministic) into S = L^T [h | 1].
 #pragma once
+#include "p2p.cuh"
 #include "kernels_simt.cuh"
 #include "ptx_sm100.cuh"
 
@@ -560,7 +561,11 @@ __global__ void __launch_bounds__(256) k_sum_spart(SumSpartArgs a) { sum_spart_b
 // (all loads of a pass in flight together, added in order), the four group sums are combined in group order -- a fixed order,
 // so the result does not depend on timing.
 constexpr int SG_ELEMS = 64, SG_GROUPS = 4, SG_MAXT = 296, SG_PER = (SG_MAXT + SG_GROUPS - 1) / SG_GROUPS;
-struct SumSpartGArgs { const float* Spart; int tiles, H, C; float* ST; };
+// Data parallel (P2P): the element sum of this rank goes to every other rank as ONE LL word (value + instance tag in an 8-byte
+// store, p2p.cuh) and the ranks' values are added in rank order, so every rank holds the same bits; this replaces the separate
+// S^T exchange kernel (k_p2p_sum_st: slices + system fence + flags, 12 us of the 2-GPU step, profiles/r3_step_timeline.md).
+struct SumSpartGArgs { const float* Spart; int tiles, H, C; float* ST; P2pArgs p2p; };
+template <bool P2P>
 __global__ void __launch_bounds__(SG_ELEMS * SG_GROUPS) k_sum_spart_g(SumSpartGArgs a) {
     __shared__ float sg[SG_GROUPS][SG_ELEMS];
     const int H = a.H, ldl = H + 1 + a.C;
@@ -585,12 +590,35 @@ __global__ void __launch_bounds__(SG_ELEMS * SG_GROUPS) k_sum_spart_g(SumSpartGA
     }
     sg[grp][el] = v;
     __syncthreads();
-    if (grp == 0 && j <= H) a.ST[(size_t)j * HR_SP_LD + l] = live ? ((sg[0][el] + sg[1][el]) + sg[2][el]) + sg[3][el] : 0.f;
+    if (grp == 0 && j <= H) {
+        float tot = live ? ((sg[0][el] + sg[1][el]) + sg[2][el]) + sg[3][el] : 0.f;
+        if constexpr (P2P) {
+            if (live) {
+                const unsigned inst = p2p_instance(a.p2p);
+                const int parity = inst & 1u;
+                char* me = a.p2p.peer[a.p2p.rank];
+                for (int r = 0; r < a.p2p.world; ++r)
+                    if (r != a.p2p.rank) p2p_f_store(p2p_st_ll(a.p2p.peer[r], parity, a.p2p.rank), e, tot, inst + 1u);
+                float sum = 0.f;
+                for (int r = 0; r < a.p2p.world; ++r)
+                    sum += r == a.p2p.rank ? tot : p2p_f_load(a.p2p, p2p_st_ll(me, parity, r), e, inst + 1u);
+                tot = sum;
+            }
+        }
+        a.ST[(size_t)j * HR_SP_LD + l] = tot;
+    }
 }
-static int launch_sum_spart_g(const float* Spart, int tiles, int H, int C, float* ST, cudaStream_t st) {
+static int launch_sum_spart_g(const float* Spart, int tiles, int H, int C, float* ST, cudaStream_t st, const P2pArgs* p2p = nullptr) {
     DBMM_CHECK_ARG(tiles >= 1 && tiles <= SG_MAXT, "k_sum_spart_g: %d shares", tiles);
-    SumSpartGArgs s; s.Spart = Spart; s.tiles = tiles; s.H = H; s.C = C; s.ST = ST;
-    DBMM_CUDA(launch_pdl(k_sum_spart_g, dim3(ceil_div((H + 1) * HR_SP_LD, SG_ELEMS)), dim3(SG_ELEMS * SG_GROUPS), 0, st, s));
+    SumSpartGArgs s;
+    memset(&s, 0, sizeof(s));
+    s.Spart = Spart; s.tiles = tiles; s.H = H; s.C = C; s.ST = ST;
+    const dim3 grid(ceil_div((H + 1) * HR_SP_LD, SG_ELEMS)), block(SG_ELEMS * SG_GROUPS);
+    if (p2p && p2p->world > 1) {
+        DBMM_CHECK_ARG((size_t)(H + 1) * HR_SP_LD <= P2P_ST_FLOATS, "S^T exceeds the peer-memory slot");
+        s.p2p = *p2p;
+        DBMM_CUDA(launch_pdl(k_sum_spart_g<true>, grid, block, 0, st, s));
+    } else DBMM_CUDA(launch_pdl(k_sum_spart_g<false>, grid, block, 0, st, s));
     return DBMM_OK;
 }
 

@@ -8,7 +8,8 @@
 //              1 / world of the quads; every thread pushes its chunk-summed quad to the owner only, the owner's thread sums the
 //              ranks in rank order, does the SGD step and pushes the UPDATED weights to every rank (2 x (N-1)/N x |W1| per rank
 //              instead of (N-1) x |W1|; momentum lives on the owner).  No cross-CTA synchronisation at all
-//   S          [H+1+C][H+1] fp32                        k_tail_w2 / k_p2p_sum_st: CTA c stores slice c to every rank and raises flag
+//   S^T        [H+1][144] fp32                          k_sum_spart_g: every element travels as ONE LL word to every rank, summed in rank order
+//   S          [H+1+C][H+1] fp32                        k_tail_w2 / k_p2p_sum_st (TN-GEMM path): CTA c stores slice c to every rank and raises flag
 //              [c][rank] (release, system scope); the consumer waits for the slices it needs (off the critical path)
 //
 // Channels 0 / 1 and dW1 travel as "LL" words: every 32 data bits ride in an 8-byte store together with the instance tag;
@@ -37,7 +38,9 @@ constexpr size_t P2P_G_OFF = P2P_S_OFF + sizeof(float) * 2 * P2P_MAX_WORLD * P2P
 constexpr size_t P2P_SF_OFF = P2P_G_OFF + 8 * (size_t)2 * P2P_MAX_WORLD * P2P_G_FLOATS;             // S flags
 constexpr size_t P2P_LL_OFF = P2P_SF_OFF + (size_t)P2P_S_CTAS * 128;                               // fp64 LL slots [channel][parity][rank][P2P_VEC] x 16 B
 constexpr size_t P2P_W_OFF = P2P_LL_OFF + (size_t)P2P_CHANNELS * 2 * P2P_MAX_WORLD * P2P_VEC * 16;   // updated-W1 LL slots [parity][P2P_G_FLOATS] x 8 B
-constexpr size_t P2P_BYTES = P2P_W_OFF + 8 * (size_t)2 * P2P_G_FLOATS;
+constexpr size_t P2P_ST_FLOATS = 20480;                                                            // >= (H + 1) * 144 elements of S^T
+constexpr size_t P2P_ST_OFF = P2P_W_OFF + 8 * (size_t)2 * P2P_G_FLOATS;                            // S^T LL slots [parity][rank][P2P_ST_FLOATS] x 8 B
+constexpr size_t P2P_BYTES = P2P_ST_OFF + 8 * (size_t)2 * P2P_MAX_WORLD * P2P_ST_FLOATS;
 
 struct P2pArgs {
     unsigned long long timeout_ns;   // wall-clock bound of every wait
@@ -165,6 +168,22 @@ __device__ __forceinline__ float4 p2p_g_load(const P2pArgs& p, const unsigned lo
 // the owner's updated W1 quads (all-gather half of the dW1 exchange): one slot per parity, written by the owner of each quad
 __device__ __forceinline__ unsigned long long* p2p_w_ll(char* buf, int parity) {
     return reinterpret_cast<unsigned long long*>(buf + P2P_W_OFF) + (size_t)parity * P2P_G_FLOATS;
+}
+// ---- single floats as LL words (S^T elements, exchanged inside k_sum_spart_g: one NVLink write latency, no fence, no flag kernel)
+__device__ __forceinline__ unsigned long long* p2p_st_ll(char* buf, int parity, int src) {
+    return reinterpret_cast<unsigned long long*>(buf + P2P_ST_OFF) + ((size_t)parity * P2P_MAX_WORLD + src) * P2P_ST_FLOATS;
+}
+__device__ __forceinline__ void p2p_f_store(unsigned long long* slot, int e, float v, unsigned tag) {
+    const unsigned long long w = (unsigned long long)__float_as_uint(v) | ((unsigned long long)tag << 32);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot + e), "l"(w) : "memory");
+}
+__device__ __forceinline__ float p2p_f_load(const P2pArgs& p, const unsigned long long* slot, int e, unsigned tag) {
+    unsigned long long w = 0, t0 = 0;
+    for (unsigned spin = 0;; ++spin) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(slot + e) : "memory");
+        if ((unsigned)(w >> 32) == tag || (p.skip & 8) || p2p_expired(p, t0, spin)) break;
+    }
+    return __uint_as_float((unsigned)w);
 }
 __device__ __forceinline__ float* p2p_s_slot(char* buf, int parity, int src) {
     return reinterpret_cast<float*>(buf + P2P_S_OFF) + ((size_t)parity * P2P_MAX_WORLD + src) * P2P_S_FLOATS;
