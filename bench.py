@@ -474,7 +474,9 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": workload_config(world), "clocks": clocks, "numa_binding": numa,
                "us_per_sgd_step": 1e3 * ms_per_step / steps_per_epoch, "final_epoch_mean_loss": final_loss,
-               "gpu_launches": args.steps * (steps_per_epoch * (8 if world == 1 else 6) + 3)}
+               # per SGD step: k_gemm1_tc, k_reduce_stats, k_rows_train, k_wgrad_tc, k_tail_w1 + (second graph branch) k_sum_spart_g, k_hs_w2,
+               # k_sum_gpart -- the same eight on one GPU and under data parallelism (the exchanges ride inside them); + 3 per epoch prologue
+               "gpu_launches": args.steps * (steps_per_epoch * 8 + 3)}
 
     # ---- per-kernel timing inside the running step (CUDA events between the kernels, stream launches) -> roofline of the
     #      dominant kernel.  Algorithmic bytes / flops per launch: GEMM-1 and dW1 each stream the
