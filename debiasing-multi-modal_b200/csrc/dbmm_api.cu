@@ -354,7 +354,7 @@ int dbmm_abi_version(void) { return DBMM_ABI_VERSION; }
 const char* dbmm_last_error(void) { return g_err; }
 
 const char* dbmm_build_info(void) {
-    return "libdbmm: sm_100a, tcgen05/TMA H-space adapter kernels (round 1), built " __DATE__ " " __TIME__;
+    return "libdbmm: sm_100a, tcgen05/TMA H-space adapter kernels (round 2: deterministic step, fp16-pair GEMMs), built " __DATE__ " " __TIME__;
 }
 
 size_t dbmm_workspace_bytes(int op, int64_t rows, int D, int H, int C, int n_adapters) {
