@@ -573,7 +573,9 @@ __global__ void __launch_bounds__(SG_ELEMS * SG_GROUPS) k_sum_spart_g(SumSpartGA
     const int e = blockIdx.x * SG_ELEMS + el;                    // e = j * HR_SP_LD + l over the PADDED row: padding written as zeros
     const int j = e / HR_SP_LD, l = e - j * HR_SP_LD;
     const bool live = j <= H && l < ldl;
+    DBMM_TL_SCOPE(TL_TN);           // (timeline builds: the slot of the TN GEMM this kernel replaced)
     ptx::pdl_wait();
+    DBMM_TL_WAIT(TL_TN);
     ptx::pdl_launch();
     const int per = (a.tiles + SG_GROUPS - 1) / SG_GROUPS, t0 = grp * per, t1 = min(a.tiles, t0 + per);
     const size_t ts = (size_t)(H + 1) * HR_SP_LD;

@@ -345,9 +345,7 @@ __global__ void __launch_bounds__(256) k_sum_gpart(SumGpartArgs a) { DBMM_TL_SCO
 // every rank ends with the same bits.  Off the critical path (W2 branch).
 constexpr int PS_CTAS = 16, PS_THREADS = 256;
 __global__ void __launch_bounds__(PS_THREADS) k_p2p_sum_st(float* ST, int n4, P2pArgs p) {
-    DBMM_TL_SCOPE(TL_TN);           // (timeline builds: the slot of the TN GEMM this branch no longer runs)
-    ptx::pdl_wait();                // S^T comes from the kernel in front of this one (share sum / TN GEMM)
-    DBMM_TL_WAIT(TL_TN);
+    ptx::pdl_wait();                // S^T comes from the kernel in front of this one (TN GEMM)
     ptx::pdl_launch();
     const unsigned inst = p2p_instance(p);
     const int parity = inst & 1u, c = blockIdx.x, tid = threadIdx.x;

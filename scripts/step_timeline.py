@@ -45,7 +45,7 @@ ring, kern = C.c_int(0), C.c_int(0)
 out = np.zeros((1024, 8, 3), np.uint64); cnt = np.zeros(8, np.uint32)
 rc = lib.dbmm_timeline_dump(out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), C.byref(ring), C.byref(kern))
 assert rc == 0, lib.dbmm_last_error().decode()
-names = ["gemm1", "reduce", "rows", "wgrad", "tail_w1", "tn_gemm(S^T) / p2p_sum_st", "hs_w2", "sum_gpart"]
+names = ["gemm1", "reduce", "rows", "wgrad", "tail_w1", "sum_spart_g (S^T)", "hs_w2", "sum_gpart"]
 print("launch counts:", dict(zip(names, cnt.tolist())))
 
 
