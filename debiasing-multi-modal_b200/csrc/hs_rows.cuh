@@ -564,6 +564,9 @@ constexpr int SG_ELEMS = 64, SG_GROUPS = 4, SG_MAXT = 296, SG_PER = (SG_MAXT + S
 // Data parallel (P2P): the element sum of this rank goes to every other rank as ONE LL word (value + instance tag in an 8-byte
 // store, p2p.cuh) and the ranks' values are added in rank order, so every rank holds the same bits; this replaces the separate
 // S^T exchange kernel (k_p2p_sum_st: slices + system fence + flags, 12 us of the 2-GPU step, profiles/r3_step_timeline.md).
+// A thread pushes before it polls and a push depends on nothing, so a CTA only ever waits for peer CTAs that will be scheduled
+// without its help: the 291 CTAs of 256 threads are far below the resident capacity of the GPU (148 SMs x 8), i.e. the pollers
+// can never hold every slot of a rank; the wait is bounded by wall clock like every other peer-memory wait (p2p_expired).
 struct SumSpartGArgs { const float* Spart; int tiles, H, C; float* ST; P2pArgs p2p; };
 template <bool P2P>
 __global__ void __launch_bounds__(SG_ELEMS * SG_GROUPS) k_sum_spart_g(SumSpartGArgs a) {
