@@ -1458,7 +1458,7 @@ int dbmm_logits_ce(const float* U, int64_t ldu, const int32_t* idx, const int32_
 
 // fp16-resident zero-shot head (head_f16.cuh): same results as dbmm_logits_ce, kind::f16 MMAs on the rows as stored
 namespace dbmm {
-struct HeadF16Ws { __half* thi; __half* tlo; float* inv_norm; SoftmaxPart* part; float* bscale; int64_t chunk; int ntile; size_t total; };
+struct HeadF16Ws { __half* thi; __half* tlo; float* inv_norm; SoftmaxPart* part; float* bscale; int* nflag; int64_t chunk; int ntile; size_t total; };
 static HeadF16Ws carve_head_f16_ws(void* base, int64_t N, int D, int C) {
     HeadF16Ws w; char* p = (char*)base; size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -1469,7 +1469,9 @@ static HeadF16Ws carve_head_f16_ws(void* base, int64_t N, int D, int C) {
     const size_t o_thi = take(sizeof(__half) * (size_t)C * D), o_tlo = take(sizeof(__half) * (size_t)C * D);
     const size_t o_in = take(sizeof(float) * (size_t)chunk), o_part = take(sizeof(SoftmaxPart) * (size_t)chunk * w.ntile);
     const size_t o_sc = take(256);              // [0]: max |That| bits, [1]: 2^k, [2]: 2^-k
+    const size_t o_nf = take(sizeof(int) * (size_t)ceil_div(chunk, 256));      // row-norm flags of the wide kernel, one per 256-row tile
     w.total = off;
+    w.nflag = (int*)(p + o_nf);
     w.thi = (__half*)(p + o_thi); w.tlo = (__half*)(p + o_tlo); w.inv_norm = (float*)(p + o_in); w.part = (SoftmaxPart*)(p + o_part);
     w.bscale = (float*)(p + o_sc);
     return w;
@@ -1507,14 +1509,20 @@ int dbmm_logits_ce_f16(const void* U16, int64_t ldu, const int32_t* y, const int
     for (int64_t pos0 = 0; pos0 < N; pos0 += w.chunk) {
         const int64_t n = (N - pos0) < w.chunk ? (N - pos0) : w.chunk;
         const __half* A = U + pos0 * ldu;
-        if (normalize_rows) {
+        // row norms: inside the wide kernel (two extra warps square-sum the x tiles of the column-tile-0 passes out of the TMA
+        // stages); a separate pass over the matrix for the 128-row kernel (DBMM_HEAD=pair) or with DBMM_HEAD_NORM=pass
+        static const bool norm_pass = getenv("DBMM_HEAD_NORM") && strcmp(getenv("DBMM_HEAD_NORM"), "pass") == 0;
+        const bool fused_norm = normalize_rows && wide && !norm_pass;
+        if (normalize_rows && !fused_norm) {
             k_row_inv_norm_f16<<<148 * 8, 256, 0, st>>>(A, ldu, n, D, w.inv_norm);
             DBMM_LAUNCH_CHECK();
         }
+        if (fused_norm) DBMM_CUDA(cudaMemsetAsync(w.nflag, 0, sizeof(int) * (size_t)ceil_div(n, 256), st));
         HeadF16Args g;
         memset(&g, 0, sizeof(g));
         g.M = n; g.N = C; g.K = D; g.scale = inv_tau; g.rowscale = normalize_rows ? w.inv_norm : nullptr; g.col_bias = col_bias;
         g.y = y; g.pos0 = pos0; g.part = w.part; g.n_ntiles = w.ntile; g.bscale_inv = w.bscale + 2;
+        if (fused_norm) { g.norm_out = w.inv_norm; g.norm_flag = w.nflag; }
         if (int rc = launch_f16_head(A, ldu, w.thi, w.tlo, D, g, wide, st)) return rc;
         k_head_finish<<<ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8, 256, 0, st>>>(
             w.part, w.ntile, n, pos0, nullptr, grp, G, batch_size, stats.loss_sum, stats.counts, pred_out, y);

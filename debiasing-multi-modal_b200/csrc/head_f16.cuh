@@ -30,6 +30,10 @@ struct HeadF16Args {
     const int32_t* y; int64_t pos0;           // target column of row pos0 + m (or null)
     SoftmaxPart* part; int n_ntiles;          // [M][n_ntiles]
     const float* bscale_inv;                  // wide kernel: 2^-k of the prompt scaling (device scalar)
+    // wide kernel, fused row norms (norm_out != nullptr): two extra warps square-sum the x tiles of every column-tile-0 pass out of
+    // the TMA stages (no second pass over the matrix), write 1 / |x_m| to norm_out and raise norm_flag[row tile]; the epilogues of
+    // the row tile's column tiles (other CTAs, the same round of the tile walk) wait for that flag.  rowscale is then ignored.
+    float* norm_out; int* norm_flag;          // [M]; [ceil(M / 256)], zero before the launch
 };
 
 __global__ void __launch_bounds__(HF_THREADS, 1)
@@ -176,9 +180,10 @@ k_f16_head(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 // mixed a / b formats: illegal instruction.)  A stage then holds two x blocks and the (Th, Tl) pair (64 KB): the prompt
 // tiles, which every CTA streams from L2, are read once per 256 rows instead of once per 128 -- the 128-row kernel above is
 // L2 -> SM bandwidth bound (48 KB per 8 MMAs = 174 GB/s per SM at full tensor rate; this one needs 116).  Two accumulator
-// blocks x double buffering = 512 TMEM columns; 8 epilogue warps (TMEM lane quarter = warp % 4, row block = (warp - 2) / 4).
+// blocks x double buffering = 512 TMEM columns; 8 epilogue warps (TMEM lane quarter = warp % 4, row block = (warp - 2) / 4);
+// two more warps compute the row norms out of the TMA stages (HeadF16Args::norm_out).
 // ------------------------------------------------------------------------------------------------
-constexpr int HWD_THREADS = 320, HWD_BM = 256, HWD_STAGES = 3;
+constexpr int HWD_THREADS = 384, HWD_BM = 256, HWD_STAGES = 3;          // TMA, MMA, 8 epilogue warps, 2 row-norm warps
 constexpr int HWD_STAGE_BYTES = 4 * EF_TILE_BYTES;                       // x block 0, x block 1, Th, Tl
 constexpr size_t HWD_SMEM = (size_t)HWD_STAGES * HWD_STAGE_BYTES + 1024 + 256;
 
@@ -200,7 +205,7 @@ k_f16_head_wide(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int KB = (a.K + HF_BK - 1) / HF_BK;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < S; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 3); }      // MMA commit + the two norm warps
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 256); }
         ptx::fence_mbar_init();
         ptx::tma_prefetch_desc(&mapA); ptx::tma_prefetch_desc(&mapBhi); ptx::tma_prefetch_desc(&mapBlo);
@@ -267,6 +272,50 @@ k_f16_head_wide(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
         __syncwarp();
+    } else if (warp >= 10) {
+        // ===================== row norms: warps 10, 11 (64 threads, 4 rows each: 2 per 128-row block) =====================
+        const int t = tid - 320;
+        uint32_t g = 0;
+        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = (int)(tile % n_ntiles);
+            const int64_t mt = tile / n_ntiles, m0 = mt * HWD_BM;
+            const bool work = a.norm_out != nullptr && nt == 0;
+            float ss[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const int s = g % S;
+                ptx::mbar_wait(&full[s], (g / S) & 1);
+                if (work) {
+                    const uint8_t* st = smem + (size_t)s * HWD_STAGE_BYTES;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = (rr & 1) * 64 + t;                                   // row of the 128-row block rr / 2
+                        const uint8_t* rp = st + (rr >> 1) * EF_TILE_BYTES + row * 128;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {                                        // the 8 chunks of the row, rotated by the lane: no bank conflicts
+                            const uint4 v = *reinterpret_cast<const uint4*>(rp + (((c + t) & 7) << 4));
+                            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+                                ss[rr] = fmaf(f.x, f.x, ss[rr]); ss[rr] = fmaf(f.y, f.y, ss[rr]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty[s]);
+            }
+            if (work) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int64_t m = m0 + (rr >> 1) * 128 + (rr & 1) * 64 + t;
+                    if (m < a.M && !((rr >> 1) == 1 && m0 + 128 >= a.M)) a.norm_out[m] = 1.0f / sqrtf(ss[rr]);
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(a.norm_flag + mt, 1);
+            }
+        }
     } else {
         const int q = warp & 3, blk = (warp - 2) >> 2;
         uint32_t it = 0;
@@ -279,11 +328,17 @@ k_f16_head_wide(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             float scale = a.scale * __ldg(a.bscale_inv);
             int yv = -1;
             if (row_ok) {
-                if (a.rowscale) scale *= __ldg(a.rowscale + m);
+                if (a.rowscale && !a.norm_out) scale *= __ldg(a.rowscale + m);
                 if (a.y) yv = a.y[a.pos0 + m];
             }
             ptx::mbar_wait(&tmem_full[as], (it >> 1) & 1);
             ptx::tc_fence_after_sync();
+            if (a.norm_out) {              // the row tile's norms come from the CTA that walks its column tile 0 (this round or earlier)
+                const int* fl = a.norm_flag + tile / n_ntiles;
+                int v;
+                do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory"); } while (v < 2);
+                if (row_ok) scale *= __ldcg(a.norm_out + m);
+            }
             float mx = -INFINITY, se = 0.f, ly = -INFINITY; int am = 0;
 #pragma unroll 1
             for (int ch = 0; ch < HF_BN / 32; ++ch) {
