@@ -28,7 +28,7 @@ struct HeadF16Args {
     const float* rowscale;                    // optional [M]: 1 / |x_m|
     const float* col_bias;                    // optional [N]
     const int32_t* y; int64_t pos0;           // target column of row pos0 + m (or null)
-    SoftmaxPart* part; int n_ntiles;          // [M][n_ntiles]
+    SoftmaxPart* part; int n_ntiles;          // [n_ntiles][M]
     const float* bscale_inv;                  // wide kernel: 2^-k of the prompt scaling (device scalar)
     // wide kernel, fused row norms (norm_out != nullptr): two extra warps square-sum the x tiles of every column-tile-0 pass out of
     // the TMA stages (no second pass over the matrix), write 1 / |x_m| to norm_out and raise norm_flag[row tile]; the epilogues of
@@ -163,7 +163,7 @@ k_f16_head(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
             ptx::mbar_arrive(&tmem_empty[as]);                        // 128 epilogue threads: accumulator pair reusable
             if (row_ok) {
                 SoftmaxPart p; p.mx = mx; p.se = se; p.ly = ly; p.am = am;
-                a.part[(size_t)m * n_ntiles + nt] = p;
+                a.part[(size_t)nt * a.M + m] = p;                  // [column tile][row]: coalesced here and in k_head_finish
             }
         }
     }
@@ -365,7 +365,7 @@ k_f16_head_wide(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             ptx::mbar_arrive(&tmem_empty[as]);                        // 256 epilogue threads
             if (row_ok) {
                 SoftmaxPart p; p.mx = mx; p.se = se; p.ly = ly; p.am = am;
-                a.part[(size_t)m * n_ntiles + nt] = p;
+                a.part[(size_t)nt * a.M + m] = p;                  // [column tile][row]: coalesced here and in k_head_finish
             }
         }
     }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) k_head_finish(const SoftmaxPart* __restri
         if (valid) {
             float mx = -INFINITY, se = 0.f, ly = -INFINITY; int am = 0;
             for (int t = 0; t < ntile; ++t) {
-                const SoftmaxPart p = part[(size_t)r * ntile + t];
+                const SoftmaxPart p = part[(size_t)t * n + r];                 // [column tile][row of this launch]
                 if (p.mx > mx) { se = se * expf(mx - p.mx) + p.se; mx = p.mx; am = p.am; }
                 else se += p.se * expf(p.mx - mx);
                 ly = fmaxf(ly, p.ly);

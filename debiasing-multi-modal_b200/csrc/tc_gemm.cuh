@@ -35,7 +35,7 @@ struct TcGemmArgs {
     float* C; int64_t ldc; int accumulate;                  // EPI_STORE: C = [C +] scaled tile
     const int32_t* y; const int32_t* idx;                   // EPI_SOFTMAX_PART: target column per DATASET row, row list (or null)
     int64_t pos0;
-    SoftmaxPart* part;                                      // [M][number of column tiles]
+    SoftmaxPart* part;                                      // [number of column tiles][M]
     // EPI_HSPACE (eval forward, t = [h, 1] G with G^T as the B operand): column tile 0 reduces t[0:128] to
     // rowdot[m] = sum_j t_j h_j (h = Ahi + Alo, re-read from global), further tiles store t[128 + j] to tail[m][j]
     const float* hs_hi; const float* hs_lo; int64_t hs_ld; const float* hs_bias; float* rowdot; float* tail; int tail_ld;
@@ -298,7 +298,7 @@ k_tc_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             }
             if (row_ok) {
                 SoftmaxPart p; p.mx = mx; p.se = se; p.ly = ly; p.am = am;
-                a.part[(size_t)m * n_ntiles + nt] = p;
+                a.part[(size_t)nt * a.M + m] = p;                      // [column tile][row]: coalesced here and in k_head_finish
             }
         }
         ptx::tc_fence_before_sync();
