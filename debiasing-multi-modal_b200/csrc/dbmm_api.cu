@@ -1522,7 +1522,7 @@ int dbmm_logits_ce_f16(const void* U16, int64_t ldu, const int32_t* y, const int
         memset(&g, 0, sizeof(g));
         g.M = n; g.N = C; g.K = D; g.scale = inv_tau; g.rowscale = normalize_rows ? w.inv_norm : nullptr; g.col_bias = col_bias;
         g.y = y; g.pos0 = pos0; g.part = w.part; g.n_ntiles = w.ntile; g.bscale_inv = w.bscale + 2;
-        if (fused_norm) { g.norm_out = w.inv_norm; g.norm_flag = w.nflag; }
+        if (fused_norm) { g.norm_out = w.inv_norm; g.norm_flag = w.nflag; g.X = A; g.ldx = ldu; }
         if (int rc = launch_f16_head(A, ldu, w.thi, w.tlo, D, g, wide, st)) return rc;
         k_head_finish<<<ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8, 256, 0, st>>>(
             w.part, w.ntile, n, pos0, nullptr, grp, G, batch_size, stats.loss_sum, stats.counts, pred_out, y);

@@ -34,6 +34,9 @@ struct HeadF16Args {
     // the TMA stages (no second pass over the matrix), write 1 / |x_m| to norm_out and raise norm_flag[row tile]; the epilogues of
     // the row tile's column tiles (other CTAs, the same round of the tile walk) wait for that flag.  rowscale is then ignored.
     float* norm_out; int* norm_flag;          // [M]; [ceil(M / 256)], zero before the launch
+    const __half* X; int64_t ldx;             // the rows again: an epilogue thread whose flag does not arrive within 200 us (the CTA that
+                                              // walks the row tile's first column tile is not resident: GPU shared with other work)
+                                              // computes the norm of its own row from global memory instead of waiting any longer
 };
 
 __global__ void __launch_bounds__(HF_THREADS, 1)
@@ -335,9 +338,36 @@ k_f16_head_wide(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             ptx::tc_fence_after_sync();
             if (a.norm_out) {              // the row tile's norms come from the CTA that walks its column tile 0 (this round or earlier)
                 const int* fl = a.norm_flag + tile / n_ntiles;
-                int v;
-                do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory"); } while (v < 2);
-                if (row_ok) scale *= __ldcg(a.norm_out + m);
+                bool ready = false;
+                unsigned long long t0 = 0;
+                for (unsigned spin = 0;; ++spin) {
+                    int v;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+                    if (v >= 2) { ready = true; break; }
+                    if ((spin & 63u) == 63u) {                            // bounded by wall clock: never a hang, whatever the CTA scheduling
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 200000ull) break;
+                    }
+                }
+                if (row_ok) {
+                    if (ready) scale *= __ldcg(a.norm_out + m);
+                    else {
+                        const uint4* xp = reinterpret_cast<const uint4*>(a.X + m * a.ldx);
+                        float ssq = 0.f;
+                        for (int c = 0; c < a.K / 8; ++c) {
+                            const uint4 v4 = __ldg(xp + c);
+                            const uint32_t w4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+                                ssq = fmaf(f.x, f.x, ssq); ssq = fmaf(f.y, f.y, ssq);
+                            }
+                        }
+                        scale *= 1.0f / sqrtf(ssq);
+                    }
+                }
             }
             float mx = -INFINITY, se = 0.f, ly = -INFINITY; int am = 0;
 #pragma unroll 1
